@@ -1,0 +1,1 @@
+"""empty stand-in (sonification is off the hot path)"""
