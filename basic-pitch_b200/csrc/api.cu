@@ -1,0 +1,738 @@
+// C ABI of the hot path (include/bp_b200.h): model lifetime, workspace, chunked launch sequences.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "bp_b200.h"
+#include "kernels.cuh"
+
+using namespace bp;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+
+#define CK(call)                                                                                         \
+  do {                                                                                                   \
+    cudaError_t e_ = (call);                                                                             \
+    if (e_ != cudaSuccess)                                                                               \
+      return fail(BP_E_CUDA, std::string(#call) + " failed: " + cudaGetErrorString(e_) + " (" __FILE__ ":" + \
+                                 std::to_string(__LINE__) + ")");                                        \
+  } while (0)
+
+#define CKL()                                                                                            \
+  do {                                                                                                   \
+    cudaError_t e_ = cudaGetLastError();                                                                 \
+    if (e_ != cudaSuccess)                                                                               \
+      return fail(BP_E_CUDA, std::string("kernel launch failed: ") + cudaGetErrorString(e_) + " (" __FILE__ ":" + \
+                                 std::to_string(__LINE__) + ")");                                        \
+  } while (0)
+
+// A device buffer that only ever grows.
+template <class T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t n) {
+    if (n <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = n + n / 8 + 256;
+    cudaError_t e = cudaMalloc(&p, want * sizeof(T));
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+struct UnwrapDesc {
+  long long dst_base;  // first output frame this window contributes to
+  int rows;            // how many of its 142 centre frames are kept (may be <= 0)
+  int pad;
+};
+
+// transposed / interleaved weight layouts derived from the parameter block
+struct DerivedLayout {
+  static constexpr int cqt_wt = 0;                           // [256][72] columns: re0,im0,re1,im1,...
+  static constexpr int contour1_wT = cqt_wt + 256 * 72;      // [936][8]
+  static constexpr int contour2_wT = contour1_wT + 936 * 8;  // [200][1]
+  static constexpr int note1_wT = contour2_wT + 200;         // [49][32]
+  static constexpr int note2_wT = note1_wT + 49 * 32;        // [672][1]
+  static constexpr int onset1_wT = note2_wT + 672;           // [200][32]
+  static constexpr int onset2_wT = onset1_wT + 200 * 32;     // [297][1] (+3)
+  static constexpr int total = onset2_wT + 300;
+};
+
+__global__ void derive_kernel(const float* __restrict__ P, float* __restrict__ D) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < 256 * 72) {
+    int k = i / 72, n = i % 72;
+    int bin = n >> 1;
+    D[DerivedLayout::cqt_wt + i] = (n & 1) ? P[ParamLayout::cqt_imag + bin * 256 + k] : P[ParamLayout::cqt_real + bin * 256 + k];
+  }
+  auto tr = [&](int src, int dst, int cout, int kk) {  // [cout][kk] -> [kk][cout]
+    if (i < cout * kk) {
+      int k = i / cout, c = i % cout;
+      D[dst + i] = P[src + c * kk + k];
+    }
+  };
+  tr(ParamLayout::contour1_w, DerivedLayout::contour1_wT, 8, 936);
+  tr(ParamLayout::contour2_w, DerivedLayout::contour2_wT, 1, 200);
+  tr(ParamLayout::note1_w, DerivedLayout::note1_wT, 32, 49);
+  tr(ParamLayout::note2_w, DerivedLayout::note2_wT, 1, 672);
+  tr(ParamLayout::onset1_w, DerivedLayout::onset1_wT, 32, 200);
+  tr(ParamLayout::onset2_w, DerivedLayout::onset2_wT, 1, 297);
+}
+
+// centre 142 frames of every window -> unwrapped position (reference: inference.py:247-279)
+__global__ void unwrap_kernel(const float* __restrict__ raw, float* __restrict__ out, const UnwrapDesc* __restrict__ ud,
+                              int width) {
+  const int w = blockIdx.y;
+  const UnwrapDesc d = ud[w];
+  const int n = d.rows * width;
+  const float* src = raw + ((size_t)w * kFrames + kOverlapHalf) * width;
+  float* dst = out + d.dst_base * width;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) dst[i] = src[i];
+}
+
+__global__ void compact_notes_kernel(const long long* __restrict__ frame_off, const long long* __restrict__ slot_off,
+                                     const int* __restrict__ note_off, const int* __restrict__ s_start,
+                                     const int* __restrict__ s_end, const int* __restrict__ s_pitch,
+                                     int* __restrict__ start, int* __restrict__ end, int* __restrict__ pitch,
+                                     long long* __restrict__ note_base) {
+  const int file = blockIdx.x;
+  const int n = note_off[file + 1] - note_off[file];
+  const long long s0 = slot_off[file];
+  const int d0 = note_off[file];
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    start[d0 + i] = s_start[s0 + i];
+    end[d0 + i] = s_end[s0 + i];
+    pitch[d0 + i] = s_pitch[s0 + i];
+    note_base[d0 + i] = frame_off[file];
+  }
+}
+
+}  // namespace
+
+struct bp_model {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  float* d_params = nullptr;
+  float* d_derived = nullptr;
+  double* d_gauss = nullptr;
+  CnnWeights cw{};
+  int chunk = 64;
+  int path = 0;
+  int64_t launches = 0;
+  // forward workspace (chunk windows)
+  DevBuf<float> chain, y, c1, n1, o1, raw_note, raw_onset, raw_contour;
+  DevBuf<unsigned int> minmax;
+  DevBuf<WinDesc> wdesc;
+  DevBuf<UnwrapDesc> udesc;
+  // staging for the host entry points
+  DevBuf<float> st_audio, st_note, st_onset, st_contour;
+  // decode workspace
+  DevBuf<long long> d_frame_off, d_slot_off, d_note_base;
+  DevBuf<float> energy, d_amp;
+  DevBuf<unsigned int> candbits, max_onset;
+  DevBuf<unsigned long long> max_fd;
+  DevBuf<int> note_count, slot_start, slot_end, slot_pitch, overflow, d_note_off, d_start, d_end, d_pitch, d_bend_off,
+      d_bends;
+  int64_t last_forward_n = 0;
+};
+
+namespace {
+
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    cudaGetDevice(&prev);
+    if (prev != dev) cudaSetDevice(dev);
+  }
+  ~DeviceGuard() {
+    int cur = -1;
+    cudaGetDevice(&cur);
+    if (prev >= 0 && cur != prev) cudaSetDevice(prev);
+  }
+};
+
+int parse_blob(const void* blob, size_t nbytes, std::vector<float>& params) {
+  const unsigned char* b = static_cast<const unsigned char*>(blob);
+  if (nbytes < 8 || std::memcmp(b, "BPW1", 4) != 0) return fail(BP_E_INVALID, "weight blob: bad magic (expected BPW1)");
+  uint32_t count;
+  std::memcpy(&count, b + 4, 4);
+  size_t pos = 8;
+  params.assign(ParamLayout::total, 0.f);
+  struct Slot {
+    const char* name;
+    int off;
+    int n;
+  };
+  const Slot slots[] = {
+      {"cqt_real", ParamLayout::cqt_real, 36 * 256},  {"cqt_imag", ParamLayout::cqt_imag, 36 * 256},
+      {"lowpass", ParamLayout::lowpass, 256},         {"cqt_scale", ParamLayout::cqt_scale, 309},
+      {"bn_scale", ParamLayout::bn, 1},               {"bn_bias", ParamLayout::bn + 1, 1},
+      {"contour1_w", ParamLayout::contour1_w, 7488},  {"contour1_b", ParamLayout::contour1_b, 8},
+      {"contour2_w", ParamLayout::contour2_w, 200},   {"contour2_b", ParamLayout::contour2_b, 1},
+      {"note1_w", ParamLayout::note1_w, 1568},        {"note1_b", ParamLayout::note1_b, 32},
+      {"note2_w", ParamLayout::note2_w, 672},         {"note2_b", ParamLayout::note2_b, 1},
+      {"onset1_w", ParamLayout::onset1_w, 6400},      {"onset1_b", ParamLayout::onset1_b, 32},
+      {"onset2_w", ParamLayout::onset2_w, 297},       {"onset2_b", ParamLayout::onset2_b, 1},
+  };
+  unsigned found = 0;
+  for (uint32_t t = 0; t < count; ++t) {
+    if (pos + 4 > nbytes) return fail(BP_E_INVALID, "weight blob: truncated");
+    uint32_t nl;
+    std::memcpy(&nl, b + pos, 4);
+    pos += 4;
+    if (nl > 64 || pos + nl > nbytes) return fail(BP_E_INVALID, "weight blob: bad tensor name");
+    std::string name(reinterpret_cast<const char*>(b + pos), nl);
+    pos += nl + ((4 - nl % 4) % 4);
+    if (pos + 4 > nbytes) return fail(BP_E_INVALID, "weight blob: truncated");
+    uint32_t nd;
+    std::memcpy(&nd, b + pos, 4);
+    pos += 4;
+    if (nd > 8 || pos + 4 * nd > nbytes) return fail(BP_E_INVALID, "weight blob: bad rank");
+    size_t n = 1;
+    for (uint32_t d = 0; d < nd; ++d) {
+      uint32_t v;
+      std::memcpy(&v, b + pos, 4);
+      pos += 4;
+      n *= v;
+    }
+    if (pos + 4 * n > nbytes) return fail(BP_E_INVALID, "weight blob: truncated tensor " + name);
+    for (size_t s = 0; s < sizeof(slots) / sizeof(slots[0]); ++s) {
+      if (name == slots[s].name) {
+        if ((int)n != slots[s].n) return fail(BP_E_INVALID, "weight blob: tensor " + name + " has wrong size");
+        std::memcpy(params.data() + slots[s].off, b + pos, 4 * n);
+        found |= 1u << s;
+      }
+    }
+    pos += 4 * n;
+  }
+  if (found != (1u << (sizeof(slots) / sizeof(slots[0]))) - 1) return fail(BP_E_INVALID, "weight blob: missing tensors");
+  return BP_OK;
+}
+
+int derive(bp_model* m, cudaStream_t st) {
+  derive_kernel<<<(256 * 72 + 255) / 256, 256, 0, st>>>(m->d_params, m->d_derived);
+  CKL();
+  upload_lowpass(m->d_params + ParamLayout::lowpass, st);
+  CKL();
+  m->launches += 1;
+  return BP_OK;
+}
+
+int ensure_forward_ws(bp_model* m, int nb) {
+  CK(m->chain.reserve((size_t)nb * kChainStride));
+  CK(m->y.reserve((size_t)nb * kFrames * kCqtBins));
+  CK(m->c1.reserve((size_t)nb * 8 * kFrames * kContourBins));
+  CK(m->n1.reserve((size_t)nb * 32 * kFrames * kPitches));
+  CK(m->o1.reserve((size_t)nb * 32 * kFrames * kPitches));
+  CK(m->minmax.reserve((size_t)nb * 2));
+  return BP_OK;
+}
+
+// HCQT + CNN for `nb` windows (nb <= chunk); outputs raw [nb][172][*].
+int forward_chunk(bp_model* m, const float* audio, const WinDesc* desc, int nb, float* note, float* onset,
+                  float* contour, cudaStream_t st) {
+  float* chain = m->chain.p;
+  for (int s = 0; s < 8; ++s) launch_decimate(audio, desc, chain, s, nb, st);
+  launch_cqt(audio, desc, chain, m->d_derived + DerivedLayout::cqt_wt, m->d_params + ParamLayout::cqt_scale, m->y.p,
+             m->minmax.p, nb, st);
+  launch_lognorm(m->y.p, m->minmax.p, m->d_params + ParamLayout::bn, nb, st);
+  launch_contour1(m->y.p, m->cw, m->c1.p, nb, st);
+  launch_contour2(m->c1.p, m->cw, contour, nb, st);
+  launch_note1(contour, m->cw, m->n1.p, nb, st);
+  launch_note2(m->n1.p, m->cw, note, nb, st);
+  launch_onset1(m->y.p, m->cw, m->o1.p, nb, st);
+  launch_onset2(note, m->o1.p, m->cw, onset, nb, st);
+  CKL();
+  m->launches += 8 + 2 + 1 + 6;
+  return BP_OK;
+}
+
+int validate_params(const bp_decode_params_t* p) {
+  if (!p) return fail(BP_E_INVALID, "decode params: null");
+  if (!(p->frame_thresh == p->frame_thresh) || !(p->onset_thresh == p->onset_thresh))
+    return fail(BP_E_INVALID, "decode params: NaN threshold");
+  if (p->melodia_trick && p->frame_thresh < 0)
+    return fail(BP_E_INVALID, "decode params: frame_thresh < 0 with melodia_trick never terminates (the reference loops forever)");
+  if (p->energy_tol < 1) return fail(BP_E_INVALID, "decode params: energy_tol must be >= 1");
+  if (p->min_note_len < 0) return fail(BP_E_INVALID, "decode params: min_note_len must be >= 0");
+  return BP_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int bp_version(void) { return 100; }
+const char* bp_last_error(void) { return g_err.c_str(); }
+
+void bp_default_decode_params(bp_decode_params_t* p) {
+  if (!p) return;
+  p->onset_thresh = 0.5;
+  p->frame_thresh = 0.3;
+  p->min_note_len = 11;
+  p->energy_tol = 11;
+  p->infer_onsets = 1;
+  p->melodia_trick = 1;
+  p->include_pitch_bends = 1;
+  p->min_pitch_idx = 0;
+  p->max_pitch_idx = BP_N_PITCHES;
+  p->reserved = 0;
+}
+
+int64_t bp_num_windows(int64_t n_samples) {
+  if (n_samples < 0) return 0;
+  return (n_samples + kLeadZeros + kHopSamples - 1) / kHopSamples;
+}
+int64_t bp_num_frames(int64_t n_samples) {
+  if (n_samples <= 0) return 0;
+  return (int64_t)((double)n_samples / (double)kHopSamples * (double)kHopFrames);
+}
+
+int bp_model_create(const void* blob, size_t nbytes, int device, bp_model_t** out) {
+  if (!blob || !out) return fail(BP_E_INVALID, "bp_model_create: null argument");
+  std::vector<float> params;
+  int rc = parse_blob(blob, nbytes, params);
+  if (rc) return rc;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(BP_E_CUDA, std::string("no CUDA device available (") + cudaGetErrorString(e) +
+                               "); this library has no CPU path");
+  if (device < 0 || device >= ndev) return fail(BP_E_INVALID, "bp_model_create: bad device index");
+  DeviceGuard g(device);
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return fail(BP_E_CUDA, std::string("device ") + prop.name + " is sm_" + std::to_string(prop.major) +
+                               std::to_string(prop.minor) + "; this library is built for sm_100a only");
+  bp_model* m = new bp_model();
+  m->device = device;
+  CK(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
+  CK(cudaMalloc(&m->d_params, sizeof(float) * ParamLayout::total));
+  CK(cudaMalloc(&m->d_derived, sizeof(float) * DerivedLayout::total));
+  CK(cudaMalloc(&m->d_gauss, sizeof(double) * 51));
+  CK(cudaMemcpy(m->d_params, params.data(), sizeof(float) * ParamLayout::total, cudaMemcpyHostToDevice));
+  double gauss[51];
+  for (int i = 0; i < 51; ++i) {  // scipy.signal.windows.gaussian(51, std=5): exp(-n^2 / (2*std^2))
+    double n = (double)i - 25.0;
+    gauss[i] = std::exp(-(n * n) / 50.0);
+  }
+  CK(cudaMemcpy(m->d_gauss, gauss, sizeof(gauss), cudaMemcpyHostToDevice));
+  const float* P = m->d_params;
+  const float* D = m->d_derived;
+  m->cw = CnnWeights{D + DerivedLayout::contour1_wT, P + ParamLayout::contour1_b, D + DerivedLayout::contour2_wT,
+                     P + ParamLayout::contour2_b,    D + DerivedLayout::note1_wT, P + ParamLayout::note1_b,
+                     D + DerivedLayout::note2_wT,    P + ParamLayout::note2_b,    D + DerivedLayout::onset1_wT,
+                     P + ParamLayout::onset1_b,      D + DerivedLayout::onset2_wT, P + ParamLayout::onset2_b};
+  cnn_setup();
+  rc = derive(m, m->stream);
+  if (rc) return rc;
+  CK(cudaStreamSynchronize(m->stream));
+  *out = m;
+  return BP_OK;
+}
+
+void bp_model_destroy(bp_model_t* m) {
+  if (!m) return;
+  DeviceGuard g(m->device);
+  cudaDeviceSynchronize();
+  m->chain.release(); m->y.release(); m->c1.release(); m->n1.release(); m->o1.release();
+  m->raw_note.release(); m->raw_onset.release(); m->raw_contour.release(); m->minmax.release();
+  m->wdesc.release(); m->udesc.release(); m->st_audio.release(); m->st_note.release(); m->st_onset.release();
+  m->st_contour.release(); m->d_frame_off.release(); m->d_slot_off.release(); m->d_note_base.release();
+  m->energy.release(); m->d_amp.release(); m->candbits.release(); m->max_onset.release(); m->max_fd.release();
+  m->note_count.release(); m->slot_start.release(); m->slot_end.release(); m->slot_pitch.release();
+  m->overflow.release(); m->d_note_off.release(); m->d_start.release(); m->d_end.release(); m->d_pitch.release();
+  m->d_bend_off.release(); m->d_bends.release();
+  if (m->d_params) cudaFree(m->d_params);
+  if (m->d_derived) cudaFree(m->d_derived);
+  if (m->d_gauss) cudaFree(m->d_gauss);
+  if (m->stream) cudaStreamDestroy(m->stream);
+  delete m;
+}
+
+int bp_model_device(const bp_model_t* m) { return m ? m->device : -1; }
+int64_t bp_model_launch_count(const bp_model_t* m) { return m ? m->launches : 0; }
+int64_t bp_model_chunk_windows(const bp_model_t* m) { return m ? m->chunk : 0; }
+
+int bp_model_param_block(bp_model_t* m, void** d_ptr, size_t* nbytes) {
+  if (!m || !d_ptr || !nbytes) return fail(BP_E_INVALID, "bp_model_param_block: null argument");
+  *d_ptr = m->d_params;
+  *nbytes = sizeof(float) * ParamLayout::total;
+  return BP_OK;
+}
+
+int bp_model_refresh(bp_model_t* m) {
+  if (!m) return fail(BP_E_INVALID, "bp_model_refresh: null model");
+  DeviceGuard g(m->device);
+  CK(cudaDeviceSynchronize());
+  int rc = derive(m, m->stream);
+  if (rc) return rc;
+  CK(cudaStreamSynchronize(m->stream));
+  return BP_OK;
+}
+
+int bp_model_set_path(bp_model_t* m, int path) {
+  if (!m) return fail(BP_E_INVALID, "bp_model_set_path: null model");
+  if (path != 0) return fail(BP_E_INVALID, "bp_model_set_path: only path 0 (FP32 FFMA) is built in this version");
+  m->path = path;
+  return BP_OK;
+}
+
+int bp_forward_device(bp_model_t* m, const float* d_audio, int64_t n_windows, float* d_note, float* d_onset,
+                      float* d_contour, void* stream) {
+  if (!m || !d_audio || !d_note || !d_onset || !d_contour) return fail(BP_E_INVALID, "bp_forward_device: null argument");
+  if (n_windows < 0) return fail(BP_E_INVALID, "bp_forward_device: negative window count");
+  DeviceGuard g(m->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int rc = ensure_forward_ws(m, (int)std::min<int64_t>(n_windows, m->chunk));
+  if (rc) return rc;
+  for (int64_t c0 = 0; c0 < n_windows; c0 += m->chunk) {
+    int nb = (int)std::min<int64_t>(m->chunk, n_windows - c0);
+    rc = forward_chunk(m, d_audio + c0 * kWinSamples, nullptr, nb, d_note + c0 * kFrames * kPitches,
+                       d_onset + c0 * kFrames * kPitches, d_contour + c0 * kFrames * kContourBins, st);
+    if (rc) return rc;
+  }
+  m->last_forward_n = n_windows;
+  return BP_OK;
+}
+
+int bp_forward_host(bp_model_t* m, const float* h_audio, int64_t n_windows, float* h_note, float* h_onset,
+                    float* h_contour) {
+  if (!m || !h_audio || !h_note || !h_onset || !h_contour) return fail(BP_E_INVALID, "bp_forward_host: null argument");
+  if (n_windows < 0) return fail(BP_E_INVALID, "bp_forward_host: negative window count");
+  DeviceGuard g(m->device);
+  CK(m->st_audio.reserve((size_t)n_windows * kWinSamples));
+  CK(m->st_note.reserve((size_t)n_windows * kFrames * kPitches));
+  CK(m->st_onset.reserve((size_t)n_windows * kFrames * kPitches));
+  CK(m->st_contour.reserve((size_t)n_windows * kFrames * kContourBins));
+  cudaStream_t st = m->stream;
+  CK(cudaMemcpyAsync(m->st_audio.p, h_audio, sizeof(float) * n_windows * kWinSamples, cudaMemcpyHostToDevice, st));
+  int rc = bp_forward_device(m, m->st_audio.p, n_windows, m->st_note.p, m->st_onset.p, m->st_contour.p, st);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(h_note, m->st_note.p, sizeof(float) * n_windows * kFrames * kPitches, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(h_onset, m->st_onset.p, sizeof(float) * n_windows * kFrames * kPitches, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(h_contour, m->st_contour.p, sizeof(float) * n_windows * kFrames * kContourBins,
+                     cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return BP_OK;
+}
+
+int bp_run_inference_device(bp_model_t* m, const float* d_audio, const int64_t* h_sample_off, int32_t n_files,
+                            float* d_note, float* d_onset, float* d_contour, int64_t* h_frame_off, void* stream) {
+  if (!m || !h_sample_off || !h_frame_off || n_files < 0)
+    return fail(BP_E_INVALID, "bp_run_inference_device: bad argument");
+  DeviceGuard g(m->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  std::vector<WinDesc> wd;
+  std::vector<UnwrapDesc> ud;
+  h_frame_off[0] = 0;
+  for (int i = 0; i < n_files; ++i) {
+    const int64_t n = h_sample_off[i + 1] - h_sample_off[i];
+    if (n < 0) return fail(BP_E_INVALID, "bp_run_inference_device: sample offsets must be non-decreasing");
+    const int64_t nw = bp_num_windows(n), nf = bp_num_frames(n);
+    for (int64_t w = 0; w < nw; ++w) {
+      const int64_t s = w * kHopSamples - kLeadZeros;  // window start relative to the file
+      WinDesc d;
+      d.base = h_sample_off[i] + s;
+      d.lo = (int)std::max<int64_t>(0, -s);
+      d.hi = (int)std::max<int64_t>(d.lo, std::min<int64_t>(kWinSamples, n - s));
+      wd.push_back(d);
+      UnwrapDesc u;
+      u.dst_base = h_frame_off[i] + w * kHopFrames;
+      u.rows = (int)std::max<int64_t>(0, std::min<int64_t>(kHopFrames, nf - w * kHopFrames));
+      u.pad = 0;
+      ud.push_back(u);
+    }
+    h_frame_off[i + 1] = h_frame_off[i] + nf;
+  }
+  const int64_t nwin = (int64_t)wd.size();
+  if (nwin == 0) return BP_OK;
+  if (!d_audio || !d_note || !d_onset || !d_contour) return fail(BP_E_INVALID, "bp_run_inference_device: null buffer");
+  const int chunk = m->chunk;
+  int rc = ensure_forward_ws(m, (int)std::min<int64_t>(nwin, chunk));
+  if (rc) return rc;
+  const int nbmax = (int)std::min<int64_t>(nwin, chunk);
+  CK(m->raw_note.reserve((size_t)nbmax * kFrames * kPitches));
+  CK(m->raw_onset.reserve((size_t)nbmax * kFrames * kPitches));
+  CK(m->raw_contour.reserve((size_t)nbmax * kFrames * kContourBins));
+  CK(m->wdesc.reserve(nwin));
+  CK(m->udesc.reserve(nwin));
+  CK(cudaMemcpyAsync(m->wdesc.p, wd.data(), sizeof(WinDesc) * nwin, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(m->udesc.p, ud.data(), sizeof(UnwrapDesc) * nwin, cudaMemcpyHostToDevice, st));
+  CK(cudaStreamSynchronize(st));  // wd/ud are about to go out of scope (pageable staging)
+  for (int64_t c0 = 0; c0 < nwin; c0 += chunk) {
+    const int nb = (int)std::min<int64_t>(chunk, nwin - c0);
+    rc = forward_chunk(m, d_audio, m->wdesc.p + c0, nb, m->raw_note.p, m->raw_onset.p, m->raw_contour.p, st);
+    if (rc) return rc;
+    unwrap_kernel<<<dim3(8, nb), 256, 0, st>>>(m->raw_note.p, d_note, m->udesc.p + c0, kPitches);
+    unwrap_kernel<<<dim3(8, nb), 256, 0, st>>>(m->raw_onset.p, d_onset, m->udesc.p + c0, kPitches);
+    unwrap_kernel<<<dim3(16, nb), 256, 0, st>>>(m->raw_contour.p, d_contour, m->udesc.p + c0, kContourBins);
+    CKL();
+    m->launches += 3;
+  }
+  m->last_forward_n = std::min<int64_t>(nwin, chunk) == nwin ? nwin : 0;
+  return BP_OK;
+}
+
+int bp_run_inference_host(bp_model_t* m, const float* h_audio, const int64_t* h_sample_off, int32_t n_files,
+                          float* h_note, float* h_onset, float* h_contour, int64_t* h_frame_off) {
+  if (!m || !h_sample_off || !h_frame_off || n_files < 0) return fail(BP_E_INVALID, "bp_run_inference_host: bad argument");
+  DeviceGuard g(m->device);
+  const int64_t n_samples = h_sample_off[n_files] - h_sample_off[0];
+  int64_t total_frames = 0;
+  for (int i = 0; i < n_files; ++i) total_frames += bp_num_frames(h_sample_off[i + 1] - h_sample_off[i]);
+  cudaStream_t st = m->stream;
+  CK(m->st_audio.reserve((size_t)std::max<int64_t>(n_samples, 1)));
+  CK(m->st_note.reserve((size_t)total_frames * kPitches + 1));
+  CK(m->st_onset.reserve((size_t)total_frames * kPitches + 1));
+  CK(m->st_contour.reserve((size_t)total_frames * kContourBins + 1));
+  if (n_samples > 0)
+    CK(cudaMemcpyAsync(m->st_audio.p, h_audio + h_sample_off[0], sizeof(float) * n_samples, cudaMemcpyHostToDevice, st));
+  std::vector<int64_t> rel(n_files + 1);
+  for (int i = 0; i <= n_files; ++i) rel[i] = h_sample_off[i] - h_sample_off[0];
+  int rc = bp_run_inference_device(m, m->st_audio.p, rel.data(), n_files, m->st_note.p, m->st_onset.p, m->st_contour.p,
+                                   h_frame_off, st);
+  if (rc) return rc;
+  if (total_frames > 0) {
+    if (!h_note || !h_onset || !h_contour) return fail(BP_E_INVALID, "bp_run_inference_host: null output");
+    CK(cudaMemcpyAsync(h_note, m->st_note.p, sizeof(float) * total_frames * kPitches, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(h_onset, m->st_onset.p, sizeof(float) * total_frames * kPitches, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(h_contour, m->st_contour.p, sizeof(float) * total_frames * kContourBins, cudaMemcpyDeviceToHost, st));
+  }
+  CK(cudaStreamSynchronize(st));
+  return BP_OK;
+}
+
+int bp_decode_device(bp_model_t* m, const float* d_note, const float* d_onset, const float* d_contour,
+                     const int64_t* h_frame_off, int32_t n_files, const bp_decode_params_t* params, bp_notes_t* notes,
+                     void* stream) {
+  if (!m || !h_frame_off || !notes || n_files < 0) return fail(BP_E_INVALID, "bp_decode_device: bad argument");
+  int rc = validate_params(params);
+  if (rc) return rc;
+  if (!notes->note_off || !notes->bend_off) return fail(BP_E_INVALID, "bp_decode_device: notes arrays missing");
+  DeviceGuard g(m->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const long long total_frames = h_frame_off[n_files] - h_frame_off[0];
+  notes->note_off[0] = 0;
+  notes->bend_off[0] = 0;
+  if (n_files == 0) return BP_OK;
+  if (h_frame_off[0] != 0) return fail(BP_E_INVALID, "bp_decode_device: frame_off[0] must be 0");
+  if (total_frames > 0 && (!d_note || !d_onset || (params->include_pitch_bends && !d_contour)))
+    return fail(BP_E_INVALID, "bp_decode_device: null posteriorgram");
+
+  DecodeParamsDev dp;
+  dp.onset_thresh = params->onset_thresh;
+  dp.frame_thresh = params->frame_thresh;
+  dp.min_note_len = params->min_note_len;
+  dp.energy_tol = params->energy_tol;
+  dp.infer_onsets = params->infer_onsets;
+  dp.melodia = params->melodia_trick;
+  dp.lo_col = std::max(0, std::min<int>(params->min_pitch_idx, kPitches));
+  dp.hi_col = std::max(0, std::min<int>(params->max_pitch_idx, kPitches));
+
+  std::vector<long long> foff(n_files + 1), soff(n_files + 1);
+  for (int i = 0; i <= n_files; ++i) {
+    foff[i] = h_frame_off[i];
+    if (i && foff[i] < foff[i - 1]) return fail(BP_E_INVALID, "bp_decode_device: frame offsets must be non-decreasing");
+  }
+  std::vector<int> counts(n_files);
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    soff[0] = 0;
+    for (int i = 0; i < n_files; ++i) {
+      long long T = foff[i + 1] - foff[i];
+      soff[i + 1] = soff[i] + (attempt == 0 ? std::min<long long>(T * kPitches, 8 * T + 64) : T * kPitches);
+    }
+    const size_t cells = (size_t)total_frames * kPitches;
+    CK(m->d_frame_off.reserve(n_files + 1));
+    CK(m->d_slot_off.reserve(n_files + 1));
+    CK(m->energy.reserve(cells + 1));
+    CK(m->candbits.reserve(cells / 32 + 2));
+    CK(m->max_onset.reserve(n_files));
+    CK(m->max_fd.reserve(n_files));
+    CK(m->note_count.reserve(n_files));
+    CK(m->overflow.reserve(1));
+    CK(m->slot_start.reserve((size_t)soff[n_files] + 1));
+    CK(m->slot_end.reserve((size_t)soff[n_files] + 1));
+    CK(m->slot_pitch.reserve((size_t)soff[n_files] + 1));
+    CK(cudaMemcpyAsync(m->d_frame_off.p, foff.data(), sizeof(long long) * (n_files + 1), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(m->d_slot_off.p, soff.data(), sizeof(long long) * (n_files + 1), cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(m->overflow.p, 0, sizeof(int), st));
+    DecodeBuffers b;
+    b.frame_off = m->d_frame_off.p;
+    b.energy = m->energy.p;
+    b.candbits = m->candbits.p;
+    b.max_onset = m->max_onset.p;
+    b.max_fd = m->max_fd.p;
+    b.slot_off = m->d_slot_off.p;
+    b.note_count = m->note_count.p;
+    b.note_start = m->slot_start.p;
+    b.note_end = m->slot_end.p;
+    b.note_pitch = m->slot_pitch.p;
+    b.overflow = m->overflow.p;
+    launch_decode_notes(d_note, d_onset, b, n_files, total_frames, dp, st);
+    CKL();
+    m->launches += total_frames > 0 ? 3 : 1;
+    int overflow = 0;
+    CK(cudaMemcpyAsync(counts.data(), m->note_count.p, sizeof(int) * n_files, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(&overflow, m->overflow.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (!overflow) break;
+    if (attempt == 1) return fail(BP_E_CUDA, "bp_decode_device: note slots overflowed at full capacity (internal error)");
+  }
+  long long n_notes = 0;
+  for (int i = 0; i < n_files; ++i) {
+    n_notes += counts[i];
+    if (n_notes > notes->note_capacity) {
+      long long need = 0;
+      for (int j = 0; j < n_files; ++j) need += counts[j];
+      return fail(BP_E_CAPACITY, "bp_decode_device: note_capacity too small, need " + std::to_string(need));
+    }
+    notes->note_off[i + 1] = (int32_t)n_notes;
+  }
+  if (n_notes == 0) return BP_OK;
+  if (!notes->start_frame || !notes->end_frame || !notes->pitch_midi || !notes->amplitude)
+    return fail(BP_E_INVALID, "bp_decode_device: notes arrays missing");
+
+  CK(m->d_note_off.reserve(n_files + 1));
+  CK(m->d_start.reserve(n_notes));
+  CK(m->d_end.reserve(n_notes));
+  CK(m->d_pitch.reserve(n_notes));
+  CK(m->d_amp.reserve(n_notes));
+  CK(m->d_note_base.reserve(n_notes));
+  CK(m->d_bend_off.reserve(n_notes + 1));
+  CK(cudaMemcpyAsync(m->d_note_off.p, notes->note_off, sizeof(int) * (n_files + 1), cudaMemcpyHostToDevice, st));
+  compact_notes_kernel<<<n_files, 128, 0, st>>>(m->d_frame_off.p, m->d_slot_off.p, m->d_note_off.p, m->slot_start.p,
+                                                m->slot_end.p, m->slot_pitch.p, m->d_start.p, m->d_end.p, m->d_pitch.p,
+                                                m->d_note_base.p);
+  CKL();
+  m->launches += 1;
+  CK(cudaMemcpyAsync(notes->start_frame, m->d_start.p, sizeof(int) * n_notes, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(notes->end_frame, m->d_end.p, sizeof(int) * n_notes, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(notes->pitch_midi, m->d_pitch.p, sizeof(int) * n_notes, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  long long n_bends = 0;
+  const int with_bends = params->include_pitch_bends ? 1 : 0;
+  for (long long j = 0; j < n_notes; ++j) {
+    if (with_bends) n_bends += notes->end_frame[j] - notes->start_frame[j];
+    if (n_bends > 0x7fffffffLL) return fail(BP_E_CAPACITY, "bp_decode_device: more than 2^31 pitch-bend values");
+    notes->bend_off[j + 1] = (int32_t)n_bends;
+  }
+  if (with_bends && n_bends > notes->bend_capacity)
+    return fail(BP_E_CAPACITY, "bp_decode_device: bend_capacity too small, need " + std::to_string(n_bends));
+  if (with_bends && n_bends > 0 && !notes->bends) return fail(BP_E_INVALID, "bp_decode_device: bends array missing");
+  CK(m->d_bends.reserve((size_t)n_bends + 1));
+  CK(cudaMemcpyAsync(m->d_bend_off.p, notes->bend_off, sizeof(int) * (n_notes + 1), cudaMemcpyHostToDevice, st));
+  launch_note_finish(d_note, d_contour, m->d_note_base.p, m->d_start.p, m->d_end.p, m->d_pitch.p, m->d_amp.p,
+                     m->d_bend_off.p, m->d_bends.p, (int)n_notes, with_bends, m->d_gauss, st);
+  CKL();
+  m->launches += 1;
+  CK(cudaMemcpyAsync(notes->amplitude, m->d_amp.p, sizeof(float) * n_notes, cudaMemcpyDeviceToHost, st));
+  if (with_bends && n_bends > 0)
+    CK(cudaMemcpyAsync(notes->bends, m->d_bends.p, sizeof(int) * n_bends, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return BP_OK;
+}
+
+int bp_decode_host(bp_model_t* m, const float* h_note, const float* h_onset, const float* h_contour,
+                   const int64_t* h_frame_off, int32_t n_files, const bp_decode_params_t* params, bp_notes_t* notes) {
+  if (!m || !h_frame_off || n_files < 0) return fail(BP_E_INVALID, "bp_decode_host: bad argument");
+  DeviceGuard g(m->device);
+  const int64_t total = h_frame_off[n_files];
+  cudaStream_t st = m->stream;
+  CK(m->st_note.reserve((size_t)total * kPitches + 1));
+  CK(m->st_onset.reserve((size_t)total * kPitches + 1));
+  CK(m->st_contour.reserve((size_t)total * kContourBins + 1));
+  if (total > 0) {
+    if (!h_note || !h_onset || !h_contour) return fail(BP_E_INVALID, "bp_decode_host: null posteriorgram");
+    CK(cudaMemcpyAsync(m->st_note.p, h_note, sizeof(float) * total * kPitches, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(m->st_onset.p, h_onset, sizeof(float) * total * kPitches, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(m->st_contour.p, h_contour, sizeof(float) * total * kContourBins, cudaMemcpyHostToDevice, st));
+  }
+  return bp_decode_device(m, m->st_note.p, m->st_onset.p, m->st_contour.p, h_frame_off, n_files, params, notes, st);
+}
+
+int bp_transcribe_device(bp_model_t* m, const float* d_audio, const int64_t* h_sample_off, int32_t n_files,
+                         const bp_decode_params_t* params, int64_t* h_frame_off, bp_notes_t* notes, void* stream) {
+  if (!m || !h_sample_off || !h_frame_off || n_files < 0) return fail(BP_E_INVALID, "bp_transcribe_device: bad argument");
+  int rc = validate_params(params);
+  if (rc) return rc;
+  DeviceGuard g(m->device);
+  int64_t total_frames = 0;
+  for (int i = 0; i < n_files; ++i) total_frames += bp_num_frames(h_sample_off[i + 1] - h_sample_off[i]);
+  CK(m->st_note.reserve((size_t)total_frames * kPitches + 1));
+  CK(m->st_onset.reserve((size_t)total_frames * kPitches + 1));
+  CK(m->st_contour.reserve((size_t)total_frames * kContourBins + 1));
+  rc = bp_run_inference_device(m, d_audio, h_sample_off, n_files, m->st_note.p, m->st_onset.p, m->st_contour.p,
+                               h_frame_off, stream);
+  if (rc) return rc;
+  return bp_decode_device(m, m->st_note.p, m->st_onset.p, m->st_contour.p, h_frame_off, n_files, params, notes, stream);
+}
+
+int bp_transcribe_host(bp_model_t* m, const float* h_audio, const int64_t* h_sample_off, int32_t n_files,
+                       const bp_decode_params_t* params, float* h_note, float* h_onset, float* h_contour,
+                       int64_t* h_frame_off, bp_notes_t* notes) {
+  if (!m || !h_sample_off || !h_frame_off || n_files < 0) return fail(BP_E_INVALID, "bp_transcribe_host: bad argument");
+  DeviceGuard g(m->device);
+  const int64_t n_samples = h_sample_off[n_files] - h_sample_off[0];
+  cudaStream_t st = m->stream;
+  CK(m->st_audio.reserve((size_t)std::max<int64_t>(n_samples, 1)));
+  if (n_samples > 0) {
+    if (!h_audio) return fail(BP_E_INVALID, "bp_transcribe_host: null audio");
+    CK(cudaMemcpyAsync(m->st_audio.p, h_audio + h_sample_off[0], sizeof(float) * n_samples, cudaMemcpyHostToDevice, st));
+  }
+  std::vector<int64_t> rel(n_files + 1);
+  for (int i = 0; i <= n_files; ++i) rel[i] = h_sample_off[i] - h_sample_off[0];
+  int rc = bp_transcribe_device(m, m->st_audio.p, rel.data(), n_files, params, h_frame_off, notes, st);
+  if (rc) return rc;
+  const int64_t total_frames = h_frame_off[n_files];
+  if (total_frames > 0) {
+    if (h_note) CK(cudaMemcpyAsync(h_note, m->st_note.p, sizeof(float) * total_frames * kPitches, cudaMemcpyDeviceToHost, st));
+    if (h_onset) CK(cudaMemcpyAsync(h_onset, m->st_onset.p, sizeof(float) * total_frames * kPitches, cudaMemcpyDeviceToHost, st));
+    if (h_contour)
+      CK(cudaMemcpyAsync(h_contour, m->st_contour.p, sizeof(float) * total_frames * kContourBins, cudaMemcpyDeviceToHost, st));
+  }
+  CK(cudaStreamSynchronize(st));
+  return BP_OK;
+}
+
+int bp_debug_activation(bp_model_t* m, int which, float* h_out, int64_t n_windows) {
+  if (!m || !h_out) return fail(BP_E_INVALID, "bp_debug_activation: null argument");
+  if (n_windows <= 0 || n_windows > m->chunk || n_windows > m->last_forward_n)
+    return fail(BP_E_INVALID, "bp_debug_activation: only valid for the windows of a single-chunk forward call");
+  DeviceGuard g(m->device);
+  const float* src = nullptr;
+  size_t per = 0;
+  switch (which) {
+    case 0: src = m->y.p; per = (size_t)kFrames * kCqtBins; break;
+    case 1: src = m->c1.p; per = (size_t)8 * kFrames * kContourBins; break;
+    case 2: src = m->n1.p; per = (size_t)32 * kFrames * kPitches; break;
+    case 3: src = m->o1.p; per = (size_t)32 * kFrames * kPitches; break;
+    default: return fail(BP_E_INVALID, "bp_debug_activation: unknown activation id");
+  }
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpy(h_out, src, sizeof(float) * per * n_windows, cudaMemcpyDeviceToHost));
+  return BP_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,60 @@
+// Launch wrappers of the hot-path kernels (host-callable; all asynchronous on `st`).
+#pragma once
+#include "common.cuh"
+
+namespace bp {
+
+// ---- hcqt.cu ------------------------------------------------------------------------------------
+void upload_lowpass(const float* d_lp, cudaStream_t st);  // device pointer -> __constant__ taps
+void launch_decimate(const float* audio, const WinDesc* desc, float* chain, int stage, int n_windows, cudaStream_t st);
+void launch_cqt(const float* audio, const WinDesc* desc, const float* chain, const float* wt, const float* scale,
+                float* logmag, unsigned int* minmax, int n_windows, cudaStream_t st);
+void launch_lognorm(float* y, const unsigned int* minmax, const float* bn /* device: scale, bias */, int n_windows,
+                    cudaStream_t st);
+
+// ---- cnn.cu (FP32 FFMA path) -------------------------------------------------------------------
+// Transposed weights wT[(ci*KH+dt)*KW+df][COUT]; activations are planar [B][C][172][W].
+struct CnnWeights {
+  const float *contour1_wT, *contour1_b;
+  const float *contour2_wT, *contour2_b;
+  const float *note1_wT, *note1_b;
+  const float *note2_wT, *note2_b;
+  const float *onset1_wT, *onset1_b;
+  const float *onset2_wT, *onset2_b;
+};
+void cnn_setup();
+void launch_contour1(const float* y, const CnnWeights& w, float* c1, int n_windows, cudaStream_t st);
+void launch_contour2(const float* c1, const CnnWeights& w, float* contour, int n_windows, cudaStream_t st);
+void launch_note1(const float* contour, const CnnWeights& w, float* n1, int n_windows, cudaStream_t st);
+void launch_note2(const float* n1, const CnnWeights& w, float* note, int n_windows, cudaStream_t st);
+void launch_onset1(const float* y, const CnnWeights& w, float* o1, int n_windows, cudaStream_t st);
+void launch_onset2(const float* note, const float* o1, const CnnWeights& w, float* onset, int n_windows,
+                   cudaStream_t st);
+
+// ---- unwrap (api.cu) / decode.cu ----------------------------------------------------------------
+struct DecodeParamsDev {
+  double onset_thresh, frame_thresh;
+  int min_note_len, energy_tol, infer_onsets, melodia, lo_col, hi_col;
+};
+struct DecodeBuffers {
+  const long long* frame_off;     // [n_files+1] device; file i covers frames [frame_off[i], frame_off[i+1])
+  float* energy;                  // [total_frames*88] "remaining energy", column-major per file
+  unsigned int* candbits;         // [(total_frames*88+31)/32 + 1] onset-candidate bit per cell
+  unsigned int* max_onset;        // [n_files]
+  unsigned long long* max_fd;     // [n_files]
+  const long long* slot_off;      // [n_files+1] device; note slots of file i
+  int* note_count;                // [n_files]
+  int* note_start;                // [slots]
+  int* note_end;
+  int* note_pitch;
+  int* overflow;                  // [1] set when a file ran out of slots
+};
+void launch_decode_notes(const float* note, const float* onset, const DecodeBuffers& buf, int n_files,
+                         long long total_frames, const DecodeParamsDev& p, cudaStream_t st);
+// amplitude (NumPy pairwise mean) + pitch bends for compacted notes
+void launch_note_finish(const float* note, const float* contour, const long long* note_frame_base /*[n_notes]*/,
+                        const int* start, const int* end, const int* pitch, float* amp, const int* bend_off,
+                        int* bends, int n_notes, int with_bends, const double* gauss /*[51] device*/,
+                        cudaStream_t st);
+
+}  // namespace bp

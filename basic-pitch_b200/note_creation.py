@@ -1,0 +1,202 @@
+"""Note decode host interface (mirrors the names of reference: basic_pitch/note_creation.py).
+
+The arithmetic of the reference's `output_to_notes_polyphonic` / `get_pitch_bends`
+(note_creation.py:360-511, 182-219) runs on the GPU (csrc/decode.cu via `bp_decode_host`); this
+module converts arguments, maps frames to seconds and assembles the MIDI object.
+"""
+from __future__ import annotations
+
+from collections import defaultdict
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+
+from .constants import (
+    ANNOT_N_FRAMES,
+    ANNOTATIONS_BASE_FREQUENCY,
+    ANNOTATIONS_N_SEMITONES,
+    AUDIO_N_SAMPLES,
+    AUDIO_SAMPLE_RATE,
+    CONTOURS_BINS_PER_SEMITONE,
+    DEFAULT_MIN_NOTE_LEN,
+    ENERGY_TOLERANCE,
+    FFT_HOP,
+    MAGIC_ALIGNMENT_OFFSET,
+    MAX_FREQ_IDX,
+    MIDI_OFFSET,
+    MIDI_VELOCITY_SCALE,
+    N_FREQ_BINS_CONTOURS,
+    N_PITCH_BEND_TICKS,
+    PITCH_BEND_SCALE,
+)
+
+try:  # the real package when present, else the bundled minimal containers
+    import pretty_midi  # type: ignore
+except ImportError:  # pragma: no cover - depends on the environment
+    from . import midi as pretty_midi
+
+NoteEvent = Tuple[float, float, int, float, Optional[List[int]]]
+
+
+def hz_to_midi(hz):
+    return 12 * (np.log2(np.asanyarray(hz)) - np.log2(440.0)) + 69
+
+
+def midi_to_hz(midi):
+    return 440.0 * (2.0 ** ((np.asanyarray(midi) - 69.0) / 12.0))
+
+
+def midi_pitch_to_contour_bin(pitch_midi: int) -> np.ndarray:
+    """reference: note_creation.py:168-179"""
+    return 12.0 * CONTOURS_BINS_PER_SEMITONE * np.log2(midi_to_hz(pitch_midi) / ANNOTATIONS_BASE_FREQUENCY)
+
+
+def frequency_to_column_range(min_freq: Optional[float], max_freq: Optional[float], n_cols: int = ANNOTATIONS_N_SEMITONES) -> Tuple[int, int]:
+    """Columns kept by the reference's `constrain_frequency` (note_creation.py:329-341), as [lo, hi).
+
+    The reference writes `m[:, :min_idx] = 0; m[:, max_idx:] = 0` with unclamped indices, so NumPy's
+    slice rules apply (a negative index counts from the end); this reproduces them exactly.
+    """
+    lo, hi = 0, n_cols
+    if min_freq is not None:
+        lo = int(np.round(hz_to_midi(min_freq) - MIDI_OFFSET))
+    if max_freq is not None:
+        hi = int(np.round(hz_to_midi(max_freq) - MIDI_OFFSET))
+    lo = slice(None, lo).indices(n_cols)[1]  # end of the zeroed prefix
+    hi = slice(hi, None).indices(n_cols)[0]  # start of the zeroed suffix
+    return lo, hi
+
+
+def constrain_frequency(onsets: np.ndarray, frames: np.ndarray, max_freq: Optional[float], min_freq: Optional[float]):
+    """Zero pitch columns outside the range, IN PLACE like the reference (note_creation.py:314-343)."""
+    lo, hi = frequency_to_column_range(min_freq, max_freq, onsets.shape[1])
+    for m in (onsets, frames):
+        m[:, :lo] = 0
+        m[:, hi:] = 0
+    return onsets, frames
+
+
+def model_frames_to_time(n_frames: int) -> np.ndarray:
+    """reference: note_creation.py:346-357 (librosa.frames_to_time inlined)."""
+    idx = np.arange(n_frames)
+    original_times = (idx * FFT_HOP).astype(int) / float(AUDIO_SAMPLE_RATE)
+    window_numbers = np.floor(idx / ANNOT_N_FRAMES)
+    window_offset = (FFT_HOP / AUDIO_SAMPLE_RATE) * (ANNOT_N_FRAMES - (AUDIO_N_SAMPLES / FFT_HOP)) + MAGIC_ALIGNMENT_OFFSET
+    return original_times - (window_offset * window_numbers)
+
+
+def _decode(output, onset_thresh, frame_thresh, infer_onsets, min_note_len, min_freq, max_freq, include_pitch_bends,
+            melodia_trick, energy_tol=ENERGY_TOLERANCE, model=None):
+    from .inference import default_model
+
+    mdl = model if model is not None else default_model()
+    frames, onsets, contours = output["note"], output["onset"], output.get("contour")
+    lo, hi = frequency_to_column_range(min_freq, max_freq, frames.shape[1])
+    res = mdl.decode_arrays(
+        [frames], [onsets], [contours] if contours is not None else None,
+        onset_thresh=onset_thresh, frame_thresh=frame_thresh, min_note_len=min_note_len, energy_tol=energy_tol,
+        infer_onsets=infer_onsets, melodia_trick=melodia_trick, include_pitch_bends=include_pitch_bends,
+        min_pitch_idx=lo, max_pitch_idx=hi,
+    )[0]
+    # the reference zeroes the out-of-range columns of the caller's arrays (note_creation.py:338-341)
+    if min_freq is not None or max_freq is not None:
+        for m in (onsets, frames):
+            if m.flags.writeable:
+                m[:, :lo] = 0
+                m[:, hi:] = 0
+    return res
+
+
+def output_to_notes_polyphonic(frames, onsets, onset_thresh, frame_thresh, min_note_len, infer_onsets, max_freq,
+                               min_freq, melodia_trick=True, energy_tol=ENERGY_TOLERANCE, model=None):
+    """reference: note_creation.py:360-511 -> [(start_frame, end_frame, pitch_midi, amplitude)]"""
+    res = _decode({"note": frames, "onset": onsets}, onset_thresh, frame_thresh, infer_onsets, min_note_len, min_freq,
+                  max_freq, False, melodia_trick, energy_tol, model)
+    return [(int(a), int(b), int(p), np.float32(amp)) for a, b, p, amp in zip(res["start"], res["end"], res["pitch"], res["amp"])]
+
+
+def model_output_to_notes(
+    output: Dict[str, np.ndarray],
+    onset_thresh: float,
+    frame_thresh: float,
+    infer_onsets: bool = True,
+    min_note_len: int = DEFAULT_MIN_NOTE_LEN,
+    min_freq: Optional[float] = None,
+    max_freq: Optional[float] = None,
+    include_pitch_bends: bool = True,
+    multiple_pitch_bends: bool = False,
+    melodia_trick: bool = True,
+    midi_tempo: float = 120,
+    model=None,
+):
+    """reference: note_creation.py:52-116 -> (PrettyMIDI, note events in seconds)."""
+    res = _decode(output, onset_thresh, frame_thresh, infer_onsets, min_note_len, min_freq, max_freq,
+                  include_pitch_bends, melodia_trick, model=model)
+    events = note_events_from_arrays(res, output["contour"].shape[0], include_pitch_bends)
+    return note_events_to_midi(events, multiple_pitch_bends, midi_tempo), events
+
+
+def note_events_from_arrays(res: Dict[str, np.ndarray], n_frames: int, include_pitch_bends: bool = True) -> List[NoteEvent]:
+    """Decode arrays (frames) -> the reference's list of (start_s, end_s, pitch, amplitude, bends)."""
+    times = model_frames_to_time(n_frames)
+    start, end, pitch, amp = res["start"], res["end"], res["pitch"], res["amp"]
+    off, flat = res["bend_off"], res["bends"]
+    events: List[NoteEvent] = []
+    for j in range(len(start)):
+        bends = list(flat[off[j] : off[j + 1]].astype(np.int64)) if include_pitch_bends else None
+        events.append((times[start[j]], times[end[j]], np.int64(pitch[j]), np.float32(amp[j]), bends))
+    return events
+
+
+def drop_overlapping_pitch_bends(note_events_with_pitch_bends: List[NoteEvent]) -> List[NoteEvent]:
+    """reference: note_creation.py:274-286 — notes overlapping in time lose their pitch bends."""
+    ev = sorted(note_events_with_pitch_bends)
+    for i in range(len(ev) - 1):
+        for j in range(i + 1, len(ev)):
+            if ev[j][0] >= ev[i][1]:
+                break
+            ev[i] = ev[i][:-1] + (None,)
+            ev[j] = ev[j][:-1] + (None,)
+    return ev
+
+
+def note_events_to_midi(note_events_with_pitch_bends: List[NoteEvent], multiple_pitch_bends: bool = False,
+                        midi_tempo: float = 120):
+    """reference: note_creation.py:222-271"""
+    mid = pretty_midi.PrettyMIDI(initial_tempo=midi_tempo)
+    if not multiple_pitch_bends:
+        note_events_with_pitch_bends = drop_overlapping_pitch_bends(note_events_with_pitch_bends)
+    program = pretty_midi.instrument_name_to_program("Electric Piano 1")
+    instruments = defaultdict(lambda: pretty_midi.Instrument(program=program))
+    for start_time, end_time, note_number, amplitude, pitch_bend in note_events_with_pitch_bends:
+        inst = instruments[note_number] if multiple_pitch_bends else instruments[0]
+        inst.notes.append(
+            pretty_midi.Note(velocity=int(np.round(MIDI_VELOCITY_SCALE * amplitude)), pitch=note_number,
+                             start=start_time, end=end_time)
+        )
+        if not pitch_bend:
+            continue
+        bend_times = np.linspace(start_time, end_time, len(pitch_bend))
+        ticks = np.round(np.array(pitch_bend) * PITCH_BEND_SCALE / CONTOURS_BINS_PER_SEMITONE).astype(int)
+        ticks[ticks > N_PITCH_BEND_TICKS - 1] = N_PITCH_BEND_TICKS - 1
+        ticks[ticks < -N_PITCH_BEND_TICKS] = -N_PITCH_BEND_TICKS
+        for t, b in zip(bend_times, ticks):
+            inst.pitch_bends.append(pretty_midi.PitchBend(b, t))
+    mid.instruments.extend(instruments.values())
+    return mid
+
+
+def sonify_midi(midi, save_path, sr: Optional[int] = 44100) -> None:
+    """reference: note_creation.py:119-128 — needs the real pretty_midi (synthesis is off the hot path)."""
+    if not hasattr(midi, "synthesize"):
+        raise NotImplementedError("sonify_midi needs the `pretty_midi` package (MIDI synthesis is outside the hot path)")
+    from scipy.io import wavfile
+
+    wavfile.write(save_path, sr, midi.synthesize(sr))
+
+
+__all__ = [
+    "model_output_to_notes", "output_to_notes_polyphonic", "note_events_to_midi", "drop_overlapping_pitch_bends",
+    "model_frames_to_time", "constrain_frequency", "midi_pitch_to_contour_bin", "sonify_midi",
+    "MIDI_OFFSET", "MAX_FREQ_IDX", "N_FREQ_BINS_CONTOURS",
+]  # fmt: skip

@@ -1,0 +1,238 @@
+"""GPU parity tests (run on the B200 box with `-m gpu`): the CUDA path, called through the C ABI
+(ctypes -> libbp_b200.so), against the oracle and the committed golden fixtures.
+
+Tolerances (floating point, BASELINE.json north_star): posteriorgram max-abs <= 1e-3 vs the reference
+model; the FP32 path is expected (and required here) to stay within 1e-4 of the fp32 oracle.
+Integer work (note decode) must be bit-identical.
+"""
+import numpy as np
+import pytest
+
+from tests.golden_util import assert_events_equal, case_expected, case_params, dequant, events_to_arrays
+
+pytestmark = pytest.mark.gpu
+
+POST_TOL = 1e-4  # vs the fp32 oracle on identical 22 050 Hz input
+GOLD_TOL = 5e-4  # vs the reference's golden file (44.1 kHz source, resampler differs; see tests/golden/README.md)
+
+
+@pytest.fixture(scope="module")
+def model():
+    from basic_pitch_b200 import ICASSP_2022_MODEL_PATH
+    from basic_pitch_b200.inference import Model
+
+    return Model(ICASSP_2022_MODEL_PATH)
+
+
+def _edge_windows():
+    from basic_pitch_b200 import synth
+
+    rng = np.random.default_rng(11)
+    w = synth.window_batch(5, seed=2)
+    zeros = np.zeros((1, 43844), np.float32)  # exercises divide_no_nan
+    noise = rng.uniform(-1, 1, (1, 43844)).astype(np.float32)  # full-scale white noise
+    tiny = (1e-6 * rng.standard_normal((1, 43844))).astype(np.float32)
+    click = np.zeros((1, 43844), np.float32)
+    click[0, 20000] = 1.0
+    return np.concatenate([w, zeros, noise, tiny, click])
+
+
+def test_forward_vs_oracle_including_activations(model, weights_np):
+    from basic_pitch_b200 import _lib
+    from oracle import model_ref
+
+    x = _edge_windows()
+    got = model.predict(x[:, :, None])
+    ref = model_ref.forward(x, weights_np, return_intermediates=True)
+    lib = _lib.load()
+    n = x.shape[0]
+    for which, key, shape, tol in ((0, "_y", (n, 172, 309), 2e-5), (1, "_c1", (n, 8, 172, 264), 2e-4),
+                                   (2, "_n1", (n, 32, 172, 88), 2e-4), (3, "_o1", (n, 32, 172, 88), 2e-4)):
+        buf = np.empty(shape, np.float32)
+        lib.bp_debug_activation(model.handle, which, buf.ctypes.data, n)
+        err = np.abs(buf - ref[key]).max()
+        assert err < tol, f"activation {key}: max-abs {err:.3e}"
+    for k in ("note", "onset", "contour"):
+        assert got[k].shape == ref[k].shape and got[k].dtype == np.float32
+        err = np.abs(got[k] - ref[k]).max()
+        assert err < POST_TOL, f"{k}: max-abs {err:.3e}"
+    assert np.all(np.isfinite(got["note"])) and np.all(np.isfinite(got["contour"]))
+
+
+def test_vocadito_golden_posteriorgrams(model, golden_dir, weights_np):
+    """reference: tests/test_inference.py:43-70 — shapes, and values vs the golden npz."""
+    from oracle import host_ref, model_ref
+
+    z = np.load(golden_dir / "vocadito10.npz")
+    audio = z["audio22k"]
+    out = model.run_inference_arrays([audio])[0]
+    o = model_ref.forward(host_ref.window_audio(audio), weights_np)
+    for k in ("note", "onset", "contour"):
+        gold = z[f"gold_{k}"]
+        assert out[k].shape == gold.shape
+        assert np.abs(out[k] - gold).max() < GOLD_TOL, k
+        assert np.abs(out[k] - host_ref.unwrap(o[k], len(audio))).max() < POST_TOL, k
+
+
+def _gpu_decode(model, post, p):
+    from basic_pitch_b200 import note_creation as nc
+
+    lo, hi = nc.frequency_to_column_range(p["min_freq"], p["max_freq"])
+    res = model.decode_arrays([post["note"]], [post["onset"]], [post["contour"]], onset_thresh=p["onset_thresh"],
+                              frame_thresh=p["frame_thresh"], min_note_len=p["min_note_len"],
+                              infer_onsets=p["infer_onsets"], melodia_trick=p["melodia_trick"], min_pitch_idx=lo,
+                              max_pitch_idx=hi)[0]
+    ev = nc.note_events_from_arrays(res, post["contour"].shape[0])
+    wb = [(int(a), int(b), int(pp), amp, None) for a, b, pp, amp in zip(res["start"], res["end"], res["pitch"], res["amp"])]
+    return events_to_arrays(wb, ev)
+
+
+def test_decode_reference_golden_events(model, golden_dir):
+    """reference: tests/test_inference.py:72-76 — the 28 golden events from the golden posteriorgrams."""
+    z = np.load(golden_dir / "vocadito10.npz")
+    post = {k: z[f"gold_{k}"] for k in ("note", "onset", "contour")}
+    got = _gpu_decode(model, post, dict(onset_thresh=0.5, frame_thresh=0.3, min_note_len=11, infer_onsets=True,
+                                        melodia_trick=True, min_freq=None, max_freq=None))
+    assert len(got["pitch"]) == 28
+    np.testing.assert_array_equal(got["pitch"], z["gold_events/pitch"])
+    np.testing.assert_array_equal(got["bend_flat"], z["gold_events/bend_flat"])
+    np.testing.assert_array_equal(got["bend_off"], z["gold_events/bend_off"])
+    np.testing.assert_allclose(got["start"], z["gold_events/start"], rtol=0, atol=1e-12)
+    np.testing.assert_allclose(got["end"], z["gold_events/end"], rtol=0, atol=1e-12)
+    np.testing.assert_allclose(got["amp"], z["gold_events/amp"], rtol=0, atol=1e-5)
+
+
+@pytest.mark.parametrize("i", range(9))
+def test_decode_bit_exact_vocadito_param_sets(model, golden_dir, i):
+    z = np.load(golden_dir / "vocadito10.npz")
+    post = {k: z[f"gold_{k}"] for k in ("note", "onset", "contour")}
+    got = _gpu_decode(model, post, case_params(z, f"decode{i}"))
+    assert_events_equal(got, case_expected(z, f"decode{i}"), ctx=f"decode{i}")
+
+
+def test_decode_bit_exact_reference_cases(model, golden_dir):
+    """Every case produced by the UNMODIFIED reference decode: dense chords, fuzz, thresholds <= 0,
+    NaN path (constant input), 1..25-frame inputs, frequency limits, melodia on/off."""
+    z = np.load(golden_dir / "decode_cases.npz")
+    for name in z["names"]:
+        name = str(name)
+        base = name.rsplit("/", 1)[0]
+        post = {k: dequant(z[f"{base}/{k}_q"]) for k in ("note", "onset", "contour")}
+        got = _gpu_decode(model, post, case_params(z, name))
+        assert_events_equal(got, case_expected(z, name), ctx=name)
+
+
+def test_decode_batch_equals_single(model, golden_dir):
+    """Files decoded in one batched call give the same events as one call per file (incl. an empty file)."""
+    z = np.load(golden_dir / "decode_cases.npz")
+    bases = ["notes10s", "fuzz0", "tiny3", "chords4s", "constant"]
+    posts = [{k: dequant(z[f"{b}/{k}_q"]) for k in ("note", "onset", "contour")} for b in bases]
+    posts.insert(2, {"note": np.zeros((0, 88), np.float32), "onset": np.zeros((0, 88), np.float32), "contour": np.zeros((0, 264), np.float32)})
+    batch = model.decode_arrays([p["note"] for p in posts], [p["onset"] for p in posts], [p["contour"] for p in posts])
+    for p, b in zip(posts, batch):
+        single = model.decode_arrays([p["note"]], [p["onset"]], [p["contour"]])[0]
+        for k in single:
+            np.testing.assert_array_equal(single[k], b[k], err_msg=k)
+    assert len(batch[2]["start"]) == 0
+
+
+def test_decode_vs_oracle_on_gpu_posteriorgrams(model, weights_np):
+    """GPU note list identical to the reference decode run on the SAME GPU posteriorgrams."""
+    from basic_pitch_b200 import synth
+    from oracle import decode_ref
+
+    for clip in (synth.random_notes_clip(12.0, seed=21), synth.dense_chords_clip(3.0, seed=7)):
+        out = model.run_inference_arrays([clip])[0]
+        got = _gpu_decode(model, out, dict(onset_thresh=0.5, frame_thresh=0.3, min_note_len=11, infer_onsets=True,
+                                           melodia_trick=True, min_freq=None, max_freq=None))
+        with np.errstate(all="ignore"):
+            wb, ev = decode_ref.model_output_to_note_events({k: np.array(v) for k, v in out.items()}, 0.5, 0.3)
+        assert len(ev) > 5
+        assert_events_equal(got, events_to_arrays(wb, ev), ctx="gpu-posteriorgrams")
+
+
+def test_predict_dropin_config1(model, golden_dir, tmp_path):
+    """BASELINE.json configs[0]: one 2 s 22 050 Hz WAV through predict(): plumbing + parity with the
+    unmodified reference predict() (fixture predict_2s.npz; its model arithmetic is the oracle's)."""
+    from scipy.io import wavfile
+
+    from basic_pitch_b200.inference import predict, predict_and_save
+
+    z = np.load(golden_dir / "predict_2s.npz")
+    wav = tmp_path / "cfg1.wav"
+    wavfile.write(wav, 22050, z["pcm16"])
+    model_output, midi_data, note_events = predict(wav, model)
+    assert set(model_output) == {"note", "onset", "contour"}
+    for k in ("note", "onset", "contour"):
+        assert model_output[k].shape == z[k].shape == (173, 88 if k != "contour" else 264)
+        assert np.abs(model_output[k] - z[k]).max() < POST_TOL, k
+    assert len(note_events) == len(z["events/pitch"])
+    assert [int(e[2]) for e in note_events] == list(z["events/pitch"])
+    np.testing.assert_array_equal(np.array([e[0] for e in note_events]), z["events/start"])
+    np.testing.assert_array_equal(np.array([e[1] for e in note_events]), z["events/end"])
+    flat = [int(b) for e in note_events for b in (e[4] or [])]
+    assert sum(abs(a - b) for a, b in zip(flat, z["events/bend_flat"])) <= 2 and len(flat) == len(z["events/bend_flat"])
+    assert len(midi_data.instruments) == 1 and len(midi_data.instruments[0].notes) == len(note_events)
+    for e in note_events:  # reference: tests/test_inference.py:55-64
+        assert 21 <= e[2] <= 108 and e[0] < e[1] <= 2.0 + 2 * 256 / 22050
+    out_dir = tmp_path / "out"
+    out_dir.mkdir()
+    predict_and_save([wav], out_dir, True, False, True, True, model)
+    for ext in ("mid", "npz", "csv"):  # reference: tests/test_inference.py:79-102
+        assert (out_dir / f"cfg1_basic_pitch.{ext}").is_file()
+    with pytest.raises(IOError):
+        predict_and_save([wav], out_dir, True, False, False, False, model)
+
+
+def test_batch_position_and_chunking_invariance(model):
+    """Size-independent property at scale: every window's result is independent of its position in the
+    batch and of the internal chunking (300 windows = several chunks, one of them ragged)."""
+    from basic_pitch_b200 import synth
+
+    base = synth.window_batch(3, seed=5)
+    x = np.tile(base, (100, 1))
+    got = model.predict(x)
+    for k in got:
+        ref = got[k][:3]
+        assert np.array_equal(got[k].reshape(100, 3, *ref.shape[1:]), np.broadcast_to(ref, (100,) + ref.shape)), k
+
+
+def test_run_inference_equals_windowed_predict(model):
+    """On-device windowing/unwrap == reference host windowing + per-window predict + unwrap, exactly."""
+    from basic_pitch_b200 import synth
+    from oracle import host_ref
+
+    clips = [synth.random_notes_clip(10.0, seed=31), synth.tones_clip(2.0, seed=1), np.zeros(1, np.float32),
+             synth.random_notes_clip(3.3, seed=33)[:36165]]
+    outs = model.run_inference_arrays(clips)
+    for clip, out in zip(clips, outs):
+        raw = model.predict(host_ref.window_audio(clip))
+        for k in raw:
+            np.testing.assert_array_equal(out[k], host_ref.unwrap(raw[k], len(clip)), err_msg=k)
+
+
+def test_linearity_scale_invariance(model):
+    """The log-normalisation makes the network invariant to input gain (a domain property that holds at any size):
+    x and 0.25*x give the same posteriorgrams up to rounding."""
+    from basic_pitch_b200 import synth
+
+    x = synth.window_batch(4, seed=9)
+    a = model.predict(x)
+    b = model.predict(0.25 * x)
+    for k in a:
+        assert np.abs(a[k] - b[k]).max() < 2e-3, k
+
+
+def test_transcribe_batch_equals_per_file(model):
+    from basic_pitch_b200 import synth
+
+    clips = [synth.random_notes_clip(6.0, seed=41), synth.dense_chords_clip(2.0, seed=3), synth.tones_clip(2.0, seed=2)]
+    outs, res, frames = model.transcribe_arrays(clips)
+    for i, c in enumerate(clips):
+        o1, r1, f1 = model.transcribe_arrays([c])
+        assert f1[0] == frames[i]
+        for k in r1[0]:
+            np.testing.assert_array_equal(r1[0][k], res[i][k], err_msg=k)
+        for k in o1[0]:
+            np.testing.assert_array_equal(o1[0][k], outs[i][k], err_msg=k)
+    assert sum(len(r["start"]) for r in res) > 20

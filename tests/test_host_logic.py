@@ -1,0 +1,172 @@
+"""CPU: host-side logic of the drop-in (no GPU): weights, constants, time mapping, MIDI assembly, audio I/O."""
+import numpy as np
+import pytest
+
+from oracle import decode_ref
+
+
+def test_weight_blob_roundtrip_and_dsp_constants(weights_np):
+    from basic_pitch_b200 import weights
+
+    blob = weights.pack(weights_np)
+    again = weights.unpack(blob)
+    for k, v in weights_np.items():
+        np.testing.assert_array_equal(again[k], v)
+    dsp = weights.dsp_constants()
+    for k in ("cqt_real", "cqt_imag", "lowpass", "cqt_scale"):
+        np.testing.assert_array_equal(dsp[k], weights_np[k], err_msg=k)  # bit-identical
+    # fingerprints, SURVEY Appendix A.4
+    assert abs(float(weights_np["onset1_w"].astype("f8").sum()) - 5.7735) < 1e-4
+    assert abs(float(weights_np["contour1_w"].astype("f8").sum()) - 2.75278) < 1e-4
+    assert abs(float(weights_np["note1_b"].astype("f8").sum()) - 7.64196) < 1e-4
+
+
+def test_bad_model_file_raises_valueerror(tmp_path):
+    from basic_pitch_b200.inference import Model
+
+    p = tmp_path / "junk.onnx"
+    p.write_bytes(b"\x08\x01\x12\x04junk")
+    with pytest.raises(ValueError):
+        Model(p)
+
+
+def test_constants_match_reference_values():
+    from basic_pitch_b200 import constants as c
+
+    assert (c.FFT_HOP, c.AUDIO_SAMPLE_RATE, c.ANNOTATIONS_FPS, c.ANNOT_N_FRAMES, c.AUDIO_N_SAMPLES) == (256, 22050, 86, 172, 43844)
+    assert (c.N_FREQ_BINS_NOTES, c.N_FREQ_BINS_CONTOURS, c.HOP_SIZE, c.FRAMES_PER_HOP) == (88, 264, 36164, 142)
+
+
+def test_frames_to_time_matches_oracle():
+    from basic_pitch_b200.note_creation import model_frames_to_time
+
+    for n in (0, 1, 171, 172, 173, 787, 15584):
+        np.testing.assert_array_equal(model_frames_to_time(n), decode_ref.frames_to_time(n))
+
+
+@pytest.mark.parametrize("mn,mx", [(None, None), (110.0, 880.0), (20.0, None), (None, 20000.0), (5000.0, 100.0), (27.5, 4186.0)])
+def test_frequency_range_follows_numpy_slicing(mn, mx):
+    from basic_pitch_b200.note_creation import constrain_frequency, frequency_to_column_range
+
+    a = np.ones((3, 88), np.float32)
+    b = np.ones((3, 88), np.float32)
+    decode_ref.constrain_frequency(a, b, mx, mn)
+    lo, hi = frequency_to_column_range(mn, mx)
+    keep = np.zeros(88, bool)
+    keep[lo:hi] = True
+    np.testing.assert_array_equal(a[0] != 0, keep)
+    c = np.ones((3, 88), np.float32)
+    d = np.ones((3, 88), np.float32)
+    constrain_frequency(c, d, mx, mn)
+    np.testing.assert_array_equal(c, a)
+    np.testing.assert_array_equal(d, b)
+
+
+def test_drop_overlapping_pitch_bends_reference_case():
+    """The hand-made case of reference: tests/test_note_creation.py:21-50."""
+    from basic_pitch_b200.note_creation import drop_overlapping_pitch_bends
+
+    ev = [
+        (0.0, 0.1, 1, 1.0, [0, 1, 2]),
+        (2.0, 2.1, 1, 1.0, [0, 1, 2]),  # overlaps the next
+        (2.0, 2.1, 1, 1.0, [0, 1, 2]),
+        (3.0, 3.2, 1, 1.0, [0, 1, 2]),  # overlaps 3.1-3.3
+        (3.1, 3.3, 1, 1.0, [0, 1, 2]),
+        (5.0, 5.1, 1, 1.0, [0, 1, 2]),
+        (5.1, 5.2, 1, 1.0, [0, 1, 2]),  # touching is not overlapping
+    ]
+    out = drop_overlapping_pitch_bends(ev)
+    got = [e[4] is None for e in out]
+    assert got == [False, True, True, True, True, False, False]
+    assert out == decode_ref.drop_overlapping_pitch_bends(ev)
+
+
+def test_note_events_to_midi_and_smf_writer(tmp_path):
+    from basic_pitch_b200 import note_creation as nc
+
+    events = [
+        (0.5, 1.0, np.int64(60), np.float32(0.5), [0, 1, -1, 3]),
+        (2.0, 2.5, np.int64(64), np.float32(0.996), None),
+        (0.7, 0.9, np.int64(67), np.float32(0.1), [5, 5]),  # overlaps the first -> both lose bends
+    ]
+    mid = nc.note_events_to_midi(events, multiple_pitch_bends=False, midi_tempo=120)
+    (inst,) = mid.instruments
+    assert inst.program == 4
+    assert sorted((n.pitch, n.velocity) for n in inst.notes) == [(60, 64), (64, 126), (67, 13)]
+    assert inst.pitch_bends == []
+    mid2 = nc.note_events_to_midi(events, multiple_pitch_bends=True)
+    assert len(mid2.instruments) == 3
+    bends = [b.pitch for i in mid2.instruments for b in i.pitch_bends]
+    assert bends == [0, 1365, -1365, 4096, 6827, 6827]
+    path = tmp_path / "x.mid"
+    mid2.write(str(path))
+    raw = path.read_bytes()
+    assert raw[:4] == b"MThd" and raw.count(b"MTrk") == 4
+
+
+def test_audio_io_wav_and_resample(tmp_path):
+    from scipy.io import wavfile
+
+    from basic_pitch_b200.audio_io import load_audio
+
+    sr = 22050
+    t = np.arange(sr) / sr
+    x = (0.5 * np.sin(2 * np.pi * 440 * t)).astype(np.float32)
+    p = tmp_path / "a.wav"
+    wavfile.write(p, sr, (x * 32767).astype(np.int16))
+    y, r = load_audio(p)
+    assert r == 22050 and y.dtype == np.float32 and y.shape == x.shape
+    assert np.abs(y - x).max() < 1e-4
+    st = np.stack([x, -x * 0.5], axis=1)
+    p2 = tmp_path / "b.wav"
+    wavfile.write(p2, 44100, np.repeat(st, 2, axis=0))
+    y2, _ = load_audio(p2)
+    assert abs(len(y2) - len(x)) <= 1
+    assert np.abs(y2[100:-100] - 0.25 * x[100 : len(y2) - 100]).max() < 2e-2
+
+
+def test_window_and_unwrap_helpers_match_oracle():
+    from basic_pitch_b200 import inference as inf
+    from oracle import host_ref
+
+    x = np.random.default_rng(0).standard_normal(100000).astype(np.float32)
+    xw = np.concatenate([np.zeros(3840, np.float32), x])
+    wins = np.concatenate([w[None, :, 0] for w, _ in inf.window_audio_file(xw, 36164)])
+    np.testing.assert_array_equal(wins, host_ref.window_audio(x))
+    out = np.random.default_rng(1).random((wins.shape[0], 172, 5)).astype(np.float32)
+    np.testing.assert_array_equal(inf.unwrap_output(out, len(x), 30, 36164), host_ref.unwrap(out, len(x)))
+
+
+def test_numpy_pairwise_sum_model():
+    """The summation order implemented in csrc/decode.cu::np_pairwise_sum, restated in Python, must equal
+    np.mean on strided float32 columns (this is what makes GPU amplitudes bit-identical)."""
+
+    def pw(a):
+        n = len(a)
+        f = np.float32
+        if n < 8:
+            r = f(0)
+            for v in a:
+                r = f(r + v)
+            return r
+        if n <= 128:
+            r = [f(v) for v in a[:8]]
+            i = 8
+            while i < n - (n % 8):
+                for j in range(8):
+                    r[j] = f(r[j] + a[i + j])
+                i += 8
+            res = f(f(f(r[0] + r[1]) + f(r[2] + r[3])) + f(f(r[4] + r[5]) + f(r[6] + r[7])))
+            while i < n:
+                res = f(res + a[i])
+                i += 1
+            return res
+        n2 = n // 2
+        n2 -= n2 % 8
+        return f(pw(a[:n2]) + pw(a[n2:]))
+
+    rng = np.random.default_rng(5)
+    m = rng.random((3100, 88)).astype(np.float32)
+    for n in (1, 2, 7, 8, 9, 15, 16, 17, 100, 127, 128, 129, 130, 255, 256, 257, 1000, 1023, 2999):
+        col = m[5 : 5 + n, 17]
+        assert np.float32(pw(col) / np.float32(n)) == np.mean(col), n
