@@ -154,6 +154,11 @@ struct bp_model {
   DevBuf<int> note_count, slot_start, slot_end, slot_pitch, overflow, d_note_off, d_start, d_end, d_pitch, d_bend_off,
       d_bends;
   int64_t last_forward_n = 0;
+  // optional per-kernel timing (bench.py roofline): CUDA events around one kernel family
+  int profile_which = -1;  // -1 off; 0 contour1, 1 onset1, 2 cqt, 3 decimate chain, 4 small convs
+  std::vector<cudaEvent_t> prof_ev;
+  size_t prof_used = 0;
+  int64_t prof_windows = 0;
 };
 
 namespace {
@@ -248,20 +253,59 @@ int ensure_forward_ws(bp_model* m, int nb) {
   return BP_OK;
 }
 
+struct ProfScope {
+  bp_model* m;
+  cudaStream_t st;
+  bool on;
+  ProfScope(bp_model* m_, int which, cudaStream_t st_) : m(m_), st(st_), on(m_->profile_which == which) {
+    if (on) rec();
+  }
+  ~ProfScope() {
+    if (on) rec();
+  }
+  void rec() {
+    if (m->prof_used == m->prof_ev.size()) {
+      cudaEvent_t e;
+      cudaEventCreate(&e);
+      m->prof_ev.push_back(e);
+    }
+    cudaEventRecord(m->prof_ev[m->prof_used++], st);
+  }
+};
+
 // HCQT + CNN for `nb` windows (nb <= chunk); outputs raw [nb][172][*].
 int forward_chunk(bp_model* m, const float* audio, const WinDesc* desc, int nb, float* note, float* onset,
                   float* contour, cudaStream_t st) {
   float* chain = m->chain.p;
-  for (int s = 0; s < 8; ++s) launch_decimate(audio, desc, chain, s, nb, st);
-  launch_cqt(audio, desc, chain, m->d_derived + DerivedLayout::cqt_wt, m->d_params + ParamLayout::cqt_scale, m->y.p,
-             m->minmax.p, nb, st);
-  launch_lognorm(m->y.p, m->minmax.p, m->d_params + ParamLayout::bn, nb, st);
-  launch_contour1(m->y.p, m->cw, m->c1.p, nb, st);
-  launch_contour2(m->c1.p, m->cw, contour, nb, st);
-  launch_note1(contour, m->cw, m->n1.p, nb, st);
-  launch_note2(m->n1.p, m->cw, note, nb, st);
-  launch_onset1(m->y.p, m->cw, m->o1.p, nb, st);
-  launch_onset2(note, m->o1.p, m->cw, onset, nb, st);
+  if (m->profile_which >= 0) m->prof_windows += nb;
+  {
+    ProfScope ps(m, 3, st);
+    for (int s = 0; s < 8; ++s) launch_decimate(audio, desc, chain, s, nb, st);
+  }
+  {
+    ProfScope ps(m, 2, st);
+    launch_cqt(audio, desc, chain, m->d_derived + DerivedLayout::cqt_wt, m->d_params + ParamLayout::cqt_scale, m->y.p,
+               m->minmax.p, nb, st);
+    launch_lognorm(m->y.p, m->minmax.p, m->d_params + ParamLayout::bn, nb, st);
+  }
+  {
+    ProfScope ps(m, 0, st);
+    launch_contour1(m->y.p, m->cw, m->c1.p, nb, st);
+  }
+  {
+    ProfScope ps(m, 4, st);
+    launch_contour2(m->c1.p, m->cw, contour, nb, st);
+    launch_note1(contour, m->cw, m->n1.p, nb, st);
+    launch_note2(m->n1.p, m->cw, note, nb, st);
+  }
+  {
+    ProfScope ps(m, 1, st);
+    launch_onset1(m->y.p, m->cw, m->o1.p, nb, st);
+  }
+  {
+    ProfScope ps(m, 4, st);
+    launch_onset2(note, m->o1.p, m->cw, onset, nb, st);
+  }
   CKL();
   m->launches += 8 + 2 + 1 + 6;
   return BP_OK;
@@ -367,6 +411,7 @@ void bp_model_destroy(bp_model_t* m) {
   if (m->d_params) cudaFree(m->d_params);
   if (m->d_derived) cudaFree(m->d_derived);
   if (m->d_gauss) cudaFree(m->d_gauss);
+  for (cudaEvent_t e : m->prof_ev) cudaEventDestroy(e);
   if (m->stream) cudaStreamDestroy(m->stream);
   delete m;
 }
@@ -713,6 +758,31 @@ int bp_transcribe_host(bp_model_t* m, const float* h_audio, const int64_t* h_sam
       CK(cudaMemcpyAsync(h_contour, m->st_contour.p, sizeof(float) * total_frames * kContourBins, cudaMemcpyDeviceToHost, st));
   }
   CK(cudaStreamSynchronize(st));
+  return BP_OK;
+}
+
+int bp_model_profile(bp_model_t* m, int which) {
+  if (!m) return fail(BP_E_INVALID, "bp_model_profile: null model");
+  if (which < -1 || which > 4) return fail(BP_E_INVALID, "bp_model_profile: unknown kernel family");
+  m->profile_which = which;
+  m->prof_used = 0;
+  m->prof_windows = 0;
+  return BP_OK;
+}
+
+int bp_model_profile_read(bp_model_t* m, double* total_ms, int64_t* n_intervals, int64_t* n_windows) {
+  if (!m || !total_ms || !n_intervals || !n_windows) return fail(BP_E_INVALID, "bp_model_profile_read: null argument");
+  DeviceGuard g(m->device);
+  CK(cudaDeviceSynchronize());
+  double total = 0.0;
+  for (size_t i = 0; i + 1 < m->prof_used; i += 2) {
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, m->prof_ev[i], m->prof_ev[i + 1]));
+    total += ms;
+  }
+  *total_ms = total;
+  *n_intervals = (int64_t)(m->prof_used / 2);
+  *n_windows = m->prof_windows;
   return BP_OK;
 }
 

@@ -158,6 +158,14 @@ int64_t bp_model_chunk_windows(const bp_model_t* m);
  * (tcgen05, split-bf16 operands, FP32 accumulate) where implemented.  Default: best available. */
 int bp_model_set_path(bp_model_t* m, int path);
 
+/* Per-kernel device timing for the roofline line of bench.py: records CUDA events on the launching
+ * stream around every launch of one kernel family (0 = contour conv 3x39, 1 = onset conv 5x5,
+ * 2 = CQT projection + log-normalise, 3 = decimation chain, 4 = the remaining small convs;
+ * -1 = off, the default) and resets the accumulators.  bp_model_profile_read synchronises the device
+ * and returns the summed interval time, the number of intervals and the windows processed. */
+int bp_model_profile(bp_model_t* m, int which);
+int bp_model_profile_read(bp_model_t* m, double* total_ms, int64_t* n_intervals, int64_t* n_windows);
+
 #ifdef __cplusplus
 }
 #endif

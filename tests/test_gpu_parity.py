@@ -46,7 +46,7 @@ def test_forward_vs_oracle_including_activations(model, weights_np):
     ref = model_ref.forward(x, weights_np, return_intermediates=True)
     lib = _lib.load()
     n = x.shape[0]
-    for which, key, shape, tol in ((0, "_y", (n, 172, 309), 2e-5), (1, "_c1", (n, 8, 172, 264), 2e-4),
+    for which, key, shape, tol in ((0, "_y", (n, 172, 309), 2e-4), (1, "_c1", (n, 8, 172, 264), 2e-4),
                                    (2, "_n1", (n, 32, 172, 88), 2e-4), (3, "_o1", (n, 32, 172, 88), 2e-4)):
         buf = np.empty(shape, np.float32)
         lib.bp_debug_activation(model.handle, which, buf.ctypes.data, n)
