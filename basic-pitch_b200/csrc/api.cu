@@ -136,8 +136,16 @@ struct bp_model {
   float* d_derived = nullptr;
   double* d_gauss = nullptr;
   CnnWeights cw{};
-  int chunk = 64;
-  int path = 0;
+  int chunk = 128;
+  int path = 1;  // 0 = FP32 FFMA everywhere, 1 = tcgen05 contour conv
+  int n_sms = 148;
+  std::vector<float> h_contour1_w;
+  TcContourPlan tc_plan;
+  TcContourDev tc_dev{};
+  DevBuf<uint16_t> tc_tiles;
+  DevBuf<int> tc_tile_seq, tc_step_use_off;
+  DevBuf<uint32_t> tc_use_words;
+  DevBuf<__nv_bfloat16> yhl;
   int64_t launches = 0;
   // forward workspace (chunk windows)
   DevBuf<float> chain, y, c1, n1, o1, raw_note, raw_onset, raw_contour;
@@ -154,6 +162,7 @@ struct bp_model {
   DevBuf<int> note_count, slot_start, slot_end, slot_pitch, overflow, d_note_off, d_start, d_end, d_pitch, d_bend_off,
       d_bends;
   int64_t last_forward_n = 0;
+  int last_path = 0;
   // optional per-kernel timing (bench.py roofline): CUDA events around one kernel family
   int profile_which = -1;  // -1 off; 0 contour1, 1 onset1, 2 cqt, 3 decimate chain, 4 small convs
   std::vector<cudaEvent_t> prof_ev;
@@ -240,6 +249,27 @@ int derive(bp_model* m, cudaStream_t st) {
   upload_lowpass(m->d_params + ParamLayout::lowpass, st);
   CKL();
   m->launches += 1;
+  // tensor-core plan of the contour conv: split-bf16 Toeplitz weight tiles + MMA programs (host-built)
+  m->h_contour1_w.resize(8 * 8 * 3 * 39);
+  CK(cudaMemcpyAsync(m->h_contour1_w.data(), m->d_params + ParamLayout::contour1_w, sizeof(float) * 7488,
+                     cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  m->tc_plan.build(m->h_contour1_w.data());
+  const TcContourPlan& pl = m->tc_plan;
+  CK(m->tc_tiles.reserve(pl.tiles.size()));
+  CK(m->tc_tile_seq.reserve(pl.tile_seq.size()));
+  CK(m->tc_step_use_off.reserve(pl.step_use_off.size()));
+  CK(m->tc_use_words.reserve(pl.use_words.size()));
+  CK(cudaMemcpyAsync(m->tc_tiles.p, pl.tiles.data(), pl.tiles.size() * 2, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(m->tc_tile_seq.p, pl.tile_seq.data(), pl.tile_seq.size() * 4, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(m->tc_step_use_off.p, pl.step_use_off.data(), pl.step_use_off.size() * 4, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(m->tc_use_words.p, pl.use_words.data(), pl.use_words.size() * 4, cudaMemcpyHostToDevice, st));
+  CK(cudaStreamSynchronize(st));
+  m->tc_dev.tiles = m->tc_tiles.p;
+  m->tc_dev.tile_seq = m->tc_tile_seq.p;
+  m->tc_dev.step_use_off = m->tc_step_use_off.p;
+  m->tc_dev.use_words = m->tc_use_words.p;
+  for (int g = 0; g < 6; ++g) m->tc_dev.group_step_off[g] = pl.group_step_off[g];
   return BP_OK;
 }
 
@@ -250,6 +280,7 @@ int ensure_forward_ws(bp_model* m, int nb) {
   CK(m->n1.reserve((size_t)nb * 32 * kFrames * kPitches));
   CK(m->o1.reserve((size_t)nb * 32 * kFrames * kPitches));
   CK(m->minmax.reserve((size_t)nb * 2));
+  CK(m->yhl.reserve((size_t)2 * 40 * 8 * tc_rows_total(nb)));
   return BP_OK;
 }
 
@@ -290,11 +321,17 @@ int forward_chunk(bp_model* m, const float* audio, const WinDesc* desc, int nb, 
   }
   {
     ProfScope ps(m, 0, st);
-    launch_contour1(m->y.p, m->cw, m->c1.p, nb, st);
+    if (m->path == 1)
+      launch_contour1_tc(m->y.p, m->yhl.p, m->tc_dev, m->cw.contour1_b, m->c1.p, nb, m->n_sms, st);
+    else
+      launch_contour1(m->y.p, m->cw, m->c1.p, nb, st);
   }
   {
     ProfScope ps(m, 4, st);
-    launch_contour2(m->c1.p, m->cw, contour, nb, st);
+    if (m->path == 1)
+      launch_contour2_nhwc(m->c1.p, m->cw, contour, nb, st);
+    else
+      launch_contour2(m->c1.p, m->cw, contour, nb, st);
     launch_note1(contour, m->cw, m->n1.p, nb, st);
     launch_note2(m->n1.p, m->cw, note, nb, st);
   }
@@ -307,7 +344,8 @@ int forward_chunk(bp_model* m, const float* audio, const WinDesc* desc, int nb, 
     launch_onset2(note, m->o1.p, m->cw, onset, nb, st);
   }
   CKL();
-  m->launches += 8 + 2 + 1 + 6;
+  m->launches += 8 + 2 + 1 + 6 + (m->path == 1 ? 1 : 0);
+  m->last_path = m->path;
   return BP_OK;
 }
 
@@ -389,6 +427,8 @@ int bp_model_create(const void* blob, size_t nbytes, int device, bp_model_t** ou
                      D + DerivedLayout::note2_wT,    P + ParamLayout::note2_b,    D + DerivedLayout::onset1_wT,
                      P + ParamLayout::onset1_b,      D + DerivedLayout::onset2_wT, P + ParamLayout::onset2_b};
   cnn_setup();
+  tc_setup();
+  m->n_sms = prop.multiProcessorCount;
   rc = derive(m, m->stream);
   if (rc) return rc;
   CK(cudaStreamSynchronize(m->stream));
@@ -407,7 +447,8 @@ void bp_model_destroy(bp_model_t* m) {
   m->energy.release(); m->d_amp.release(); m->candbits.release(); m->max_onset.release(); m->max_fd.release();
   m->note_count.release(); m->slot_start.release(); m->slot_end.release(); m->slot_pitch.release();
   m->overflow.release(); m->d_note_off.release(); m->d_start.release(); m->d_end.release(); m->d_pitch.release();
-  m->d_bend_off.release(); m->d_bends.release();
+  m->d_bend_off.release(); m->d_bends.release(); m->tc_tiles.release(); m->tc_tile_seq.release();
+  m->tc_step_use_off.release(); m->tc_use_words.release(); m->yhl.release();
   if (m->d_params) cudaFree(m->d_params);
   if (m->d_derived) cudaFree(m->d_derived);
   if (m->d_gauss) cudaFree(m->d_gauss);
@@ -439,7 +480,7 @@ int bp_model_refresh(bp_model_t* m) {
 
 int bp_model_set_path(bp_model_t* m, int path) {
   if (!m) return fail(BP_E_INVALID, "bp_model_set_path: null model");
-  if (path != 0) return fail(BP_E_INVALID, "bp_model_set_path: only path 0 (FP32 FFMA) is built in this version");
+  if (path != 0 && path != 1) return fail(BP_E_INVALID, "bp_model_set_path: path must be 0 (FP32 FFMA) or 1 (tcgen05 contour conv)");
   m->path = path;
   return BP_OK;
 }
@@ -761,6 +802,22 @@ int bp_transcribe_host(bp_model_t* m, const float* h_audio, const int64_t* h_sam
   return BP_OK;
 }
 
+int bp_debug_tc_plan(const float* contour1_w, int32_t* sizes, uint16_t* tiles, int32_t* tile_seq, int32_t* step_use_off,
+                     uint32_t* use_words, int32_t* group_step_off) {
+  if (!contour1_w || !sizes) return fail(BP_E_INVALID, "bp_debug_tc_plan: null argument");
+  TcContourPlan pl;
+  pl.build(contour1_w);
+  sizes[0] = pl.n_tiles;
+  sizes[1] = (int32_t)pl.tile_seq.size();
+  sizes[2] = (int32_t)pl.use_words.size();
+  if (tiles) std::memcpy(tiles, pl.tiles.data(), pl.tiles.size() * 2);
+  if (tile_seq) std::memcpy(tile_seq, pl.tile_seq.data(), pl.tile_seq.size() * 4);
+  if (step_use_off) std::memcpy(step_use_off, pl.step_use_off.data(), pl.step_use_off.size() * 4);
+  if (use_words) std::memcpy(use_words, pl.use_words.data(), pl.use_words.size() * 4);
+  if (group_step_off) std::memcpy(group_step_off, pl.group_step_off.data(), 6 * 4);
+  return BP_OK;
+}
+
 int bp_model_profile(bp_model_t* m, int which) {
   if (!m) return fail(BP_E_INVALID, "bp_model_profile: null model");
   if (which < -1 || which > 4) return fail(BP_E_INVALID, "bp_model_profile: unknown kernel family");
@@ -802,6 +859,14 @@ int bp_debug_activation(bp_model_t* m, int which, float* h_out, int64_t n_window
   }
   CK(cudaDeviceSynchronize());
   CK(cudaMemcpy(h_out, src, sizeof(float) * per * n_windows, cudaMemcpyDeviceToHost));
+  if (which == 1 && m->last_path == 1) {  // tensor-core path keeps this activation channels-last: return NCHW
+    std::vector<float> tmp(h_out, h_out + per * n_windows);
+    for (int64_t b = 0; b < n_windows; ++b)
+      for (int t = 0; t < kFrames; ++t)
+        for (int f = 0; f < kContourBins; ++f)
+          for (int c = 0; c < 8; ++c)
+            h_out[((b * 8 + c) * kFrames + t) * kContourBins + f] = tmp[((b * kFrames + t) * kContourBins + f) * 8 + c];
+  }
   return BP_OK;
 }
 

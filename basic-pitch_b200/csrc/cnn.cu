@@ -36,6 +36,15 @@ struct PlanarIn {
     return __ldg(p + (((size_t)b * C + ci) * kFrames + t) * W + g);
   }
 };
+// channels-last activations [B][172][W][C] (what the tensor-core contour kernel writes)
+template <int C, int W>
+struct NhwcIn {
+  const float* p;
+  __device__ __forceinline__ float load(int b, int ci, int t, int g) const {
+    if ((unsigned)t >= (unsigned)kFrames || (unsigned)g >= (unsigned)W) return 0.f;
+    return __ldg(p + (((size_t)b * kFrames + t) * W + g) * C + ci);
+  }
+};
 // channel 0 = note posteriorgram [B][172][88], channels 1..32 = onset conv1 output [B][32][172][88]
 struct ConcatIn {
   const float* note;
@@ -177,6 +186,7 @@ static void set_attr() {
 void cnn_setup() {
   set_attr<Contour1Cfg, StackIn>();
   set_attr<Contour2Cfg, PlanarIn<8, 264>>();
+  set_attr<Contour2Cfg, NhwcIn<8, 264>>();
   set_attr<Note1Cfg, PlanarIn<1, 264>>();
   set_attr<Note2Cfg, PlanarIn<32, 88>>();
   set_attr<Onset1Cfg, StackIn>();
@@ -194,6 +204,9 @@ void launch_contour1(const float* y, const CnnWeights& w, float* c1, int n, cuda
 }
 void launch_contour2(const float* c1, const CnnWeights& w, float* contour, int n, cudaStream_t st) {
   launch<Contour2Cfg>(PlanarIn<8, 264>{c1}, w.contour2_wT, w.contour2_b, contour, n, st);
+}
+void launch_contour2_nhwc(const float* c1, const CnnWeights& w, float* contour, int n, cudaStream_t st) {
+  launch<Contour2Cfg>(NhwcIn<8, 264>{c1}, w.contour2_wT, w.contour2_b, contour, n, st);
 }
 void launch_note1(const float* contour, const CnnWeights& w, float* n1, int n, cudaStream_t st) {
   launch<Note1Cfg>(PlanarIn<1, 264>{contour}, w.note1_wT, w.note1_b, n1, n, st);

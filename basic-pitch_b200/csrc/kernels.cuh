@@ -1,5 +1,10 @@
 // Launch wrappers of the hot-path kernels (host-callable; all asynchronous on `st`).
 #pragma once
+#include <cuda_bf16.h>
+
+#include <cstring>
+#include <vector>
+
 #include "common.cuh"
 
 namespace bp {
@@ -30,6 +35,30 @@ void launch_note2(const float* n1, const CnnWeights& w, float* note, int n_windo
 void launch_onset1(const float* y, const CnnWeights& w, float* o1, int n_windows, cudaStream_t st);
 void launch_onset2(const float* note, const float* o1, const CnnWeights& w, float* onset, int n_windows,
                    cudaStream_t st);
+
+void launch_contour2_nhwc(const float* c1_nhwc, const CnnWeights& w, float* contour, int n_windows, cudaStream_t st);
+
+// ---- tc_contour.cu (tcgen05 path of the contour conv) ---------------------------------------------
+struct TcContourPlan {  // host side: weight tiles + the per-frequency-group MMA programs
+  std::vector<uint16_t> tiles;       // n_tiles x 4096 bf16 : [plane hi/lo][k-chunk 2][n 128][8]
+  std::vector<int> tile_seq;         // per step: tile id
+  std::vector<int> step_use_off;     // [n_steps + 1] into use_words
+  std::vector<uint32_t> use_words;   // ft_local | q << 2 | dt << 7 | first << 9
+  std::vector<int> group_step_off;   // [6]
+  int n_tiles = 0;
+  void build(const float* contour1_w /* [8][8][3][39] */);
+};
+struct TcContourDev {
+  const uint16_t* tiles;
+  const int* tile_seq;
+  const int* step_use_off;
+  const uint32_t* use_words;
+  int group_step_off[6];
+};
+int tc_rows_total(int n_windows);
+void tc_setup();
+void launch_contour1_tc(const float* y, __nv_bfloat16* yhl, const TcContourDev& dev, const float* bias, float* c1_nhwc,
+                        int n_windows, int n_sms, cudaStream_t st);
 
 // ---- unwrap (api.cu) / decode.cu ----------------------------------------------------------------
 struct DecodeParamsDev {

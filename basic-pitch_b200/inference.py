@@ -95,6 +95,10 @@ class Model:
     def handle(self) -> C.c_void_p:
         return self._h
 
+    def set_path(self, path: int) -> None:
+        """0 = FP32 FFMA kernels everywhere (on-device accuracy reference), 1 = tcgen05 tensor-core contour conv (default)."""
+        self._lib.bp_model_set_path(self._h, int(path))
+
     @property
     def launch_count(self) -> int:
         return int(self._lib.bp_model_launch_count(self._h))

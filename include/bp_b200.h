@@ -158,6 +158,13 @@ int64_t bp_model_chunk_windows(const bp_model_t* m);
  * (tcgen05, split-bf16 operands, FP32 accumulate) where implemented.  Default: best available. */
 int bp_model_set_path(bp_model_t* m, int path);
 
+/* Host-only (no GPU needed): builds the tensor-core plan of the contour conv (split-bf16 Toeplitz weight tiles and
+ * the per-frequency-group MMA programs, csrc/tc_contour.cu) for the given [8][8][3][39] weights, so that tests can
+ * emulate the program on the CPU.  sizes[3] = {n_tiles, n_steps, n_uses}; pass NULL arrays to query sizes first.
+ * tiles: n_tiles x 4096 bf16 ([plane hi/lo][k-chunk 2][n 128][8]); step_use_off has n_steps + 1 entries. */
+int bp_debug_tc_plan(const float* contour1_w, int32_t* sizes, uint16_t* tiles, int32_t* tile_seq, int32_t* step_use_off,
+                     uint32_t* use_words, int32_t* group_step_off);
+
 /* Per-kernel device timing for the roofline line of bench.py: records CUDA events on the launching
  * stream around every launch of one kernel family (0 = contour conv 3x39, 1 = onset conv 5x5,
  * 2 = CQT projection + log-normalise, 3 = decimation chain, 4 = the remaining small convs;

@@ -59,6 +59,34 @@ def test_forward_vs_oracle_including_activations(model, weights_np):
     assert np.all(np.isfinite(got["note"])) and np.all(np.isfinite(got["contour"]))
 
 
+def test_tensor_core_contour_conv_matches_fp32_path(model):
+    """tcgen05 path (split-bf16 operands, fp32 accumulate in TMEM) vs the FP32 FFMA kernel of the same layer, on device:
+    the activation itself and the three posteriorgrams; includes windows that end in ragged M-tiles (9 and 130 windows)."""
+    from basic_pitch_b200 import _lib, synth
+
+    lib = _lib.load()
+    for n in (9, 130):
+        x = np.concatenate([_edge_windows(), synth.window_batch(n - 9, seed=4)]) if n > 9 else _edge_windows()
+        try:
+            model.set_path(0)
+            ref = model.predict(x)
+            c_ref = np.empty((min(n, 128), 8, 172, 264), np.float32)
+            if n <= 128:
+                lib.bp_debug_activation(model.handle, 1, c_ref.ctypes.data, n)
+            model.set_path(1)
+            got = model.predict(x)
+            if n <= 128:
+                c_got = np.empty_like(c_ref)
+                lib.bp_debug_activation(model.handle, 1, c_got.ctypes.data, n)
+                err = np.abs(c_got - c_ref).max()
+                assert err < 5e-4, f"contour conv activation: max-abs {err:.3e} (n={n})"
+        finally:
+            model.set_path(1)
+        for k in ref:
+            err = np.abs(got[k] - ref[k]).max()
+            assert err < 1e-4, f"{k}: tensor-core vs FP32 path max-abs {err:.3e} (n={n})"
+
+
 def test_vocadito_golden_posteriorgrams(model, golden_dir, weights_np):
     """reference: tests/test_inference.py:43-70 — shapes, and values vs the golden npz."""
     from oracle import host_ref, model_ref
