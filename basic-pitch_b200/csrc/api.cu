@@ -136,15 +136,16 @@ struct bp_model {
   float* d_derived = nullptr;
   double* d_gauss = nullptr;
   CnnWeights cw{};
-  int chunk = 128;
+  int chunk = 217;  // 217 windows = 296 M-tiles of 128 rows = 2 per SM on 148 SMs
   int path = 1;  // 0 = FP32 FFMA everywhere, 1 = tcgen05 contour conv
   int n_sms = 148;
-  std::vector<float> h_contour1_w;
-  TcContourPlan tc_plan;
-  TcContourDev tc_dev{};
-  DevBuf<uint16_t> tc_tiles;
-  DevBuf<int> tc_tile_seq, tc_step_use_off;
-  DevBuf<uint32_t> tc_use_words;
+  struct TcLayer {
+    TcConvPlan plan;
+    TcConvDev dev{};
+    DevBuf<uint16_t> tiles;
+    DevBuf<int> tile_seq, group_step_off, group_use_off, group_ft;
+    DevBuf<uint32_t> use_words;
+  } tc_contour, tc_onset;
   DevBuf<__nv_bfloat16> yhl;
   int64_t launches = 0;
   // forward workspace (chunk windows)
@@ -249,27 +250,36 @@ int derive(bp_model* m, cudaStream_t st) {
   upload_lowpass(m->d_params + ParamLayout::lowpass, st);
   CKL();
   m->launches += 1;
-  // tensor-core plan of the contour conv: split-bf16 Toeplitz weight tiles + MMA programs (host-built)
-  m->h_contour1_w.resize(8 * 8 * 3 * 39);
-  CK(cudaMemcpyAsync(m->h_contour1_w.data(), m->d_params + ParamLayout::contour1_w, sizeof(float) * 7488,
-                     cudaMemcpyDeviceToHost, st));
+  // tensor-core plans: split-bf16 Toeplitz weight tiles + MMA programs (host-built from the parameter block)
+  std::vector<float> hw(7488 + 6400);
+  CK(cudaMemcpyAsync(hw.data(), m->d_params + ParamLayout::contour1_w, sizeof(float) * 7488, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(hw.data() + 7488, m->d_params + ParamLayout::onset1_w, sizeof(float) * 6400, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
-  m->tc_plan.build(m->h_contour1_w.data());
-  const TcContourPlan& pl = m->tc_plan;
-  CK(m->tc_tiles.reserve(pl.tiles.size()));
-  CK(m->tc_tile_seq.reserve(pl.tile_seq.size()));
-  CK(m->tc_step_use_off.reserve(pl.step_use_off.size()));
-  CK(m->tc_use_words.reserve(pl.use_words.size()));
-  CK(cudaMemcpyAsync(m->tc_tiles.p, pl.tiles.data(), pl.tiles.size() * 2, cudaMemcpyHostToDevice, st));
-  CK(cudaMemcpyAsync(m->tc_tile_seq.p, pl.tile_seq.data(), pl.tile_seq.size() * 4, cudaMemcpyHostToDevice, st));
-  CK(cudaMemcpyAsync(m->tc_step_use_off.p, pl.step_use_off.data(), pl.step_use_off.size() * 4, cudaMemcpyHostToDevice, st));
-  CK(cudaMemcpyAsync(m->tc_use_words.p, pl.use_words.data(), pl.use_words.size() * 4, cudaMemcpyHostToDevice, st));
-  CK(cudaStreamSynchronize(st));
-  m->tc_dev.tiles = m->tc_tiles.p;
-  m->tc_dev.tile_seq = m->tc_tile_seq.p;
-  m->tc_dev.step_use_off = m->tc_step_use_off.p;
-  m->tc_dev.use_words = m->tc_use_words.p;
-  for (int g = 0; g < 6; ++g) m->tc_dev.group_step_off[g] = pl.group_step_off[g];
+  const TcConvSpec specs[2] = {tc_contour_spec(), tc_onset_spec()};
+  bp_model::TcLayer* layers[2] = {&m->tc_contour, &m->tc_onset};
+  const float* wsrc[2] = {hw.data(), hw.data() + 7488};
+  for (int l = 0; l < 2; ++l) {
+    bp_model::TcLayer& L = *layers[l];
+    L.plan.build(specs[l], wsrc[l]);
+    const TcConvPlan& pl = L.plan;
+    for (int g = 0; g < pl.n_groups; ++g)
+      if (pl.group_use_off[g + 1] - pl.group_use_off[0] > 1664)
+        return fail(BP_E_INVALID, "tensor-core program does not fit its shared-memory staging area");
+    CK(L.tiles.reserve(pl.tiles.size()));
+    CK(L.tile_seq.reserve(pl.tile_seq.size()));
+    CK(L.use_words.reserve(pl.use_words.size()));
+    CK(L.group_step_off.reserve(pl.group_step_off.size()));
+    CK(L.group_use_off.reserve(pl.group_use_off.size()));
+    CK(L.group_ft.reserve(pl.group_ft.size()));
+    CK(cudaMemcpyAsync(L.tiles.p, pl.tiles.data(), pl.tiles.size() * 2, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(L.tile_seq.p, pl.tile_seq.data(), pl.tile_seq.size() * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(L.use_words.p, pl.use_words.data(), pl.use_words.size() * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(L.group_step_off.p, pl.group_step_off.data(), pl.group_step_off.size() * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(L.group_use_off.p, pl.group_use_off.data(), pl.group_use_off.size() * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(L.group_ft.p, pl.group_ft.data(), pl.group_ft.size() * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));
+    L.dev = TcConvDev{pl.spec, L.tiles.p, L.tile_seq.p, L.use_words.p, L.group_step_off.p, L.group_use_off.p, L.group_ft.p, pl.n_groups};
+  }
   return BP_OK;
 }
 
@@ -321,10 +331,12 @@ int forward_chunk(bp_model* m, const float* audio, const WinDesc* desc, int nb, 
   }
   {
     ProfScope ps(m, 0, st);
-    if (m->path == 1)
-      launch_contour1_tc(m->y.p, m->yhl.p, m->tc_dev, m->cw.contour1_b, m->c1.p, nb, m->n_sms, st);
-    else
+    if (m->path == 1) {
+      launch_y_split(m->y.p, m->yhl.p, nb, st);
+      launch_conv_tc(m->yhl.p, m->tc_contour.dev, m->cw.contour1_b, m->c1.p, nb, m->n_sms, st);
+    } else {
       launch_contour1(m->y.p, m->cw, m->c1.p, nb, st);
+    }
   }
   {
     ProfScope ps(m, 4, st);
@@ -337,11 +349,17 @@ int forward_chunk(bp_model* m, const float* audio, const WinDesc* desc, int nb, 
   }
   {
     ProfScope ps(m, 1, st);
-    launch_onset1(m->y.p, m->cw, m->o1.p, nb, st);
+    if (m->path == 1)
+      launch_conv_tc(m->yhl.p, m->tc_onset.dev, m->cw.onset1_b, m->o1.p, nb, m->n_sms, st);
+    else
+      launch_onset1(m->y.p, m->cw, m->o1.p, nb, st);
   }
   {
     ProfScope ps(m, 4, st);
-    launch_onset2(note, m->o1.p, m->cw, onset, nb, st);
+    if (m->path == 1)
+      launch_onset2_nhwc(note, m->o1.p, m->cw, onset, nb, st);
+    else
+      launch_onset2(note, m->o1.p, m->cw, onset, nb, st);
   }
   CKL();
   m->launches += 8 + 2 + 1 + 6 + (m->path == 1 ? 1 : 0);
@@ -447,8 +465,12 @@ void bp_model_destroy(bp_model_t* m) {
   m->energy.release(); m->d_amp.release(); m->candbits.release(); m->max_onset.release(); m->max_fd.release();
   m->note_count.release(); m->slot_start.release(); m->slot_end.release(); m->slot_pitch.release();
   m->overflow.release(); m->d_note_off.release(); m->d_start.release(); m->d_end.release(); m->d_pitch.release();
-  m->d_bend_off.release(); m->d_bends.release(); m->tc_tiles.release(); m->tc_tile_seq.release();
-  m->tc_step_use_off.release(); m->tc_use_words.release(); m->yhl.release();
+  m->d_bend_off.release(); m->d_bends.release();
+  m->yhl.release();
+  for (bp_model::TcLayer* L : {&m->tc_contour, &m->tc_onset}) {
+    L->tiles.release(); L->tile_seq.release(); L->use_words.release(); L->group_step_off.release();
+    L->group_use_off.release(); L->group_ft.release();
+  }
   if (m->d_params) cudaFree(m->d_params);
   if (m->d_derived) cudaFree(m->d_derived);
   if (m->d_gauss) cudaFree(m->d_gauss);
@@ -802,19 +824,21 @@ int bp_transcribe_host(bp_model_t* m, const float* h_audio, const int64_t* h_sam
   return BP_OK;
 }
 
-int bp_debug_tc_plan(const float* contour1_w, int32_t* sizes, uint16_t* tiles, int32_t* tile_seq, int32_t* step_use_off,
-                     uint32_t* use_words, int32_t* group_step_off) {
-  if (!contour1_w || !sizes) return fail(BP_E_INVALID, "bp_debug_tc_plan: null argument");
-  TcContourPlan pl;
-  pl.build(contour1_w);
+int bp_debug_tc_plan(int which, const float* w, int32_t* sizes, uint16_t* tiles, int32_t* tile_seq, uint32_t* use_words,
+                     int32_t* group_step_off, int32_t* group_use_off, int32_t* group_ft) {
+  if (!w || !sizes || which < 0 || which > 1) return fail(BP_E_INVALID, "bp_debug_tc_plan: bad argument");
+  TcConvPlan pl;
+  pl.build(which == 0 ? tc_contour_spec() : tc_onset_spec(), w);
   sizes[0] = pl.n_tiles;
   sizes[1] = (int32_t)pl.tile_seq.size();
   sizes[2] = (int32_t)pl.use_words.size();
+  sizes[3] = pl.n_groups;
   if (tiles) std::memcpy(tiles, pl.tiles.data(), pl.tiles.size() * 2);
   if (tile_seq) std::memcpy(tile_seq, pl.tile_seq.data(), pl.tile_seq.size() * 4);
-  if (step_use_off) std::memcpy(step_use_off, pl.step_use_off.data(), pl.step_use_off.size() * 4);
   if (use_words) std::memcpy(use_words, pl.use_words.data(), pl.use_words.size() * 4);
-  if (group_step_off) std::memcpy(group_step_off, pl.group_step_off.data(), 6 * 4);
+  if (group_step_off) std::memcpy(group_step_off, pl.group_step_off.data(), pl.group_step_off.size() * 4);
+  if (group_use_off) std::memcpy(group_use_off, pl.group_use_off.data(), pl.group_use_off.size() * 4);
+  if (group_ft) std::memcpy(group_ft, pl.group_ft.data(), pl.group_ft.size() * 4);
   return BP_OK;
 }
 
@@ -859,13 +883,14 @@ int bp_debug_activation(bp_model_t* m, int which, float* h_out, int64_t n_window
   }
   CK(cudaDeviceSynchronize());
   CK(cudaMemcpy(h_out, src, sizeof(float) * per * n_windows, cudaMemcpyDeviceToHost));
-  if (which == 1 && m->last_path == 1) {  // tensor-core path keeps this activation channels-last: return NCHW
+  if ((which == 1 || which == 3) && m->last_path == 1) {  // tensor-core path keeps these channels-last: return NCHW
+    const int C = which == 1 ? 8 : 32, Wd = which == 1 ? kContourBins : kPitches;
     std::vector<float> tmp(h_out, h_out + per * n_windows);
     for (int64_t b = 0; b < n_windows; ++b)
       for (int t = 0; t < kFrames; ++t)
-        for (int f = 0; f < kContourBins; ++f)
-          for (int c = 0; c < 8; ++c)
-            h_out[((b * 8 + c) * kFrames + t) * kContourBins + f] = tmp[((b * kFrames + t) * kContourBins + f) * 8 + c];
+        for (int f = 0; f < Wd; ++f)
+          for (int c = 0; c < C; ++c)
+            h_out[((b * C + c) * kFrames + t) * Wd + f] = tmp[((b * kFrames + t) * Wd + f) * C + c];
   }
   return BP_OK;
 }

@@ -56,6 +56,17 @@ struct ConcatIn {
   }
 };
 
+// same, with the onset conv1 output channels-last [B][172][88][32] (tensor-core path)
+struct ConcatNhwcIn {
+  const float* note;
+  const float* o1;
+  __device__ __forceinline__ float load(int b, int ci, int t, int g) const {
+    if ((unsigned)t >= (unsigned)kFrames || (unsigned)g >= (unsigned)kPitches) return 0.f;
+    if (ci == 0) return __ldg(note + ((size_t)b * kFrames + t) * kPitches + g);
+    return __ldg(o1 + (((size_t)b * kFrames + t) * kPitches + g) * 32 + (ci - 1));
+  }
+};
+
 enum { ACT_RELU = 0, ACT_SIGMOID = 1 };
 
 template <int CIN_, int CIC_, int COUT_, int COB_, int KH_, int KW_, int SF_, int PT_, int PL_, int WOUT_, int TT_,
@@ -170,27 +181,134 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) conv_kernel(In in, const floa
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Single-output-channel convolutions (contour2 8->1 5x5, note2 32->1 7x3, onset2 33->1 3x3) + sigmoid.
+// With one output channel there is no channel blocking to amortise input loads, so each thread owns a
+// 4 frames x 4 bins register tile and keeps the (4+KH-1) x (4+KW-1) input patch of the current channel in
+// registers: every shared-memory load feeds up to KH*KW*16/patch FMAs.  The patch columns of a thread are
+// contiguous, so rows are stored de-interleaved into 4 phases (x -> [x & 3][x >> 2]) to keep lanes on
+// consecutive words.  Weights are warp-uniform broadcast loads from shared memory.
+// ------------------------------------------------------------------------------------------------
+template <int CIN_, int CIC_, int KH_, int KW_, int PT_, int PL_, int WOUT_, int TR_>
+struct Conv1Cfg {
+  static constexpr int CIN = CIN_, CIC = CIC_, KH = KH_, KW = KW_, PT = PT_, PL = PL_, WOUT = WOUT_, TR = TR_;
+  static constexpr int Q = 4, P = 4, FL = 22, FT = FL * P;       // 88 bins per tile
+  static constexpr int TT = TR * Q;                             // frames per tile
+  static constexpr int THREADS = FL * TR;
+  static constexpr int ROWS = TT + KH - 1;
+  static constexpr int NEED = FT + KW - 1;
+  static constexpr int PH = (NEED + 3) / 4 + 1;                 // words per phase
+  static constexpr int RS = 4 * PH;
+  static constexpr int IN_ELEMS = CIC * ROWS * RS;
+  static constexpr int W_ELEMS = CIN * KH * KW;
+  static constexpr int SMEM_BYTES = (IN_ELEMS + W_ELEMS) * 4;
+  static constexpr int FTILES = (WOUT + FT - 1) / FT;
+  static constexpr int TTILES = (kFrames + TT - 1) / TT;
+  static_assert(CIN % CIC == 0, "channel blocking");
+};
+
+template <class Cfg, class In>
+__global__ void __launch_bounds__(Cfg::THREADS) conv1_kernel(In in, const float* __restrict__ w /* [CIN*KH*KW] */,
+                                                             const float* __restrict__ bias,
+                                                             float* __restrict__ out /* [B][172][WOUT] */) {
+  extern __shared__ float smem[];
+  float* in_s = smem;
+  float* w_s = smem + Cfg::IN_ELEMS;
+  const int b = blockIdx.y;
+  const int ftile = blockIdx.x % Cfg::FTILES, ttile = blockIdx.x / Cfg::FTILES;
+  const int f0 = ftile * Cfg::FT, t0 = ttile * Cfg::TT;
+  const int tid = threadIdx.x;
+  const int fp = tid % Cfg::FL, tq = tid / Cfg::FL;
+
+  for (int e = tid; e < Cfg::W_ELEMS; e += Cfg::THREADS) w_s[e] = __ldg(w + e);
+
+  float acc[Cfg::Q][Cfg::P];
+#pragma unroll
+  for (int q = 0; q < Cfg::Q; ++q)
+#pragma unroll
+    for (int p = 0; p < Cfg::P; ++p) acc[q][p] = 0.f;
+
+  for (int c0 = 0; c0 < Cfg::CIN; c0 += Cfg::CIC) {
+    __syncthreads();
+    for (int e = tid; e < Cfg::CIC * Cfg::ROWS * Cfg::NEED; e += Cfg::THREADS) {
+      const int x = e % Cfg::NEED;
+      const int r = (e / Cfg::NEED) % Cfg::ROWS;
+      const int c = e / (Cfg::NEED * Cfg::ROWS);
+      in_s[(c * Cfg::ROWS + r) * Cfg::RS + (x & 3) * Cfg::PH + (x >> 2)] =
+          in.load(b, c0 + c, t0 - Cfg::PT + r, f0 - Cfg::PL + x);
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int c = 0; c < Cfg::CIC; ++c) {
+      float patch[Cfg::Q + Cfg::KH - 1][Cfg::P + Cfg::KW - 1];
+      const float* base = in_s + (c * Cfg::ROWS + tq * Cfg::Q) * Cfg::RS + fp;
+#pragma unroll
+      for (int r = 0; r < Cfg::Q + Cfg::KH - 1; ++r)
+#pragma unroll
+        for (int j = 0; j < Cfg::P + Cfg::KW - 1; ++j) patch[r][j] = base[r * Cfg::RS + (j & 3) * Cfg::PH + (j >> 2)];
+      const float* wc = w_s + (c0 + c) * Cfg::KH * Cfg::KW;
+#pragma unroll
+      for (int dt = 0; dt < Cfg::KH; ++dt)
+#pragma unroll
+        for (int df = 0; df < Cfg::KW; ++df) {
+          const float wv = wc[dt * Cfg::KW + df];
+#pragma unroll
+          for (int q = 0; q < Cfg::Q; ++q)
+#pragma unroll
+            for (int p = 0; p < Cfg::P; ++p) acc[q][p] = fmaf(wv, patch[q + dt][p + df], acc[q][p]);
+        }
+    }
+  }
+  const float bv = __ldg(bias);
+#pragma unroll
+  for (int q = 0; q < Cfg::Q; ++q) {
+    const int t = t0 + tq * Cfg::Q + q;
+    const int f = f0 + fp * Cfg::P;
+    if (t < kFrames && f < Cfg::WOUT) {
+      float4 o;
+      o.x = 1.f / (1.f + expf(-(acc[q][0] + bv)));
+      o.y = 1.f / (1.f + expf(-(acc[q][1] + bv)));
+      o.z = 1.f / (1.f + expf(-(acc[q][2] + bv)));
+      o.w = 1.f / (1.f + expf(-(acc[q][3] + bv)));
+      *reinterpret_cast<float4*>(out + ((size_t)b * kFrames + t) * Cfg::WOUT + f) = o;
+    }
+  }
+}
+
+//                           CIN CIC KH KW PT PL WOUT TR
+using Contour2Cfg1 = Conv1Cfg<8, 4, 5, 5, 2, 2, 264, 11>;
+using Note2Cfg1 = Conv1Cfg<32, 4, 7, 3, 3, 1, 88, 11>;
+using Onset2Cfg1 = Conv1Cfg<33, 3, 3, 3, 1, 1, 88, 11>;
+
 //                         CIN CIC COUT COB KH  KW SF PT PL  WOUT TT  FL P  ACT
 using Contour1Cfg = ConvCfg<8, 8, 8, 8, 3, 39, 1, 1, 19, 264, 12, 22, 4, ACT_RELU>;
-using Contour2Cfg = ConvCfg<8, 8, 1, 1, 5, 5, 1, 2, 2, 264, 12, 22, 4, ACT_SIGMOID>;
 using Note1Cfg = ConvCfg<1, 1, 32, 8, 7, 7, 3, 3, 2, 88, 4, 22, 4, ACT_RELU>;
-using Note2Cfg = ConvCfg<32, 8, 1, 1, 7, 3, 1, 3, 1, 88, 12, 22, 4, ACT_SIGMOID>;
 using Onset1Cfg = ConvCfg<8, 8, 32, 8, 5, 5, 3, 2, 1, 88, 4, 22, 4, ACT_RELU>;
-using Onset2Cfg = ConvCfg<33, 11, 1, 1, 3, 3, 1, 1, 1, 88, 12, 22, 4, ACT_SIGMOID>;
 
 template <class Cfg, class In>
 static void set_attr() {
   cudaFuncSetAttribute(conv_kernel<Cfg, In>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
 }
 
+template <class Cfg, class In>
+static void set_attr1() {
+  cudaFuncSetAttribute(conv1_kernel<Cfg, In>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+}
+template <class Cfg, class In>
+static void launch1(In in, const float* w, const float* bias, float* out, int n_windows, cudaStream_t st) {
+  dim3 grid(Cfg::FTILES * Cfg::TTILES, n_windows);
+  conv1_kernel<Cfg, In><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(in, w, bias, out);
+}
+
 void cnn_setup() {
+  set_attr1<Contour2Cfg1, PlanarIn<8, 264>>();
+  set_attr1<Contour2Cfg1, NhwcIn<8, 264>>();
+  set_attr1<Note2Cfg1, PlanarIn<32, 88>>();
+  set_attr1<Onset2Cfg1, ConcatIn>();
+  set_attr1<Onset2Cfg1, ConcatNhwcIn>();
   set_attr<Contour1Cfg, StackIn>();
-  set_attr<Contour2Cfg, PlanarIn<8, 264>>();
-  set_attr<Contour2Cfg, NhwcIn<8, 264>>();
   set_attr<Note1Cfg, PlanarIn<1, 264>>();
-  set_attr<Note2Cfg, PlanarIn<32, 88>>();
   set_attr<Onset1Cfg, StackIn>();
-  set_attr<Onset2Cfg, ConcatIn>();
 }
 
 template <class Cfg, class In>
@@ -203,22 +321,25 @@ void launch_contour1(const float* y, const CnnWeights& w, float* c1, int n, cuda
   launch<Contour1Cfg>(StackIn{y}, w.contour1_wT, w.contour1_b, c1, n, st);
 }
 void launch_contour2(const float* c1, const CnnWeights& w, float* contour, int n, cudaStream_t st) {
-  launch<Contour2Cfg>(PlanarIn<8, 264>{c1}, w.contour2_wT, w.contour2_b, contour, n, st);
+  launch1<Contour2Cfg1>(PlanarIn<8, 264>{c1}, w.contour2_wT, w.contour2_b, contour, n, st);
+}
+void launch_onset2_nhwc(const float* note, const float* o1, const CnnWeights& w, float* onset, int n, cudaStream_t st) {
+  launch1<Onset2Cfg1>(ConcatNhwcIn{note, o1}, w.onset2_wT, w.onset2_b, onset, n, st);
 }
 void launch_contour2_nhwc(const float* c1, const CnnWeights& w, float* contour, int n, cudaStream_t st) {
-  launch<Contour2Cfg>(NhwcIn<8, 264>{c1}, w.contour2_wT, w.contour2_b, contour, n, st);
+  launch1<Contour2Cfg1>(NhwcIn<8, 264>{c1}, w.contour2_wT, w.contour2_b, contour, n, st);
 }
 void launch_note1(const float* contour, const CnnWeights& w, float* n1, int n, cudaStream_t st) {
   launch<Note1Cfg>(PlanarIn<1, 264>{contour}, w.note1_wT, w.note1_b, n1, n, st);
 }
 void launch_note2(const float* n1, const CnnWeights& w, float* note, int n, cudaStream_t st) {
-  launch<Note2Cfg>(PlanarIn<32, 88>{n1}, w.note2_wT, w.note2_b, note, n, st);
+  launch1<Note2Cfg1>(PlanarIn<32, 88>{n1}, w.note2_wT, w.note2_b, note, n, st);
 }
 void launch_onset1(const float* y, const CnnWeights& w, float* o1, int n, cudaStream_t st) {
   launch<Onset1Cfg>(StackIn{y}, w.onset1_wT, w.onset1_b, o1, n, st);
 }
 void launch_onset2(const float* note, const float* o1, const CnnWeights& w, float* onset, int n, cudaStream_t st) {
-  launch<Onset2Cfg>(ConcatIn{note, o1}, w.onset2_wT, w.onset2_b, onset, n, st);
+  launch1<Onset2Cfg1>(ConcatIn{note, o1}, w.onset2_wT, w.onset2_b, onset, n, st);
 }
 
 }  // namespace bp

@@ -38,27 +38,40 @@ void launch_onset2(const float* note, const float* o1, const CnnWeights& w, floa
 
 void launch_contour2_nhwc(const float* c1_nhwc, const CnnWeights& w, float* contour, int n_windows, cudaStream_t st);
 
-// ---- tc_contour.cu (tcgen05 path of the contour conv) ---------------------------------------------
-struct TcContourPlan {  // host side: weight tiles + the per-frequency-group MMA programs
+// ---- tc_conv.cu (tcgen05 path of the two convolutions that read the harmonic stack) ---------------
+struct TcConvSpec {
+  int KH, KW, SF, PT, PL, COUT, FLT, WOUT;  // taps, frequency stride, pads, channels, bins per 128-column tile, output bins
+};
+TcConvSpec tc_contour_spec();
+TcConvSpec tc_onset_spec();
+struct TcConvPlan {  // host side: weight tiles + the per-group MMA programs
+  TcConvSpec spec{};
   std::vector<uint16_t> tiles;       // n_tiles x 4096 bf16 : [plane hi/lo][k-chunk 2][n 128][8]
   std::vector<int> tile_seq;         // per step: tile id
-  std::vector<int> step_use_off;     // [n_steps + 1] into use_words
-  std::vector<uint32_t> use_words;   // ft_local | q << 2 | dt << 7 | first << 9
-  std::vector<int> group_step_off;   // [6]
-  int n_tiles = 0;
-  void build(const float* contour1_w /* [8][8][3][39] */);
+  std::vector<uint32_t> use_words;   // A offset >> 4 | slot << 14 | flags (tc_conv.cu)
+  std::vector<int> group_step_off;   // [n_groups + 1]
+  std::vector<int> group_use_off;    // [n_groups + 1]
+  std::vector<int> group_ft;         // [n_groups][2] frequency tiles of the group (-1 = none)
+  int n_tiles = 0, n_groups = 0;
+  void build(const TcConvSpec& spec, const float* w /* [COUT][8][KH][KW] */);
 };
-struct TcContourDev {
+struct TcConvDev {
+  TcConvSpec spec;
   const uint16_t* tiles;
   const int* tile_seq;
-  const int* step_use_off;
   const uint32_t* use_words;
-  int group_step_off[6];
+  const int* group_step_off;
+  const int* group_use_off;
+  const int* group_ft;
+  int n_groups;
 };
 int tc_rows_total(int n_windows);
 void tc_setup();
-void launch_contour1_tc(const float* y, __nv_bfloat16* yhl, const TcContourDev& dev, const float* bias, float* c1_nhwc,
-                        int n_windows, int n_sms, cudaStream_t st);
+void launch_y_split(const float* y, __nv_bfloat16* yhl, int n_windows, cudaStream_t st);
+void launch_conv_tc(const __nv_bfloat16* yhl, const TcConvDev& dev, const float* bias, float* out_nhwc, int n_windows,
+                    int n_sms, cudaStream_t st);
+void launch_onset2_nhwc(const float* note, const float* o1_nhwc, const CnnWeights& w, float* onset, int n_windows,
+                        cudaStream_t st);
 
 // ---- unwrap (api.cu) / decode.cu ----------------------------------------------------------------
 struct DecodeParamsDev {

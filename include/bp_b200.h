@@ -155,15 +155,16 @@ int bp_transcribe_device(bp_model_t* m, const float* d_audio, const int64_t* h_s
 int bp_debug_activation(bp_model_t* m, int which, float* h_out, int64_t n_windows);
 int64_t bp_model_chunk_windows(const bp_model_t* m);
 /* Selects the arithmetic path of the convolution stack: 0 = FP32 FFMA kernels, 1 = tensor-core
- * (tcgen05, split-bf16 operands, FP32 accumulate) where implemented.  Default: best available. */
+ * (tcgen05, split-bf16 operands, FP32 accumulate) for the contour and onset convolutions.  Default: 1. */
 int bp_model_set_path(bp_model_t* m, int path);
 
-/* Host-only (no GPU needed): builds the tensor-core plan of the contour conv (split-bf16 Toeplitz weight tiles and
- * the per-frequency-group MMA programs, csrc/tc_contour.cu) for the given [8][8][3][39] weights, so that tests can
- * emulate the program on the CPU.  sizes[3] = {n_tiles, n_steps, n_uses}; pass NULL arrays to query sizes first.
- * tiles: n_tiles x 4096 bf16 ([plane hi/lo][k-chunk 2][n 128][8]); step_use_off has n_steps + 1 entries. */
-int bp_debug_tc_plan(const float* contour1_w, int32_t* sizes, uint16_t* tiles, int32_t* tile_seq, int32_t* step_use_off,
-                     uint32_t* use_words, int32_t* group_step_off);
+/* Host-only (no GPU needed): builds the tensor-core plan (split-bf16 Toeplitz weight tiles and the per-group MMA
+ * programs, csrc/tc_conv.cu) of the contour conv (which = 0, w = [8][8][3][39]) or the onset conv (which = 1,
+ * w = [32][8][5][5]) so that tests can emulate the program on the CPU.  sizes[4] = {n_tiles, n_steps, n_uses,
+ * n_groups}; pass NULL arrays to query sizes first.  tiles: n_tiles x 4096 bf16 ([plane hi/lo][k-chunk 2][n 128][8]);
+ * group_*_off have n_groups + 1 entries, group_ft n_groups x 2. */
+int bp_debug_tc_plan(int which, const float* w, int32_t* sizes, uint16_t* tiles, int32_t* tile_seq, uint32_t* use_words,
+                     int32_t* group_step_off, int32_t* group_use_off, int32_t* group_ft);
 
 /* Per-kernel device timing for the roofline line of bench.py: records CUDA events on the launching
  * stream around every launch of one kernel family (0 = contour conv 3x39, 1 = onset conv 5x5,
