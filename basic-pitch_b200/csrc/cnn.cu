@@ -20,6 +20,7 @@ __constant__ int c_shift[kHarmonics] = {-36, 0, 36, 57, 72, 84, 93, 101};
 // Harmonic stack as a view of y[B][172][309]:  H[ci][t][g] = y[t][g + shift_ci] for 0<=g<264 and
 // 0 <= g+shift < 309, else 0 (zeros are inserted AFTER BatchNorm).
 struct StackIn {
+  static constexpr bool kChannelsLast = false;
   const float* y;
   __device__ __forceinline__ float load(int b, int ci, int t, int g) const {
     if ((unsigned)t >= (unsigned)kFrames || (unsigned)g >= (unsigned)kContourBins) return 0.f;
@@ -30,6 +31,7 @@ struct StackIn {
 };
 template <int C, int W>
 struct PlanarIn {
+  static constexpr bool kChannelsLast = false;
   const float* p;  // [B][C][172][W]
   __device__ __forceinline__ float load(int b, int ci, int t, int g) const {
     if ((unsigned)t >= (unsigned)kFrames || (unsigned)g >= (unsigned)W) return 0.f;
@@ -39,6 +41,7 @@ struct PlanarIn {
 // channels-last activations [B][172][W][C] (what the tensor-core contour kernel writes)
 template <int C, int W>
 struct NhwcIn {
+  static constexpr bool kChannelsLast = true;
   const float* p;
   __device__ __forceinline__ float load(int b, int ci, int t, int g) const {
     if ((unsigned)t >= (unsigned)kFrames || (unsigned)g >= (unsigned)W) return 0.f;
@@ -47,6 +50,7 @@ struct NhwcIn {
 };
 // channel 0 = note posteriorgram [B][172][88], channels 1..32 = onset conv1 output [B][32][172][88]
 struct ConcatIn {
+  static constexpr bool kChannelsLast = false;
   const float* note;
   const float* o1;
   __device__ __forceinline__ float load(int b, int ci, int t, int g) const {
@@ -58,6 +62,7 @@ struct ConcatIn {
 
 // same, with the onset conv1 output channels-last [B][172][88][32] (tensor-core path)
 struct ConcatNhwcIn {
+  static constexpr bool kChannelsLast = true;
   const float* note;
   const float* o1;
   __device__ __forceinline__ float load(int b, int ci, int t, int g) const {
@@ -231,9 +236,16 @@ __global__ void __launch_bounds__(Cfg::THREADS) conv1_kernel(In in, const float*
   for (int c0 = 0; c0 < Cfg::CIN; c0 += Cfg::CIC) {
     __syncthreads();
     for (int e = tid; e < Cfg::CIC * Cfg::ROWS * Cfg::NEED; e += Cfg::THREADS) {
-      const int x = e % Cfg::NEED;
-      const int r = (e / Cfg::NEED) % Cfg::ROWS;
-      const int c = e / (Cfg::NEED * Cfg::ROWS);
+      int x, r, c;
+      if (In::kChannelsLast) {  // channels are contiguous in memory: walk them fastest for coalesced reads
+        c = e % Cfg::CIC;
+        x = (e / Cfg::CIC) % Cfg::NEED;
+        r = e / (Cfg::CIC * Cfg::NEED);
+      } else {
+        x = e % Cfg::NEED;
+        r = (e / Cfg::NEED) % Cfg::ROWS;
+        c = e / (Cfg::NEED * Cfg::ROWS);
+      }
       in_s[(c * Cfg::ROWS + r) * Cfg::RS + (x & 3) * Cfg::PH + (x >> 2)] =
           in.load(b, c0 + c, t0 - Cfg::PT + r, f0 - Cfg::PL + x);
     }
@@ -277,8 +289,10 @@ __global__ void __launch_bounds__(Cfg::THREADS) conv1_kernel(In in, const float*
 
 //                           CIN CIC KH KW PT PL WOUT TR
 using Contour2Cfg1 = Conv1Cfg<8, 4, 5, 5, 2, 2, 264, 11>;
+using Contour2CfgN = Conv1Cfg<8, 8, 5, 5, 2, 2, 264, 5>;  // channels-last input
 using Note2Cfg1 = Conv1Cfg<32, 4, 7, 3, 3, 1, 88, 11>;
 using Onset2Cfg1 = Conv1Cfg<33, 3, 3, 3, 1, 1, 88, 11>;
+using Onset2CfgN = Conv1Cfg<33, 11, 3, 3, 1, 1, 88, 5>;   // channels-last input: whole 44-byte channel runs per pass
 
 //                         CIN CIC COUT COB KH  KW SF PT PL  WOUT TT  FL P  ACT
 using Contour1Cfg = ConvCfg<8, 8, 8, 8, 3, 39, 1, 1, 19, 264, 12, 22, 4, ACT_RELU>;
@@ -302,10 +316,10 @@ static void launch1(In in, const float* w, const float* bias, float* out, int n_
 
 void cnn_setup() {
   set_attr1<Contour2Cfg1, PlanarIn<8, 264>>();
-  set_attr1<Contour2Cfg1, NhwcIn<8, 264>>();
+  set_attr1<Contour2CfgN, NhwcIn<8, 264>>();
   set_attr1<Note2Cfg1, PlanarIn<32, 88>>();
   set_attr1<Onset2Cfg1, ConcatIn>();
-  set_attr1<Onset2Cfg1, ConcatNhwcIn>();
+  set_attr1<Onset2CfgN, ConcatNhwcIn>();
   set_attr<Contour1Cfg, StackIn>();
   set_attr<Note1Cfg, PlanarIn<1, 264>>();
   set_attr<Onset1Cfg, StackIn>();
@@ -324,10 +338,10 @@ void launch_contour2(const float* c1, const CnnWeights& w, float* contour, int n
   launch1<Contour2Cfg1>(PlanarIn<8, 264>{c1}, w.contour2_wT, w.contour2_b, contour, n, st);
 }
 void launch_onset2_nhwc(const float* note, const float* o1, const CnnWeights& w, float* onset, int n, cudaStream_t st) {
-  launch1<Onset2Cfg1>(ConcatNhwcIn{note, o1}, w.onset2_wT, w.onset2_b, onset, n, st);
+  launch1<Onset2CfgN>(ConcatNhwcIn{note, o1}, w.onset2_wT, w.onset2_b, onset, n, st);
 }
 void launch_contour2_nhwc(const float* c1, const CnnWeights& w, float* contour, int n, cudaStream_t st) {
-  launch1<Contour2Cfg1>(NhwcIn<8, 264>{c1}, w.contour2_wT, w.contour2_b, contour, n, st);
+  launch1<Contour2CfgN>(NhwcIn<8, 264>{c1}, w.contour2_wT, w.contour2_b, contour, n, st);
 }
 void launch_note1(const float* contour, const CnnWeights& w, float* n1, int n, cudaStream_t st) {
   launch<Note1Cfg>(PlanarIn<1, 264>{contour}, w.note1_wT, w.note1_b, n1, n, st);
