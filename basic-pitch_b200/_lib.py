@@ -105,7 +105,7 @@ def load() -> C.CDLL:
     lib.bp_transcribe_host.argtypes = [vp, vp, vp, i32, C.POINTER(DecodeParams), vp, vp, vp, vp, C.POINTER(Notes)]
     lib.bp_transcribe_device.argtypes = [vp, vp, vp, i32, C.POINTER(DecodeParams), vp, C.POINTER(Notes), vp]
     lib.bp_debug_activation.argtypes = [vp, C.c_int, vp, i64]
-    lib.bp_debug_tc_plan.argtypes = [C.c_int, vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.bp_debug_tc_plan.argtypes = [C.c_int, vp, vp, vp, vp, vp, vp, vp]
     lib.bp_model_profile.argtypes = [vp, C.c_int]
     lib.bp_model_profile_read.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(i64), C.POINTER(i64)]
     for name in EXPORTS:

@@ -143,8 +143,7 @@ struct bp_model {
     TcConvPlan plan;
     TcConvDev dev{};
     DevBuf<uint16_t> tiles;
-    DevBuf<int> tile_seq, group_step_off, group_use_off, group_ft;
-    DevBuf<uint32_t> use_words;
+    DevBuf<int> tile_seq;
   } tc_contour, tc_onset;
   DevBuf<__nv_bfloat16> yhl;
   int64_t launches = 0;
@@ -262,23 +261,14 @@ int derive(bp_model* m, cudaStream_t st) {
     bp_model::TcLayer& L = *layers[l];
     L.plan.build(specs[l], wsrc[l]);
     const TcConvPlan& pl = L.plan;
-    for (int g = 0; g < pl.n_groups; ++g)
-      if (pl.group_use_off[g + 1] - pl.group_use_off[0] > 1664)
-        return fail(BP_E_INVALID, "tensor-core program does not fit its shared-memory staging area");
+    if (tc_upload_program(l, pl, st) != 0)
+      return fail(BP_E_INVALID, "tensor-core program does not fit its constant-memory area");
     CK(L.tiles.reserve(pl.tiles.size()));
     CK(L.tile_seq.reserve(pl.tile_seq.size()));
-    CK(L.use_words.reserve(pl.use_words.size()));
-    CK(L.group_step_off.reserve(pl.group_step_off.size()));
-    CK(L.group_use_off.reserve(pl.group_use_off.size()));
-    CK(L.group_ft.reserve(pl.group_ft.size()));
     CK(cudaMemcpyAsync(L.tiles.p, pl.tiles.data(), pl.tiles.size() * 2, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(L.tile_seq.p, pl.tile_seq.data(), pl.tile_seq.size() * 4, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(L.use_words.p, pl.use_words.data(), pl.use_words.size() * 4, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(L.group_step_off.p, pl.group_step_off.data(), pl.group_step_off.size() * 4, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(L.group_use_off.p, pl.group_use_off.data(), pl.group_use_off.size() * 4, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(L.group_ft.p, pl.group_ft.data(), pl.group_ft.size() * 4, cudaMemcpyHostToDevice, st));
     CK(cudaStreamSynchronize(st));
-    L.dev = TcConvDev{pl.spec, L.tiles.p, L.tile_seq.p, L.use_words.p, L.group_step_off.p, L.group_use_off.p, L.group_ft.p, pl.n_groups};
+    L.dev = TcConvDev{pl.spec, L.tiles.p, L.tile_seq.p, pl.n_groups, l};
   }
   return BP_OK;
 }
@@ -468,8 +458,7 @@ void bp_model_destroy(bp_model_t* m) {
   m->d_bend_off.release(); m->d_bends.release();
   m->yhl.release();
   for (bp_model::TcLayer* L : {&m->tc_contour, &m->tc_onset}) {
-    L->tiles.release(); L->tile_seq.release(); L->use_words.release(); L->group_step_off.release();
-    L->group_use_off.release(); L->group_ft.release();
+    L->tiles.release(); L->tile_seq.release();
   }
   if (m->d_params) cudaFree(m->d_params);
   if (m->d_derived) cudaFree(m->d_derived);
@@ -824,20 +813,22 @@ int bp_transcribe_host(bp_model_t* m, const float* h_audio, const int64_t* h_sam
   return BP_OK;
 }
 
-int bp_debug_tc_plan(int which, const float* w, int32_t* sizes, uint16_t* tiles, int32_t* tile_seq, uint32_t* use_words,
-                     int32_t* group_step_off, int32_t* group_use_off, int32_t* group_ft) {
+int bp_debug_tc_plan(int which, const float* w, int32_t* sizes, uint16_t* tiles, int32_t* tile_seq, uint32_t* slot_words,
+                     int32_t* group_step_off, int32_t* group_ft) {
   if (!w || !sizes || which < 0 || which > 1) return fail(BP_E_INVALID, "bp_debug_tc_plan: bad argument");
   TcConvPlan pl;
   pl.build(which == 0 ? tc_contour_spec() : tc_onset_spec(), w);
   sizes[0] = pl.n_tiles;
   sizes[1] = (int32_t)pl.tile_seq.size();
-  sizes[2] = (int32_t)pl.use_words.size();
+  sizes[2] = pl.n_uses;
   sizes[3] = pl.n_groups;
   if (tiles) std::memcpy(tiles, pl.tiles.data(), pl.tiles.size() * 2);
   if (tile_seq) std::memcpy(tile_seq, pl.tile_seq.data(), pl.tile_seq.size() * 4);
-  if (use_words) std::memcpy(use_words, pl.use_words.data(), pl.use_words.size() * 4);
+  if (slot_words) {
+    std::memcpy(slot_words, pl.slot_words[0].data(), pl.slot_words[0].size() * 4);
+    std::memcpy(slot_words + pl.slot_words[0].size(), pl.slot_words[1].data(), pl.slot_words[1].size() * 4);
+  }
   if (group_step_off) std::memcpy(group_step_off, pl.group_step_off.data(), pl.group_step_off.size() * 4);
-  if (group_use_off) std::memcpy(group_use_off, pl.group_use_off.data(), pl.group_use_off.size() * 4);
   if (group_ft) std::memcpy(group_ft, pl.group_ft.data(), pl.group_ft.size() * 4);
   return BP_OK;
 }

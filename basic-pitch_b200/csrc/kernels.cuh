@@ -48,23 +48,20 @@ struct TcConvPlan {  // host side: weight tiles + the per-group MMA programs
   TcConvSpec spec{};
   std::vector<uint16_t> tiles;       // n_tiles x 4096 bf16 : [plane hi/lo][k-chunk 2][n 128][8]
   std::vector<int> tile_seq;         // per step: tile id
-  std::vector<uint32_t> use_words;   // A offset >> 4 | slot << 14 | flags (tc_conv.cu)
+  std::vector<uint32_t> slot_words[2];  // per step and accumulator slot: A offset >> 4 | first << 15, or 0xffffffff
   std::vector<int> group_step_off;   // [n_groups + 1]
-  std::vector<int> group_use_off;    // [n_groups + 1]
   std::vector<int> group_ft;         // [n_groups][2] frequency tiles of the group (-1 = none)
-  int n_tiles = 0, n_groups = 0;
+  int n_tiles = 0, n_groups = 0, n_uses = 0;
   void build(const TcConvSpec& spec, const float* w /* [COUT][8][KH][KW] */);
 };
 struct TcConvDev {
   TcConvSpec spec;
   const uint16_t* tiles;
   const int* tile_seq;
-  const uint32_t* use_words;
-  const int* group_step_off;
-  const int* group_use_off;
-  const int* group_ft;
   int n_groups;
+  int layer;  // index of the program in constant memory (0 contour, 1 onset)
 };
+int tc_upload_program(int layer, const TcConvPlan& plan, cudaStream_t st);  // 0 on success
 int tc_rows_total(int n_windows);
 void tc_setup();
 void launch_y_split(const float* y, __nv_bfloat16* yhl, int n_windows, cudaStream_t st);

@@ -28,8 +28,10 @@
 // i = blockIdx.x, +gridDim.x, ...:
 //   warp 0      producer: bulk-copies the (128+KH-1) x 320 bf16 hi/lo data tile (k-chunk-major) once per item and
 //               streams the weight tiles of each group's program (8 KB each) through a 6-stage ring
-//   warp 1      MMA issuer: program words staged in shared memory, descriptors are base + precomputed offset,
-//               3 x tcgen05.mma per use issued by one elected lane, tcgen05.commit frees stages / publishes TMEM
+//   warps 1, 6  MMA issuers, one per accumulator slot of the group (instruction issue, not the tensor pipe, limits
+//               a single issuing warp at this MMA size): program words from constant memory, descriptors are
+//               base + precomputed offset, 3 x tcgen05.mma per step by one elected lane, tcgen05.commit frees the
+//               weight stage / publishes the accumulators
 //   warps 2-5   epilogue: tcgen05.ld the accumulator columns, + bias, ReLU, store channels-last
 #include <cuda_bf16.h>
 
@@ -48,13 +50,14 @@ constexpr int kChunks8 = 40;                                     // 320 bins / 8
 constexpr int kMaxDataBytes = 2 * kChunks8 * kMaxDataRows * 16;  // hi + lo = 168960
 constexpr int kTileBytes = 8192;                                 // weight tile: [plane 2][kchunk 2][128][8] bf16
 constexpr int kStages = 6;
-constexpr int kMaxProgWords = 1664;                              // uses of one item's groups (6.5 KB)
-constexpr int kThreads = 192;
-constexpr int kSmemBytes = kMaxDataBytes + kStages * kTileBytes + kMaxProgWords * 4 + 512;
+constexpr int kMaxSteps = 1024;                                  // program steps per layer (constant memory)
+constexpr int kMaxGroups = 15;
+constexpr int kThreads = 224;
+constexpr int kSmemBytes = kMaxDataBytes + kStages * kTileBytes + 512;
 constexpr int kShift[kHarmonics] = {-36, 0, 36, 57, 72, 84, 93, 101};
-// use word: [0,14) A start-address offset >> 4, [14] ft slot in the group, [15] first MMA into that accumulator,
-//           [16] first use of a step (wait for the staged tile), [17] last use of a step (release the stage)
-constexpr uint32_t kUseFirstAcc = 1u << 15, kUseStepBegin = 1u << 16, kUseStepEnd = 1u << 17;
+// step word of a slot: [0,14) A start-address offset >> 4, [15] first MMA into that accumulator; kNoUse = the
+// slot's frequency tile does not use this step's weight tile
+constexpr uint32_t kUseFirstAcc = 1u << 15, kNoUse = 0xffffffffu;
 }  // namespace tc
 
 // ------------------------------------------------------------------------------------------------
@@ -82,9 +85,9 @@ void TcConvPlan::build(const TcConvSpec& sp, const float* W /* [COUT][8][KH][KW]
   spec = sp;
   tiles.clear();
   tile_seq.clear();
-  use_words.clear();
+  slot_words[0].clear();
+  slot_words[1].clear();
   group_step_off.clear();
-  group_use_off.clear();
   group_ft.clear();
   const int n_ft = (sp.WOUT + sp.FLT - 1) / sp.FLT;
   const int data_rows = kMTile + sp.KH - 1;
@@ -131,7 +134,7 @@ void TcConvPlan::build(const TcConvSpec& sp, const float* W /* [COUT][8][KH][KW]
   // groups: pairs {ft, ft + stride} (or singles)
   std::vector<bool> taken(n_ft, false);
   group_step_off.push_back(0);
-  group_use_off.push_back(0);
+  n_uses = 0;
   for (int ft_a = 0; ft_a < n_ft; ++ft_a) {
     if (taken[ft_a]) continue;
     taken[ft_a] = true;
@@ -183,22 +186,42 @@ void TcConvPlan::build(const TcConvSpec& sp, const float* W /* [COUT][8][KH][KW]
       size_t j = i;
       while (j < uses.size() && uses[j].tile == uses[i].tile) ++j;
       tile_seq.push_back(uses[i].tile);
+      uint32_t w[2] = {kNoUse, kNoUse};
       for (size_t u = i; u < j; ++u) {
-        const uint32_t aoff16 = (uint32_t)(2 * uses[u].q * lbo16 + uses[u].dt);
-        uint32_t w = aoff16 | ((uint32_t)uses[u].slot << 14);
-        if (!seen[uses[u].slot]) w |= kUseFirstAcc;
-        seen[uses[u].slot] = true;
-        if (u == i) w |= kUseStepBegin;
-        if (u + 1 == j) w |= kUseStepEnd;
-        use_words.push_back(w);
+        const int sl = uses[u].slot;
+        // a (tile, frequency tile) pair determines the chunk q, so a slot uses a tile at most once
+        w[sl] = (uint32_t)(2 * uses[u].q * lbo16 + uses[u].dt);
+        if (!seen[sl]) w[sl] |= kUseFirstAcc;
+        seen[sl] = true;
+        ++n_uses;
       }
+      slot_words[0].push_back(w[0]);
+      slot_words[1].push_back(w[1]);
       i = j;
     }
     group_step_off.push_back((int)tile_seq.size());
-    group_use_off.push_back((int)use_words.size());
   }
   n_tiles = (int)keys.size();
   n_groups = (int)group_ft.size() / 2;
+}
+
+// The MMA programs live in constant memory: the issuing warp indexes them with warp-uniform values, so the words,
+// the descriptors derived from them and the loop state stay in uniform registers (no per-use R2UR traffic).
+// They depend only on the layer geometry (TcConvSpec), not on the weights.
+__constant__ uint32_t c_prog[2][2][tc::kMaxSteps];  // [layer][slot][step]
+__constant__ int c_group_step_off[2][tc::kMaxGroups + 1];
+__constant__ int c_group_ft[2][2 * tc::kMaxGroups];
+
+int tc_upload_program(int layer, const TcConvPlan& pl, cudaStream_t st) {
+  if (layer < 0 || layer > 1 || (int)pl.tile_seq.size() > tc::kMaxSteps - 1 || pl.n_groups > tc::kMaxGroups) return -1;
+  for (int sl = 0; sl < 2; ++sl)
+    cudaMemcpyToSymbolAsync(c_prog, pl.slot_words[sl].data(), pl.slot_words[sl].size() * 4,
+                            ((size_t)layer * 2 + sl) * tc::kMaxSteps * 4, cudaMemcpyHostToDevice, st);
+  cudaMemcpyToSymbolAsync(c_group_step_off, pl.group_step_off.data(), pl.group_step_off.size() * 4,
+                          (size_t)layer * (tc::kMaxGroups + 1) * 4, cudaMemcpyHostToDevice, st);
+  cudaMemcpyToSymbolAsync(c_group_ft, pl.group_ft.data(), pl.group_ft.size() * 4, (size_t)layer * 2 * tc::kMaxGroups * 4,
+                          cudaMemcpyHostToDevice, st);
+  return cudaStreamSynchronize(st) == cudaSuccess ? 0 : -1;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -267,6 +290,40 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// The three split-precision products of one program use, issued by the elected lane only (PTX predication, no
+// branch): D (+)= Ahi*Bhi ; D += Ahi*Blo ; D += Alo*Bhi.  Descriptors are passed as (low word, shared high word).
+__device__ __forceinline__ void umma_bf16_x3(uint32_t tmem_d, uint32_t a_hi_lo32, uint32_t a_lo_lo32, uint32_t b_hi_lo32,
+                                             uint32_t b_lo_lo32, uint32_t desc_hi32, uint32_t idesc, uint32_t accumulate,
+                                             uint32_t leader) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, q, t;\n\t"
+      ".reg .b64 dah, dal, dbh, dbl;\n\t"
+      "setp.ne.b32 p, %7, 0;\n\t"
+      "setp.ne.b32 q, %8, 0;\n\t"
+      "setp.eq.b32 t, 0, 0;\n\t"
+      "mov.b64 dah, {%1, %5};\n\t"
+      "mov.b64 dal, {%2, %5};\n\t"
+      "mov.b64 dbh, {%3, %5};\n\t"
+      "mov.b64 dbl, {%4, %5};\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], dah, dbh, %6, p;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], dah, dbl, %6, t;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], dal, dbh, %6, t;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "r"(a_hi_lo32), "r"(a_lo_lo32), "r"(b_hi_lo32), "r"(b_lo_lo32), "r"(desc_hi32), "r"(idesc), "r"(accumulate),
+      "r"(leader)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_pred(uint64_t* bar, uint32_t leader) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred q;\n\t"
+      "setp.ne.b32 q, %1, 0;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(leader)
+      : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
@@ -330,11 +387,8 @@ struct TcArgs {
   const __nv_bfloat16* yhl;     // [2][40][rows_total][8]
   const uint16_t* tiles;        // [n_tiles][8192 B]
   const int* tile_seq;          // per step: tile id
-  const uint32_t* use_words;    // packed uses
-  const int* group_step_off;    // [n_groups + 1]
-  const int* group_use_off;     // [n_groups + 1]
-  const int* group_ft;          // [n_groups][2]  (-1 = unused slot)
   const float* bias;            // [COUT]
+  int layer;                    // which constant-memory program (0 contour, 1 onset)
   float* out;                   // [B][172][WOUT][COUT]  (channels-last)
   int rows_total, n_mtiles, n_windows;
   int n_groups, n_split;        // an item covers groups [s*n_groups/n_split, (s+1)*n_groups/n_split)
@@ -347,8 +401,7 @@ __global__ void __launch_bounds__(tc::kThreads, 1) conv_tc_kernel(const TcArgs a
   extern __shared__ __align__(128) unsigned char smem[];
   unsigned char* s_data = smem;                    // [2 planes][40 chunks][data_rows][16 B]
   unsigned char* s_w = smem + kMaxDataBytes;       // [kStages][8192]
-  uint32_t* s_prog = reinterpret_cast<uint32_t*>(smem + kMaxDataBytes + kStages * kTileBytes);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kMaxDataBytes + kStages * kTileBytes + kMaxProgWords * 4);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kMaxDataBytes + kStages * kTileBytes);
   uint64_t* full_w = bars;             // [kStages]
   uint64_t* empty_w = bars + kStages;  // [kStages]
   uint64_t* data_full = bars + 2 * kStages;
@@ -365,12 +418,12 @@ __global__ void __launch_bounds__(tc::kThreads, 1) conv_tc_kernel(const TcArgs a
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) {
       mbar_init(full_w + s, 1);
-      mbar_init(empty_w + s, 1);
+      mbar_init(empty_w + s, 2);  // one arrival per MMA warp
     }
     mbar_init(data_full, 1);
-    mbar_init(data_empty, 1);
+    mbar_init(data_empty, 2);
     for (int i = 0; i < 2; ++i) {
-      mbar_init(tmem_full + i, 1);
+      mbar_init(tmem_full + i, 2);
       mbar_init(tmem_empty + i, 4);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -382,7 +435,7 @@ __global__ void __launch_bounds__(tc::kThreads, 1) conv_tc_kernel(const TcArgs a
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
   const int n_items = a.n_mtiles * a.n_split;
 
@@ -402,7 +455,7 @@ __global__ void __launch_bounds__(tc::kThreads, 1) conv_tc_kernel(const TcArgs a
             bulk_g2s(s_data + p * plane_bytes + c * lbo, a.yhl + p * plane_elems + ((size_t)c * a.rows_total + row) * 8,
                      lbo, data_full);
         ph_d ^= 1;
-        const int s0 = __ldg(a.group_step_off + g0), s1 = __ldg(a.group_step_off + g1);
+        const int s0 = c_group_step_off[a.layer][g0], s1 = c_group_step_off[a.layer][g1];
         for (int s = s0; s < s1; ++s) {
           mbar_wait(empty_w + stage, ph_w ^ 1);
           mbar_expect_tx(full_w + stage, kTileBytes);
@@ -415,24 +468,23 @@ __global__ void __launch_bounds__(tc::kThreads, 1) conv_tc_kernel(const TcArgs a
         }
       }
     }
-  } else if (warp == 1) {
-    // ------------------------------ MMA issuer (whole warp, one elected lane issues) ------------------------------
+  } else if (warp == 1 || warp == 6) {
+    // ------------------------------ MMA issuers: warp 1 -> accumulator slot 0, warp 6 -> slot 1 ---------------------
     constexpr uint32_t idesc = make_idesc(128, 128);
+    const int slot = (warp == 1) ? 0 : 1;
+    const uint32_t leader = elect_one() ? 1u : 0u;
     uint32_t stage = 0, ph_w = 0, ph_d = 0;
     uint32_t ph_t[2] = {0, 0};
     uint32_t gcount = 0;  // groups issued so far by this CTA -> TMEM buffer = gcount & 1
-    const uint64_t a_hi0 = make_desc(smem_u32(s_data), lbo, 128);
-    const uint64_t a_lo0 = make_desc(smem_u32(s_data) + plane_bytes, lbo, 128);
-    const uint64_t b_hi0 = make_desc(smem_u32(s_w), 2048, 128);
-    const uint64_t b_lo0 = make_desc(smem_u32(s_w) + 4096, 2048, 128);
+    // descriptor words: low = start >> 4 | (LBO >> 4) << 16 ; high = SBO >> 4 | version 1 << 14 (shared by all)
+    const uint32_t desc_hi32 = (128u >> 4) | (1u << 14);
+    const uint32_t a_hi_base = ((smem_u32(s_data) >> 4) & 0x3fffu) | ((uint32_t)a.data_rows << 16);
+    const uint32_t a_lo_base = a_hi_base + (plane_bytes >> 4);
+    const uint32_t b_base = ((smem_u32(s_w) >> 4) & 0x3fffu) | ((2048u >> 4) << 16);
+    const uint32_t* prog = c_prog[a.layer][slot];
     for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
       const int sp = it % a.n_split;
       const int g0 = sp * a.n_groups / a.n_split, g1 = (sp + 1) * a.n_groups / a.n_split;
-      // stage this item's program words (previous item's MMAs were all issued; the words are only read by this warp)
-      const int w0 = __ldg(a.group_use_off + g0), w1 = __ldg(a.group_use_off + g1);
-      __syncwarp();
-      for (int i = w0 + lane; i < w1; i += 32) s_prog[i - w0] = __ldg(a.use_words + i);
-      __syncwarp();
       mbar_wait(data_full, ph_d);
       ph_d ^= 1;
       for (int g = g0; g < g1; ++g) {
@@ -440,39 +492,32 @@ __global__ void __launch_bounds__(tc::kThreads, 1) conv_tc_kernel(const TcArgs a
         mbar_wait(tmem_empty + buf, ph_t[buf] ^ 1);
         ph_t[buf] ^= 1;
         tc_fence_after();
-        const int u0 = __ldg(a.group_use_off + g) - w0, u1 = __ldg(a.group_use_off + g + 1) - w0;
-        const uint32_t dbase = tmem_base + buf * 256u;
-        for (int k = u0; k < u1; ++k) {
-          const uint32_t w = s_prog[k];
-          if (w & kUseStepBegin) {
-            mbar_wait(full_w + stage, ph_w);
+        const int s0 = c_group_step_off[a.layer][g], s1 = c_group_step_off[a.layer][g + 1];
+        const uint32_t d = tmem_base + buf * 256u + (uint32_t)slot * 128u;
+        uint32_t w = prog[s0];
+        for (int s = s0; s < s1; ++s) {
+          const uint32_t w_next = prog[s + 1];  // (one word past the end is inside the array)
+          mbar_wait(full_w + stage, ph_w);
+          if (w != kNoUse) {
             tc_fence_after();
+            const uint32_t off = w & 0x3fffu;
+            const uint32_t bl = b_base + stage * (kTileBytes >> 4);
+            umma_bf16_x3(d, a_hi_base + off, a_lo_base + off, bl, bl + 256u, desc_hi32, idesc,
+                         (w & kUseFirstAcc) ? 0u : 1u, leader);
+            umma_commit_pred(empty_w + stage, leader);
+          } else if (leader) {
+            mbar_arrive(empty_w + stage);
           }
-          const uint64_t a_hi = a_hi0 + (w & 0x3fffu);
-          const uint64_t a_lo = a_lo0 + (w & 0x3fffu);
-          const uint64_t b_hi = b_hi0 + (uint64_t)(stage * (kTileBytes >> 4));
-          const uint64_t b_lo = b_lo0 + (uint64_t)(stage * (kTileBytes >> 4));
-          const uint32_t d = dbase + ((w >> 14) & 1u) * 128u;
-          if (elect_one()) {
-            umma_bf16(d, a_hi, b_hi, idesc, (w & kUseFirstAcc) ? 0u : 1u);
-            umma_bf16(d, a_hi, b_lo, idesc, 1u);
-            umma_bf16(d, a_lo, b_hi, idesc, 1u);
-            if (w & kUseStepEnd) umma_commit(empty_w + stage);
+          if (++stage == kStages) {
+            stage = 0;
+            ph_w ^= 1;
           }
-          __syncwarp();
-          if (w & kUseStepEnd) {
-            if (++stage == kStages) {
-              stage = 0;
-              ph_w ^= 1;
-            }
-          }
+          w = w_next;
         }
-        if (elect_one()) umma_commit(tmem_full + buf);  // accumulators of this group are complete
-        __syncwarp();
+        umma_commit_pred(tmem_full + buf, leader);  // this slot's accumulator is complete
         ++gcount;
       }
-      if (elect_one()) umma_commit(data_empty);  // the data tile may be overwritten
-      __syncwarp();
+      umma_commit_pred(data_empty, leader);  // the data tile may be overwritten
     }
   } else {
     // ------------------------------ epilogue (warps 2..5) ------------------------------
@@ -501,7 +546,7 @@ __global__ void __launch_bounds__(tc::kThreads, 1) conv_tc_kernel(const TcArgs a
         tc_fence_after();
 #pragma unroll 1
         for (int slot = 0; slot < 2; ++slot) {
-          const int ft = __ldg(a.group_ft + 2 * g + slot);
+          const int ft = c_group_ft[a.layer][2 * g + slot];
           if (ft < 0) continue;
           const int n_valid = min(a.flt, a.wout - ft * a.flt) * a.cout;  // valid columns of this 128-column tile
           float* dst = orow + (size_t)ft * 128;
@@ -563,11 +608,8 @@ void launch_conv_tc(const __nv_bfloat16* yhl, const TcConvDev& dev, const float*
   a.yhl = yhl;
   a.tiles = dev.tiles;
   a.tile_seq = dev.tile_seq;
-  a.use_words = dev.use_words;
-  a.group_step_off = dev.group_step_off;
-  a.group_use_off = dev.group_use_off;
-  a.group_ft = dev.group_ft;
   a.bias = bias;
+  a.layer = dev.layer;
   a.out = out_nhwc;
   a.rows_total = tc_rows_total(n_windows);
   a.n_mtiles = (a.rows_total - 4) / tc::kMTile;

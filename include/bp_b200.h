@@ -162,9 +162,9 @@ int bp_model_set_path(bp_model_t* m, int path);
  * programs, csrc/tc_conv.cu) of the contour conv (which = 0, w = [8][8][3][39]) or the onset conv (which = 1,
  * w = [32][8][5][5]) so that tests can emulate the program on the CPU.  sizes[4] = {n_tiles, n_steps, n_uses,
  * n_groups}; pass NULL arrays to query sizes first.  tiles: n_tiles x 4096 bf16 ([plane hi/lo][k-chunk 2][n 128][8]);
- * group_*_off have n_groups + 1 entries, group_ft n_groups x 2. */
-int bp_debug_tc_plan(int which, const float* w, int32_t* sizes, uint16_t* tiles, int32_t* tile_seq, uint32_t* use_words,
-                     int32_t* group_step_off, int32_t* group_use_off, int32_t* group_ft);
+ * slot_words: [2][n_steps]; group_step_off has n_groups + 1 entries, group_ft n_groups x 2. */
+int bp_debug_tc_plan(int which, const float* w, int32_t* sizes, uint16_t* tiles, int32_t* tile_seq, uint32_t* slot_words,
+                     int32_t* group_step_off, int32_t* group_ft);
 
 /* Per-kernel device timing for the roofline line of bench.py: records CUDA events on the launching
  * stream around every launch of one kernel family (0 = contour conv 3x39, 1 = onset conv 5x5,

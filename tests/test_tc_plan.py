@@ -25,66 +25,62 @@ def _plan(which, w):
     lib = _lib.load()
     sizes = np.zeros(4, np.int32)
     wc = np.ascontiguousarray(w, np.float32)
-    lib.bp_debug_tc_plan(which, wc.ctypes.data, sizes.ctypes.data, None, None, None, None, None, None)
+    lib.bp_debug_tc_plan(which, wc.ctypes.data, sizes.ctypes.data, None, None, None, None, None)
     n_tiles, n_steps, n_uses, n_groups = (int(x) for x in sizes)
     tiles = np.zeros((n_tiles, 2, 2, 128, 8), np.uint16)
     tile_seq = np.zeros(n_steps, np.int32)
-    use_words = np.zeros(n_uses, np.uint32)
+    slot_words = np.zeros((2, n_steps), np.uint32)
     gso = np.zeros(n_groups + 1, np.int32)
-    guo = np.zeros(n_groups + 1, np.int32)
     gft = np.zeros((n_groups, 2), np.int32)
     lib.bp_debug_tc_plan(which, wc.ctypes.data, sizes.ctypes.data, tiles.ctypes.data, tile_seq.ctypes.data,
-                         use_words.ctypes.data, gso.ctypes.data, guo.ctypes.data, gft.ctypes.data)
-    return tiles, tile_seq, use_words, gso, guo, gft
+                         slot_words.ctypes.data, gso.ctypes.data, gft.ctypes.data)
+    return tiles, tile_seq, slot_words, gso, gft, n_uses
 
 
 @pytest.mark.parametrize("which", [0, 1])
 def test_tc_program_reproduces_convolution(weights_np, which):
     key, KH, KW, SF, PT, PL, COUT, FLT, WOUT = SPECS[which]
     w = weights_np[key]
-    tiles, tile_seq, use_words, gso, guo, gft = _plan(which, w)
+    tiles, tile_seq, slot_words, gso, gft, n_uses = _plan(which, w)
     n_groups = len(gft)
-    assert gso[0] == 0 and gso[-1] == len(tile_seq) and guo[-1] == len(use_words)
-    assert (guo[1:] - guo[0]).max() <= 1664  # fits the shared-memory staging area of one item
+    assert gso[0] == 0 and gso[-1] == len(tile_seq) < 1023 and n_groups <= 15  # constant-memory program area
     tf = _bf16_to_f32(tiles).astype(np.float64)
     t_full = (tf[:, 0] + tf[:, 1]).transpose(0, 1, 3, 2).reshape(len(tiles), 16, 128)  # [tile][k][n]
     rng = np.random.default_rng(which)
     n_t = 40
-    data_rows = n_t + KH - 1
     y = rng.standard_normal((n_t, 309))
-    # data rows d = t + PT ... the kernel's tile row (i + dt) holds input frame i + dt - PT
-    ypad = np.zeros((data_rows, 320))
+    # the kernel's tile row (i + dt) holds input frame i + dt - PT
+    ypad = np.zeros((n_t + KH - 1, 320))
     ypad[PT : PT + n_t, :309] = y
     n_ft = (WOUT + FLT - 1) // FLT
     out = np.zeros((n_t, n_ft * 128))
     lbo16 = 128 + KH - 1  # the program is built for 128-row M-tiles
     seen_ft = set()
+    used = 0
     for g in range(n_groups):
         first_seen = set()
-        step = gso[g]
-        for k in range(guo[g], guo[g + 1]):
-            wd = int(use_words[k])
-            aoff16, slot = wd & 0x3FFF, (wd >> 14) & 1
-            first_acc, step_begin, step_end = (wd >> 15) & 1, (wd >> 16) & 1, (wd >> 17) & 1
-            q2, dt = divmod(aoff16, lbo16)
-            assert q2 % 2 == 0 and dt < KH
-            q = q2 // 2
-            ft = int(gft[g, slot])
-            assert ft >= 0
-            assert bool(first_acc) == (slot not in first_seen)
-            first_seen.add(slot)
-            a = ypad[dt : dt + n_t, 16 * q : 16 * q + 16]
-            out[:, 128 * ft : 128 * ft + 128] += a @ t_full[tile_seq[step]]
-            if step_end:
-                step += 1
-            else:
-                assert not (int(use_words[k + 1]) >> 16) & 1  # next use stays in the same step
-        assert step == gso[g + 1]
+        for step in range(gso[g], gso[g + 1]):
+            for slot in (0, 1):
+                wd = int(slot_words[slot, step])
+                if wd == 0xFFFFFFFF:
+                    continue
+                used += 1
+                aoff16, first_acc = wd & 0x3FFF, (wd >> 15) & 1
+                assert wd >> 16 == 0
+                q2, dt = divmod(aoff16, lbo16)
+                assert q2 % 2 == 0 and dt < KH
+                q = q2 // 2
+                ft = int(gft[g, slot])
+                assert ft >= 0
+                assert bool(first_acc) == (slot not in first_seen)
+                first_seen.add(slot)
+                a = ypad[dt : dt + n_t, 16 * q : 16 * q + 16]
+                out[:, 128 * ft : 128 * ft + 128] += a @ t_full[tile_seq[step]]
         for slot in (0, 1):
             if gft[g, slot] >= 0:
-                assert gft[g, slot] not in seen_ft
+                assert gft[g, slot] not in seen_ft and slot in first_seen
                 seen_ft.add(int(gft[g, slot]))
-    assert seen_ft == set(range(n_ft))
+    assert seen_ft == set(range(n_ft)) and used == n_uses
     got = out.reshape(n_t, n_ft * FLT, COUT)[:, :WOUT]  # n = fl * COUT + co
     h = model_ref.harmonic_stack(torch.from_numpy(y)[None])  # (1,8,T,264)
     ref = F.conv2d(F.pad(h, (PL, PL, PT, PT)), torch.from_numpy(w.astype(np.float64)), stride=(1, SF))[0].numpy()
@@ -96,6 +92,6 @@ def test_tc_program_reproduces_convolution(weights_np, which):
 def test_tc_program_statistics(weights_np):
     for which in (0, 1):
         key = SPECS[which][0]
-        tiles, tile_seq, use_words, gso, guo, gft = _plan(which, weights_np[key])
+        tiles, tile_seq, slot_words, gso, gft, n_uses = _plan(which, weights_np[key])
         assert (tile_seq >= 0).all() and (tile_seq < len(tiles)).all()
-        assert len(tiles) < 700 and len(use_words) < 2200
+        assert len(tiles) < 700 and n_uses < 2200
