@@ -209,6 +209,7 @@ void TcConvPlan::build(const TcConvSpec& sp, const float* W /* [COUT][8][KH][KW]
 // the descriptors derived from them and the loop state stay in uniform registers (no per-use R2UR traffic).
 // They depend only on the layer geometry (TcConvSpec), not on the weights.
 __constant__ uint32_t c_prog[2][2][tc::kMaxSteps];  // [layer][slot][step]
+__constant__ int c_tile_seq[2][tc::kMaxSteps];       // [layer][step] -> weight tile id
 __constant__ int c_group_step_off[2][tc::kMaxGroups + 1];
 __constant__ int c_group_ft[2][2 * tc::kMaxGroups];
 
@@ -217,6 +218,8 @@ int tc_upload_program(int layer, const TcConvPlan& pl, cudaStream_t st) {
   for (int sl = 0; sl < 2; ++sl)
     cudaMemcpyToSymbolAsync(c_prog, pl.slot_words[sl].data(), pl.slot_words[sl].size() * 4,
                             ((size_t)layer * 2 + sl) * tc::kMaxSteps * 4, cudaMemcpyHostToDevice, st);
+  cudaMemcpyToSymbolAsync(c_tile_seq, pl.tile_seq.data(), pl.tile_seq.size() * 4, (size_t)layer * tc::kMaxSteps * 4,
+                          cudaMemcpyHostToDevice, st);
   cudaMemcpyToSymbolAsync(c_group_step_off, pl.group_step_off.data(), pl.group_step_off.size() * 4,
                           (size_t)layer * (tc::kMaxGroups + 1) * 4, cudaMemcpyHostToDevice, st);
   cudaMemcpyToSymbolAsync(c_group_ft, pl.group_ft.data(), pl.group_ft.size() * 4, (size_t)layer * 2 * tc::kMaxGroups * 4,
@@ -459,7 +462,7 @@ __global__ void __launch_bounds__(tc::kThreads, 1) conv_tc_kernel(const TcArgs a
         for (int s = s0; s < s1; ++s) {
           mbar_wait(empty_w + stage, ph_w ^ 1);
           mbar_expect_tx(full_w + stage, kTileBytes);
-          bulk_g2s(s_w + stage * kTileBytes, a.tiles + (size_t)__ldg(a.tile_seq + s) * (kTileBytes / 2), kTileBytes,
+          bulk_g2s(s_w + stage * kTileBytes, a.tiles + (size_t)c_tile_seq[a.layer][s] * (kTileBytes / 2), kTileBytes,
                    full_w + stage);
           if (++stage == kStages) {
             stage = 0;
