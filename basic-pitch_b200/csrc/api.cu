@@ -330,10 +330,7 @@ int forward_chunk(bp_model* m, const float* audio, const WinDesc* desc, int nb, 
   }
   {
     ProfScope ps(m, 4, st);
-    if (m->path == 1)
-      launch_contour2_nhwc(m->c1.p, m->cw, contour, nb, st);
-    else
-      launch_contour2(m->c1.p, m->cw, contour, nb, st);
+    launch_contour2(m->c1.p, m->cw, contour, nb, st);
     launch_note1(contour, m->cw, m->n1.p, nb, st);
     launch_note2(m->n1.p, m->cw, note, nb, st);
   }
@@ -346,10 +343,7 @@ int forward_chunk(bp_model* m, const float* audio, const WinDesc* desc, int nb, 
   }
   {
     ProfScope ps(m, 4, st);
-    if (m->path == 1)
-      launch_onset2_nhwc(note, m->o1.p, m->cw, onset, nb, st);
-    else
-      launch_onset2(note, m->o1.p, m->cw, onset, nb, st);
+    launch_onset2(note, m->o1.p, m->cw, onset, nb, st);
   }
   CKL();
   m->launches += 8 + 2 + 1 + 6 + (m->path == 1 ? 1 : 0);
@@ -874,15 +868,6 @@ int bp_debug_activation(bp_model_t* m, int which, float* h_out, int64_t n_window
   }
   CK(cudaDeviceSynchronize());
   CK(cudaMemcpy(h_out, src, sizeof(float) * per * n_windows, cudaMemcpyDeviceToHost));
-  if ((which == 1 || which == 3) && m->last_path == 1) {  // tensor-core path keeps these channels-last: return NCHW
-    const int C = which == 1 ? 8 : 32, Wd = which == 1 ? kContourBins : kPitches;
-    std::vector<float> tmp(h_out, h_out + per * n_windows);
-    for (int64_t b = 0; b < n_windows; ++b)
-      for (int t = 0; t < kFrames; ++t)
-        for (int f = 0; f < Wd; ++f)
-          for (int c = 0; c < C; ++c)
-            h_out[((b * C + c) * kFrames + t) * Wd + f] = tmp[((b * kFrames + t) * Wd + f) * C + c];
-  }
   return BP_OK;
 }
 

@@ -32,7 +32,7 @@
 //               a single issuing warp at this MMA size): program words from constant memory, descriptors are
 //               base + precomputed offset, 3 x tcgen05.mma per step by one elected lane, tcgen05.commit frees the
 //               weight stage / publishes the accumulators
-//   warps 2-5   epilogue: tcgen05.ld the accumulator columns, + bias, ReLU, store channels-last
+//   warps 2-5   epilogue: tcgen05.ld the accumulator columns, + bias, ReLU, float4 stores along frequency (planar)
 #include <cuda_bf16.h>
 
 #include <vector>
@@ -345,6 +345,11 @@ __device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&v)[3
         "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
       : "r"(taddr));
 }
+__device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, uint32_t (&v)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr));
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ------------------------------------------------------------------------------------------------
@@ -392,7 +397,7 @@ struct TcArgs {
   const int* tile_seq;          // per step: tile id
   const float* bias;            // [COUT]
   int layer;                    // which constant-memory program (0 contour, 1 onset)
-  float* out;                   // [B][172][WOUT][COUT]  (channels-last)
+  float* out;                   // [B][COUT][172][WOUT]  (planar, like the FP32 path)
   int rows_total, n_mtiles, n_windows;
   int n_groups, n_split;        // an item covers groups [s*n_groups/n_split, (s+1)*n_groups/n_split)
   int data_rows, row0;          // tile rows (128 + KH - 1); first data row of M-tile 0 (= 2 - PT)
@@ -529,19 +534,17 @@ __global__ void __launch_bounds__(tc::kThreads, 1) conv_tc_kernel(const TcArgs a
     float* s_bias = reinterpret_cast<float*>(tmem_slot + 2);  // 32 floats behind the barriers
     if (warp == 2) s_bias[lane] = __ldg(a.bias + (lane % a.cout));
     asm volatile("bar.sync 1, 128;" ::: "memory");
-    float bias[32];
-#pragma unroll
-    for (int j = 0; j < 32; ++j) bias[j] = s_bias[j];  // column j of a 32-column slab has channel j % COUT
     uint32_t ph_t[2] = {0, 0};
     uint32_t gcount = 0;
-    const size_t row_pitch = (size_t)a.wout * a.cout;
+    const size_t chan_pitch = (size_t)kFrames * a.wout;  // planar output [B][COUT][172][WOUT]
+    const int cshift = (a.cout == 8) ? 0 : 1;           // column of (fl, co): COUT = 8 -> fl*8 + co ; 32 -> fl*32 + co
     for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
       const int mt = it / a.n_split, sp = it % a.n_split;
       const int g0 = sp * a.n_groups / a.n_split, g1 = (sp + 1) * a.n_groups / a.n_split;
       const int m = mt * kMTile + row;
       const int b = m / kRowsPerWindow, t = m - b * kRowsPerWindow;
       const bool live = (b < a.n_windows) && (t < kFrames);
-      float* orow = a.out + ((size_t)b * kFrames + t) * row_pitch;
+      float* orow = a.out + (size_t)b * a.cout * chan_pitch + (size_t)t * a.wout;
       for (int g = g0; g < g1; ++g) {
         const uint32_t buf = gcount & 1u;
         mbar_wait(tmem_full + buf, ph_t[buf]);
@@ -551,23 +554,39 @@ __global__ void __launch_bounds__(tc::kThreads, 1) conv_tc_kernel(const TcArgs a
         for (int slot = 0; slot < 2; ++slot) {
           const int ft = c_group_ft[a.layer][2 * g + slot];
           if (ft < 0) continue;
-          const int n_valid = min(a.flt, a.wout - ft * a.flt) * a.cout;  // valid columns of this 128-column tile
-          float* dst = orow + (size_t)ft * 128;
           const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * 256u + (uint32_t)slot * 128u;
+          // one pass = 4 consecutive bins x 8 channels: 4 passes cover the 128 columns of the tile
 #pragma unroll 1
-          for (int c4 = 0; c4 < 4; ++c4) {
-            uint32_t v[32];
-            tmem_ld32_nowait(taddr + c4 * 32, v);
+          for (int pass = 0; pass < 4; ++pass) {
+            uint32_t v[32];  // v[fq * 8 + c] : bin quad index fq, channel c of the block
+            int f, co0;
+            if (cshift == 0) {  // COUT = 8: 32 consecutive columns are 4 bins x 8 channels
+              tmem_ld32_nowait(taddr + pass * 32, v);
+              f = ft * 16 + pass * 4;
+              co0 = 0;
+            } else {  // COUT = 32: the tile is 4 bins x 32 channels; take 8 channels of each bin
+              uint32_t(&v0)[8] = *reinterpret_cast<uint32_t(*)[8]>(&v[0]);
+              uint32_t(&v1)[8] = *reinterpret_cast<uint32_t(*)[8]>(&v[8]);
+              uint32_t(&v2)[8] = *reinterpret_cast<uint32_t(*)[8]>(&v[16]);
+              uint32_t(&v3)[8] = *reinterpret_cast<uint32_t(*)[8]>(&v[24]);
+              tmem_ld8_nowait(taddr + 0 * 32 + pass * 8, v0);
+              tmem_ld8_nowait(taddr + 1 * 32 + pass * 8, v1);
+              tmem_ld8_nowait(taddr + 2 * 32 + pass * 8, v2);
+              tmem_ld8_nowait(taddr + 3 * 32 + pass * 8, v3);
+              f = ft * 4;
+              co0 = pass * 8;
+            }
             tmem_ld_wait();
-            if (live) {
+            if (live && f < a.wout) {
 #pragma unroll
-              for (int i = 0; i < 8; ++i) {
+              for (int c = 0; c < 8; ++c) {
+                const float bv = s_bias[(co0 + c) & 31];
                 float4 o;
-                o.x = fmaxf(__uint_as_float(v[4 * i + 0]) + bias[4 * i + 0], 0.f);
-                o.y = fmaxf(__uint_as_float(v[4 * i + 1]) + bias[4 * i + 1], 0.f);
-                o.z = fmaxf(__uint_as_float(v[4 * i + 2]) + bias[4 * i + 2], 0.f);
-                o.w = fmaxf(__uint_as_float(v[4 * i + 3]) + bias[4 * i + 3], 0.f);
-                if (c4 * 32 + 4 * i < n_valid) reinterpret_cast<float4*>(dst + c4 * 32)[i] = o;
+                o.x = fmaxf(__uint_as_float(v[0 * 8 + c]) + bv, 0.f);
+                o.y = fmaxf(__uint_as_float(v[1 * 8 + c]) + bv, 0.f);
+                o.z = fmaxf(__uint_as_float(v[2 * 8 + c]) + bv, 0.f);
+                o.w = fmaxf(__uint_as_float(v[3 * 8 + c]) + bv, 0.f);
+                *reinterpret_cast<float4*>(orow + (size_t)(co0 + c) * chan_pitch + f) = o;
               }
             }
           }
