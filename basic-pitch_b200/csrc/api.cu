@@ -143,9 +143,9 @@ struct bp_model {
     TcConvPlan plan;
     TcConvDev dev{};
     DevBuf<uint16_t> tiles;
-    DevBuf<int> tile_seq;
-  } tc_contour, tc_onset;
-  DevBuf<__nv_bfloat16> yhl;
+  } tc_contour, tc_onset, tc_note;
+  DevBuf<__nv_bfloat16> yhl, chl;
+  size_t chl_zeroed = 0;  // elements of chl known to hold zeros in every row/bin the kernels never write
   int64_t launches = 0;
   // forward workspace (chunk windows)
   DevBuf<float> chain, y, c1, n1, o1, raw_note, raw_onset, raw_contour;
@@ -250,26 +250,27 @@ int derive(bp_model* m, cudaStream_t st) {
   CKL();
   m->launches += 1;
   // tensor-core plans: split-bf16 Toeplitz weight tiles + MMA programs (host-built from the parameter block)
-  std::vector<float> hw(7488 + 6400);
-  CK(cudaMemcpyAsync(hw.data(), m->d_params + ParamLayout::contour1_w, sizeof(float) * 7488, cudaMemcpyDeviceToHost, st));
-  CK(cudaMemcpyAsync(hw.data() + 7488, m->d_params + ParamLayout::onset1_w, sizeof(float) * 6400, cudaMemcpyDeviceToHost, st));
+  std::vector<float> hp(ParamLayout::total);
+  CK(cudaMemcpyAsync(hp.data(), m->d_params, sizeof(float) * ParamLayout::total, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
-  const TcConvSpec specs[2] = {tc_contour_spec(), tc_onset_spec()};
-  bp_model::TcLayer* layers[2] = {&m->tc_contour, &m->tc_onset};
-  const float* wsrc[2] = {hw.data(), hw.data() + 7488};
-  for (int l = 0; l < 2; ++l) {
+  const TcConvSpec specs[3] = {tc_contour_spec(), tc_onset_spec(), tc_note_spec()};
+  bp_model::TcLayer* layers[3] = {&m->tc_contour, &m->tc_onset, &m->tc_note};
+  const float* wsrc[3] = {hp.data() + ParamLayout::contour1_w, hp.data() + ParamLayout::onset1_w,
+                          hp.data() + ParamLayout::note1_w};
+  for (int l = 0; l < 3; ++l) {
     bp_model::TcLayer& L = *layers[l];
     L.plan.build(specs[l], wsrc[l]);
     const TcConvPlan& pl = L.plan;
     if (tc_upload_program(l, pl, st) != 0)
       return fail(BP_E_INVALID, "tensor-core program does not fit its constant-memory area");
     CK(L.tiles.reserve(pl.tiles.size()));
-    CK(L.tile_seq.reserve(pl.tile_seq.size()));
     CK(cudaMemcpyAsync(L.tiles.p, pl.tiles.data(), pl.tiles.size() * 2, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(L.tile_seq.p, pl.tile_seq.data(), pl.tile_seq.size() * 4, cudaMemcpyHostToDevice, st));
     CK(cudaStreamSynchronize(st));
-    L.dev = TcConvDev{pl.spec, L.tiles.p, L.tile_seq.p, pl.n_groups, l};
+    L.dev = TcConvDev{pl.spec, L.tiles.p, pl.n_groups, l};
   }
+  tc_upload_epilogue(hp.data() + ParamLayout::contour1_b, hp.data() + ParamLayout::onset1_b,
+                     hp.data() + ParamLayout::note1_b, hp.data() + ParamLayout::onset2_w, hp.data() + ParamLayout::note2_w, st);
+  CKL();
   return BP_OK;
 }
 
@@ -280,7 +281,17 @@ int ensure_forward_ws(bp_model* m, int nb) {
   CK(m->n1.reserve((size_t)nb * 32 * kFrames * kPitches));
   CK(m->o1.reserve((size_t)nb * 32 * kFrames * kPitches));
   CK(m->minmax.reserve((size_t)nb * 2));
-  CK(m->yhl.reserve((size_t)2 * 40 * 8 * tc_rows_total(nb)));
+  CK(m->yhl.reserve((size_t)2 * 40 * 8 * tc_rows_total(nb, tc_contour_spec().rows_per_window)));
+  {
+    const TcConvSpec ns = tc_note_spec();
+    const size_t need = (size_t)2 * ns.chunks8 * 8 * tc_rows_total(nb, ns.rows_per_window);
+    const __nv_bfloat16* before = m->chl.p;
+    CK(m->chl.reserve(need));
+    if (m->chl.p != before || m->chl_zeroed < m->chl.cap) {  // separator rows / pad bins are never written: zero once
+      CK(cudaMemset(m->chl.p, 0, m->chl.cap * sizeof(__nv_bfloat16)));
+      m->chl_zeroed = m->chl.cap;
+    }
+  }
   return BP_OK;
 }
 
@@ -319,34 +330,49 @@ int forward_chunk(bp_model* m, const float* audio, const WinDesc* desc, int nb, 
                m->minmax.p, nb, st);
     launch_lognorm(m->y.p, m->minmax.p, m->d_params + ParamLayout::bn, nb, st);
   }
-  {
-    ProfScope ps(m, 0, st);
-    if (m->path == 1) {
-      launch_y_split(m->y.p, m->yhl.p, nb, st);
-      launch_conv_tc(m->yhl.p, m->tc_contour.dev, m->cw.contour1_b, m->c1.p, nb, m->n_sms, st);
-    } else {
+  if (m->path == 1) {
+    const TcConvSpec cs = tc_contour_spec(), ns = tc_note_spec();
+    launch_split(m->y.p, m->yhl.p, cs, nb, st);
+    {
+      ProfScope ps(m, 0, st);
+      launch_conv_tc(m->yhl.p, m->tc_contour.dev, m->c1.p, nb, m->n_sms, st);
+    }
+    {
+      ProfScope ps(m, 4, st);
+      launch_contour2_tc(m->c1.p, m->cw, contour, m->chl.p, tc_rows_total(nb, ns.rows_per_window), nb, st);
+    }
+    {
+      ProfScope ps(m, 1, st);
+      launch_conv_tc(m->yhl.p, m->tc_onset.dev, m->o1.p, nb, m->n_sms, st);  // -> 9 tap planes
+    }
+    {
+      ProfScope ps(m, 4, st);
+      launch_conv_tc(m->chl.p, m->tc_note.dev, m->n1.p, nb, m->n_sms, st);  // -> 21 tap planes
+      launch_note_tapsum(m->n1.p, m->cw, note, nb, st);
+      launch_onset_tapsum(m->o1.p, note, m->cw, onset, nb, st);
+    }
+  } else {
+    {
+      ProfScope ps(m, 0, st);
       launch_contour1(m->y.p, m->cw, m->c1.p, nb, st);
     }
-  }
-  {
-    ProfScope ps(m, 4, st);
-    launch_contour2(m->c1.p, m->cw, contour, nb, st);
-    launch_note1(contour, m->cw, m->n1.p, nb, st);
-    launch_note2(m->n1.p, m->cw, note, nb, st);
-  }
-  {
-    ProfScope ps(m, 1, st);
-    if (m->path == 1)
-      launch_conv_tc(m->yhl.p, m->tc_onset.dev, m->cw.onset1_b, m->o1.p, nb, m->n_sms, st);
-    else
+    {
+      ProfScope ps(m, 4, st);
+      launch_contour2(m->c1.p, m->cw, contour, nb, st);
+      launch_note1(contour, m->cw, m->n1.p, nb, st);
+      launch_note2(m->n1.p, m->cw, note, nb, st);
+    }
+    {
+      ProfScope ps(m, 1, st);
       launch_onset1(m->y.p, m->cw, m->o1.p, nb, st);
-  }
-  {
-    ProfScope ps(m, 4, st);
-    launch_onset2(note, m->o1.p, m->cw, onset, nb, st);
+    }
+    {
+      ProfScope ps(m, 4, st);
+      launch_onset2(note, m->o1.p, m->cw, onset, nb, st);
+    }
   }
   CKL();
-  m->launches += 8 + 2 + 1 + 6 + (m->path == 1 ? 1 : 0);
+  m->launches += 8 + 2 + 1 + (m->path == 1 ? 7 : 6);
   m->last_path = m->path;
   return BP_OK;
 }
@@ -451,9 +477,8 @@ void bp_model_destroy(bp_model_t* m) {
   m->overflow.release(); m->d_note_off.release(); m->d_start.release(); m->d_end.release(); m->d_pitch.release();
   m->d_bend_off.release(); m->d_bends.release();
   m->yhl.release();
-  for (bp_model::TcLayer* L : {&m->tc_contour, &m->tc_onset}) {
-    L->tiles.release(); L->tile_seq.release();
-  }
+  m->chl.release();
+  for (bp_model::TcLayer* L : {&m->tc_contour, &m->tc_onset, &m->tc_note}) L->tiles.release();
   if (m->d_params) cudaFree(m->d_params);
   if (m->d_derived) cudaFree(m->d_derived);
   if (m->d_gauss) cudaFree(m->d_gauss);
@@ -809,9 +834,9 @@ int bp_transcribe_host(bp_model_t* m, const float* h_audio, const int64_t* h_sam
 
 int bp_debug_tc_plan(int which, const float* w, int32_t* sizes, uint16_t* tiles, int32_t* tile_seq, uint32_t* slot_words,
                      int32_t* group_step_off, int32_t* group_ft) {
-  if (!w || !sizes || which < 0 || which > 1) return fail(BP_E_INVALID, "bp_debug_tc_plan: bad argument");
+  if (!w || !sizes || which < 0 || which > 2) return fail(BP_E_INVALID, "bp_debug_tc_plan: bad argument");
   TcConvPlan pl;
-  pl.build(which == 0 ? tc_contour_spec() : tc_onset_spec(), w);
+  pl.build(which == 0 ? tc_contour_spec() : which == 1 ? tc_onset_spec() : tc_note_spec(), w);
   sizes[0] = pl.n_tiles;
   sizes[1] = (int32_t)pl.tile_seq.size();
   sizes[2] = pl.n_uses;
@@ -866,8 +891,19 @@ int bp_debug_activation(bp_model_t* m, int which, float* h_out, int64_t n_window
     case 3: src = m->o1.p; per = (size_t)32 * kFrames * kPitches; break;
     default: return fail(BP_E_INVALID, "bp_debug_activation: unknown activation id");
   }
+  if (m->last_path == 1 && which >= 2)
+    return fail(BP_E_INVALID, "bp_debug_activation: the tensor-core path never materialises the 32-channel activations "
+                              "(use bp_model_set_path(m, 0))");
   CK(cudaDeviceSynchronize());
   CK(cudaMemcpy(h_out, src, sizeof(float) * per * n_windows, cudaMemcpyDeviceToHost));
+  if (which == 1 && m->last_path == 1) {  // the tensor-core path keeps this activation channels-last: return NCHW
+    std::vector<float> tmp(h_out, h_out + per * n_windows);
+    for (int64_t b = 0; b < n_windows; ++b)
+      for (int t = 0; t < kFrames; ++t)
+        for (int f = 0; f < kContourBins; ++f)
+          for (int c = 0; c < 8; ++c)
+            h_out[((b * 8 + c) * kFrames + t) * kContourBins + f] = tmp[((b * kFrames + t) * kContourBins + f) * 8 + c];
+  }
   return BP_OK;
 }
 

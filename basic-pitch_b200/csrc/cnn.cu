@@ -47,6 +47,10 @@ struct NhwcIn {
     if ((unsigned)t >= (unsigned)kFrames || (unsigned)g >= (unsigned)W) return 0.f;
     return __ldg(p + (((size_t)b * kFrames + t) * W + g) * C + ci);
   }
+  __device__ __forceinline__ float4 load4(int b, int c4, int t, int g) const {
+    if ((unsigned)t >= (unsigned)kFrames || (unsigned)g >= (unsigned)W) return make_float4(0.f, 0.f, 0.f, 0.f);
+    return __ldg(reinterpret_cast<const float4*>(p + (((size_t)b * kFrames + t) * W + g) * C + c4));
+  }
 };
 // channel 0 = note posteriorgram [B][172][88], channels 1..32 = onset conv1 output [B][32][172][88]
 struct ConcatIn {
@@ -57,18 +61,6 @@ struct ConcatIn {
     if ((unsigned)t >= (unsigned)kFrames || (unsigned)g >= (unsigned)kPitches) return 0.f;
     if (ci == 0) return __ldg(note + ((size_t)b * kFrames + t) * kPitches + g);
     return __ldg(o1 + (((size_t)b * 32 + (ci - 1)) * kFrames + t) * kPitches + g);
-  }
-};
-
-// same, with the onset conv1 output channels-last [B][172][88][32] (tensor-core path)
-struct ConcatNhwcIn {
-  static constexpr bool kChannelsLast = true;
-  const float* note;
-  const float* o1;
-  __device__ __forceinline__ float load(int b, int ci, int t, int g) const {
-    if ((unsigned)t >= (unsigned)kFrames || (unsigned)g >= (unsigned)kPitches) return 0.f;
-    if (ci == 0) return __ldg(note + ((size_t)b * kFrames + t) * kPitches + g);
-    return __ldg(o1 + (((size_t)b * kFrames + t) * kPitches + g) * 32 + (ci - 1));
   }
 };
 
@@ -212,10 +204,16 @@ struct Conv1Cfg {
   static_assert(CIN % CIC == 0, "channel blocking");
 };
 
+struct SplitOut {           // optional bf16 hi/lo copy of the output in the tensor-core row layout (tc_conv.cu)
+  __nv_bfloat16* planes;    // [2][chunks8][rows_total][8]; nullptr = off
+  int rows_total, chunks8, rows_per_window, lead;
+};
+
 template <class Cfg, class In>
 __global__ void __launch_bounds__(Cfg::THREADS) conv1_kernel(In in, const float* __restrict__ w /* [CIN*KH*KW] */,
                                                              const float* __restrict__ bias,
-                                                             float* __restrict__ out /* [B][172][WOUT] */) {
+                                                             float* __restrict__ out /* [B][172][WOUT] */,
+                                                             SplitOut so) {
   extern __shared__ float smem[];
   float* in_s = smem;
   float* w_s = smem + Cfg::IN_ELEMS;
@@ -235,19 +233,29 @@ __global__ void __launch_bounds__(Cfg::THREADS) conv1_kernel(In in, const float*
 
   for (int c0 = 0; c0 < Cfg::CIN; c0 += Cfg::CIC) {
     __syncthreads();
-    for (int e = tid; e < Cfg::CIC * Cfg::ROWS * Cfg::NEED; e += Cfg::THREADS) {
-      int x, r, c;
-      if (In::kChannelsLast) {  // channels are contiguous in memory: walk them fastest for coalesced reads
-        c = e % Cfg::CIC;
-        x = (e / Cfg::CIC) % Cfg::NEED;
-        r = e / (Cfg::CIC * Cfg::NEED);
-      } else {
-        x = e % Cfg::NEED;
-        r = (e / Cfg::NEED) % Cfg::ROWS;
-        c = e / (Cfg::NEED * Cfg::ROWS);
+    if constexpr (In::kChannelsLast) {
+      // channels-last input: every tile row is one contiguous run of NEED x CIN floats -> float4 loads
+      static_assert(Cfg::CIC == Cfg::CIN && Cfg::CIN % 4 == 0, "channels-last staging takes all channels in one pass");
+      constexpr int V = Cfg::CIN / 4;
+      for (int e = tid; e < Cfg::ROWS * Cfg::NEED * V; e += Cfg::THREADS) {
+        const int c4 = (e % V) * 4;
+        const int x = (e / V) % Cfg::NEED;
+        const int r = e / (V * Cfg::NEED);
+        const float4 v = in.load4(b, c4, t0 - Cfg::PT + r, f0 - Cfg::PL + x);
+        float* d = in_s + (c4 * Cfg::ROWS + r) * Cfg::RS + (x & 3) * Cfg::PH + (x >> 2);
+        d[0] = v.x;
+        d[Cfg::ROWS * Cfg::RS] = v.y;
+        d[2 * Cfg::ROWS * Cfg::RS] = v.z;
+        d[3 * Cfg::ROWS * Cfg::RS] = v.w;
       }
-      in_s[(c * Cfg::ROWS + r) * Cfg::RS + (x & 3) * Cfg::PH + (x >> 2)] =
-          in.load(b, c0 + c, t0 - Cfg::PT + r, f0 - Cfg::PL + x);
+    } else {
+      for (int e = tid; e < Cfg::CIC * Cfg::ROWS * Cfg::NEED; e += Cfg::THREADS) {
+        const int x = e % Cfg::NEED;
+        const int r = (e / Cfg::NEED) % Cfg::ROWS;
+        const int c = e / (Cfg::NEED * Cfg::ROWS);
+        in_s[(c * Cfg::ROWS + r) * Cfg::RS + (x & 3) * Cfg::PH + (x >> 2)] =
+            in.load(b, c0 + c, t0 - Cfg::PT + r, f0 - Cfg::PL + x);
+      }
     }
     __syncthreads();
 #pragma unroll 1
@@ -283,8 +291,51 @@ __global__ void __launch_bounds__(Cfg::THREADS) conv1_kernel(In in, const float*
       o.z = 1.f / (1.f + expf(-(acc[q][2] + bv)));
       o.w = 1.f / (1.f + expf(-(acc[q][3] + bv)));
       *reinterpret_cast<float4*>(out + ((size_t)b * kFrames + t) * Cfg::WOUT + f) = o;
+      if (so.planes) {  // hi/lo bf16 split for the tensor-core consumer: 4 bins = half of an 8-bin chunk
+        const float ov[4] = {o.x, o.y, o.z, o.w};
+        __align__(8) __nv_bfloat16 hi[4], lo[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          hi[j] = __float2bfloat16_rn(ov[j]);
+          lo[j] = __float2bfloat16_rn(ov[j] - __bfloat162float(hi[j]));
+        }
+        const size_t d = (size_t)so.lead + (size_t)b * so.rows_per_window + t;
+        const size_t off = ((size_t)(f >> 3) * so.rows_total + d) * 8 + (f & 7);
+        const size_t plane = (size_t)so.chunks8 * so.rows_total * 8;
+        *reinterpret_cast<uint2*>(so.planes + off) = *reinterpret_cast<const uint2*>(hi);
+        *reinterpret_cast<uint2*>(so.planes + plane + off) = *reinterpret_cast<const uint2*>(lo);
+      }
     }
   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Second convs of the note / onset branches after the tensor-core epilogue has reduced the 32 channels:
+//   out[t][f] = sigmoid(bias + sum_{dt,df} P[dt*KW+df][t+dt-PT][f+df-PL] (+ sum x[t+dt-PT][f+df-PL] * wx[dt*KW+df]))
+// ------------------------------------------------------------------------------------------------
+template <int KH, int KW, int PT, int PL, bool EXTRA>
+__global__ void tap_sum_kernel(const float* __restrict__ P /* [B][KH*KW][172][88] */, const float* __restrict__ x,
+                               const float* __restrict__ wx, const float* __restrict__ bias, float* __restrict__ out,
+                               int n_windows) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = blockIdx.y;
+  if (idx >= kFrames * kPitches) return;
+  const int t = idx / kPitches, f = idx - t * kPitches;
+  float acc = __ldg(bias);
+  const float* Pb = P + (size_t)b * KH * KW * kFrames * kPitches;
+#pragma unroll
+  for (int dt = 0; dt < KH; ++dt) {
+    const int tt = t + dt - PT;
+    if ((unsigned)tt >= (unsigned)kFrames) continue;
+#pragma unroll
+    for (int df = 0; df < KW; ++df) {
+      const int ff = f + df - PL;
+      if ((unsigned)ff >= (unsigned)kPitches) continue;
+      acc += __ldg(Pb + ((size_t)(dt * KW + df) * kFrames + tt) * kPitches + ff);
+      if (EXTRA) acc = fmaf(__ldg(x + ((size_t)b * kFrames + tt) * kPitches + ff), __ldg(wx + dt * KW + df), acc);
+    }
+  }
+  out[((size_t)b * kFrames + t) * kPitches + f] = 1.f / (1.f + expf(-acc));
 }
 
 //                           CIN CIC KH KW PT PL WOUT TR
@@ -292,7 +343,6 @@ using Contour2Cfg1 = Conv1Cfg<8, 4, 5, 5, 2, 2, 264, 11>;
 using Contour2CfgN = Conv1Cfg<8, 8, 5, 5, 2, 2, 264, 5>;  // channels-last input
 using Note2Cfg1 = Conv1Cfg<32, 4, 7, 3, 3, 1, 88, 11>;
 using Onset2Cfg1 = Conv1Cfg<33, 3, 3, 3, 1, 1, 88, 11>;
-using Onset2CfgN = Conv1Cfg<33, 11, 3, 3, 1, 1, 88, 5>;   // channels-last input: whole 44-byte channel runs per pass
 
 //                         CIN CIC COUT COB KH  KW SF PT PL  WOUT TT  FL P  ACT
 using Contour1Cfg = ConvCfg<8, 8, 8, 8, 3, 39, 1, 1, 19, 264, 12, 22, 4, ACT_RELU>;
@@ -309,9 +359,10 @@ static void set_attr1() {
   cudaFuncSetAttribute(conv1_kernel<Cfg, In>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
 }
 template <class Cfg, class In>
-static void launch1(In in, const float* w, const float* bias, float* out, int n_windows, cudaStream_t st) {
+static void launch1(In in, const float* w, const float* bias, float* out, int n_windows, cudaStream_t st,
+                    SplitOut so = SplitOut{nullptr, 0, 0, 0, 0}) {
   dim3 grid(Cfg::FTILES * Cfg::TTILES, n_windows);
-  conv1_kernel<Cfg, In><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(in, w, bias, out);
+  conv1_kernel<Cfg, In><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(in, w, bias, out, so);
 }
 
 void cnn_setup() {
@@ -319,7 +370,6 @@ void cnn_setup() {
   set_attr1<Contour2CfgN, NhwcIn<8, 264>>();
   set_attr1<Note2Cfg1, PlanarIn<32, 88>>();
   set_attr1<Onset2Cfg1, ConcatIn>();
-  set_attr1<Onset2CfgN, ConcatNhwcIn>();
   set_attr<Contour1Cfg, StackIn>();
   set_attr<Note1Cfg, PlanarIn<1, 264>>();
   set_attr<Onset1Cfg, StackIn>();
@@ -337,11 +387,20 @@ void launch_contour1(const float* y, const CnnWeights& w, float* c1, int n, cuda
 void launch_contour2(const float* c1, const CnnWeights& w, float* contour, int n, cudaStream_t st) {
   launch1<Contour2Cfg1>(PlanarIn<8, 264>{c1}, w.contour2_wT, w.contour2_b, contour, n, st);
 }
-void launch_onset2_nhwc(const float* note, const float* o1, const CnnWeights& w, float* onset, int n, cudaStream_t st) {
-  launch1<Onset2CfgN>(ConcatNhwcIn{note, o1}, w.onset2_wT, w.onset2_b, onset, n, st);
+void launch_contour2_tc(const float* c1, const CnnWeights& w, float* contour, __nv_bfloat16* chl, int rows_total, int n,
+                        cudaStream_t st) {
+  const TcConvSpec sp = tc_note_spec();
+  launch1<Contour2CfgN>(NhwcIn<8, 264>{c1}, w.contour2_wT, w.contour2_b, contour, n, st,
+                        SplitOut{chl, rows_total, sp.chunks8, sp.rows_per_window, sp.lead_rows});
 }
-void launch_contour2_nhwc(const float* c1, const CnnWeights& w, float* contour, int n, cudaStream_t st) {
-  launch1<Contour2CfgN>(NhwcIn<8, 264>{c1}, w.contour2_wT, w.contour2_b, contour, n, st);
+void launch_note_tapsum(const float* p21, const CnnWeights& w, float* note, int n, cudaStream_t st) {
+  tap_sum_kernel<7, 3, 3, 1, false><<<dim3((kFrames * kPitches + 255) / 256, n), 256, 0, st>>>(p21, nullptr, nullptr,
+                                                                                               w.note2_b, note, n);
+}
+void launch_onset_tapsum(const float* p9, const float* note, const CnnWeights& w, float* onset, int n, cudaStream_t st) {
+  // channel 0 of the onset conv2 weights multiplies the note posteriorgram (models.py:305: concat[note, onset1])
+  tap_sum_kernel<3, 3, 1, 1, true><<<dim3((kFrames * kPitches + 255) / 256, n), 256, 0, st>>>(p9, note, w.onset2_wT,
+                                                                                              w.onset2_b, onset, n);
 }
 void launch_note1(const float* contour, const CnnWeights& w, float* n1, int n, cudaStream_t st) {
   launch<Note1Cfg>(PlanarIn<1, 264>{contour}, w.note1_wT, w.note1_b, n1, n, st);

@@ -36,39 +36,50 @@ void launch_onset1(const float* y, const CnnWeights& w, float* o1, int n_windows
 void launch_onset2(const float* note, const float* o1, const CnnWeights& w, float* onset, int n_windows,
                    cudaStream_t st);
 
-void launch_contour2_nhwc(const float* c1_nhwc, const CnnWeights& w, float* contour, int n_windows, cudaStream_t st);
 
-// ---- tc_conv.cu (tcgen05 path of the two convolutions that read the harmonic stack) ---------------
+// ---- tc_conv.cu (tcgen05 path of the three wide convolutions) ------------------------------------
 struct TcConvSpec {
   int KH, KW, SF, PT, PL, COUT, FLT, WOUT;  // taps, frequency stride, pads, channels, bins per 128-column tile, output bins
+  int n_ci;                                 // input channels (harmonics of y, or 1 for the contour posteriorgram)
+  int shifts[8];                            // frequency shift of every input channel (harmonic stacking)
+  int data_bins, chunks8;                   // bins of the input rows and 8-bin chunks of the split layout (even)
+  int rows_per_window, lead_rows;           // row layout of the split input: 172 frames + >= PT zero rows per window
+  int epi, taps;                            // epilogue: 0 = bias+ReLU channels-last; 1/2 = fused reduction to `taps` planes
 };
 TcConvSpec tc_contour_spec();
 TcConvSpec tc_onset_spec();
+TcConvSpec tc_note_spec();
 struct TcConvPlan {  // host side: weight tiles + the per-group MMA programs
   TcConvSpec spec{};
-  std::vector<uint16_t> tiles;       // n_tiles x 4096 bf16 : [plane hi/lo][k-chunk 2][n 128][8]
-  std::vector<int> tile_seq;         // per step: tile id
+  std::vector<uint16_t> tiles;          // n_tiles x 4096 bf16 : [plane hi/lo][k-chunk 2][n 128][8]
+  std::vector<int> tile_seq;            // per step: tile id
   std::vector<uint32_t> slot_words[2];  // per step and accumulator slot: A offset >> 4 | first << 15, or 0xffffffff
-  std::vector<int> group_step_off;   // [n_groups + 1]
-  std::vector<int> group_ft;         // [n_groups][2] frequency tiles of the group (-1 = none)
+  std::vector<int> group_step_off;      // [n_groups + 1]
+  std::vector<int> group_ft;            // [n_groups][2] frequency tiles of the group (-1 = none)
   int n_tiles = 0, n_groups = 0, n_uses = 0;
-  void build(const TcConvSpec& spec, const float* w /* [COUT][8][KH][KW] */);
+  void build(const TcConvSpec& spec, const float* w /* [COUT][n_ci][KH][KW] */);
 };
 struct TcConvDev {
   TcConvSpec spec;
   const uint16_t* tiles;
-  const int* tile_seq;
   int n_groups;
-  int layer;  // index of the program in constant memory (0 contour, 1 onset)
+  int layer;  // index of the program in constant memory (0 contour, 1 onset, 2 note)
 };
 int tc_upload_program(int layer, const TcConvPlan& plan, cudaStream_t st);  // 0 on success
-int tc_rows_total(int n_windows);
+void tc_upload_epilogue(const float* contour1_b, const float* onset1_b, const float* note1_b, const float* onset2_w,
+                        const float* note2_w, cudaStream_t st);
+int tc_rows_total(int n_windows, int rows_per_window);
 void tc_setup();
-void launch_y_split(const float* y, __nv_bfloat16* yhl, int n_windows, cudaStream_t st);
-void launch_conv_tc(const __nv_bfloat16* yhl, const TcConvDev& dev, const float* bias, float* out_nhwc, int n_windows,
-                    int n_sms, cudaStream_t st);
-void launch_onset2_nhwc(const float* note, const float* o1_nhwc, const CnnWeights& w, float* onset, int n_windows,
-                        cudaStream_t st);
+void launch_split(const float* src, __nv_bfloat16* dst, const TcConvSpec& spec, int n_windows, cudaStream_t st);
+void launch_conv_tc(const __nv_bfloat16* data, const TcConvDev& dev, float* out, int n_windows, int n_sms, cudaStream_t st);
+// contour conv2 on the channels-last output of the tensor-core contour conv; also emits the bf16 hi/lo split of the
+// contour posteriorgram in the layout of tc_note_spec()
+void launch_contour2_tc(const float* c1_nhwc, const CnnWeights& w, float* contour, __nv_bfloat16* chl, int rows_total,
+                        int n_windows, cudaStream_t st);
+// second convs after the fused channel reduction: shifted sums over the tap planes (+ the note input of the onset conv)
+void launch_note_tapsum(const float* p21, const CnnWeights& w, float* note, int n_windows, cudaStream_t st);
+void launch_onset_tapsum(const float* p9, const float* note, const CnnWeights& w, float* onset, int n_windows,
+                         cudaStream_t st);
 
 // ---- unwrap (api.cu) / decode.cu ----------------------------------------------------------------
 struct DecodeParamsDev {

@@ -1,12 +1,16 @@
-// The two convolutions that read the harmonic stack — contour (8 -> 8 channels, 3 x 39 taps, 65 % of the
-// model's FLOPs) and onset (8 -> 32 channels, 5 x 5 taps, frequency stride 3, 18 %) — on the 5th-gen tensor
-// cores: tcgen05.mma (kind::f16, bf16 operands, fp32 accumulators in TMEM), operands staged in shared
+// The three wide convolutions — contour (8 -> 8 channels, 3 x 39 taps, 65 % of the model's FLOPs), onset
+// (8 -> 32 channels, 5 x 5 taps, frequency stride 3, 18 %) and note (1 -> 32 channels, 7 x 7, stride 3, 4.5 %) —
+// on the 5th-gen tensor cores: tcgen05.mma (kind::f16, bf16 operands, fp32 accumulators in TMEM), operands staged in shared
 // memory by bulk async copies (UBLKCP) signalled through mbarriers, warp-specialised roles.
 //
 // Replaces nodes 231/232 (contour conv + ReLU, reference: basic_pitch/models.py:241-250) and 230/243 (onset
 // conv + ReLU, reference: basic_pitch/models.py:295-304) of the deployed graph, and the harmonic stacking in
 // front of them (reference: basic_pitch/nn.py:69-88), which is folded into the weight operand and never
-// materialised.  One kernel, two specs (TcConvSpec).
+// materialised; node 238/239 (note conv1 + ReLU, models.py:270-279) reads the contour posteriorgram instead.
+// One kernel template, three specs (TcConvSpec).  For the two 32-channel layers the epilogue also applies the
+// channel reduction of the following single-output conv (onset conv2 models.py:305-313, note conv2 :282-290):
+// it emits P[tap][t][f] = sum_c relu(conv1)[c][t][f] * w2[c][tap], so the 32-channel activations never reach
+// HBM and the second conv degenerates to a 9- / 21-tap shifted sum (cnn.cu: tap_sum_kernel).
 //
 // Formulation ("Toeplitz along frequency on 16-bin aligned chunks")
 //   rows  m = b*174 + t            time frames of all windows of the chunk, two zero rows between windows
@@ -32,7 +36,8 @@
 //               a single issuing warp at this MMA size): program words from constant memory, descriptors are
 //               base + precomputed offset, 3 x tcgen05.mma per step by one elected lane, tcgen05.commit frees the
 //               weight stage / publishes the accumulators
-//   warps 2-5   epilogue: tcgen05.ld the accumulator columns, + bias, ReLU, float4 stores along frequency (planar)
+//   warps 2-5   epilogue: tcgen05.ld the accumulator columns, + bias, ReLU, then either a channels-last store
+//               (contour) or the fused 32 -> taps reduction with planar float4 stores (onset, note)
 #include <cuda_bf16.h>
 
 #include <vector>
@@ -42,19 +47,14 @@
 namespace bp {
 
 namespace tc {
-constexpr int kRowsPerWindow = kFrames + 2;  // 174: two zero separator rows after every window (time pad <= 2)
-constexpr int kLeadRows = 2;                 // zero rows in front of the first window
 constexpr int kMTile = 128;
-constexpr int kMaxDataRows = kMTile + 4;                         // 132 (KH = 5)
-constexpr int kChunks8 = 40;                                     // 320 bins / 8
-constexpr int kMaxDataBytes = 2 * kChunks8 * kMaxDataRows * 16;  // hi + lo = 168960
+constexpr int kMaxDataBytes = 2 * 40 * (kMTile + 4) * 16;        // hi + lo planes, 40 chunks x 132 rows = 168960
 constexpr int kTileBytes = 8192;                                 // weight tile: [plane 2][kchunk 2][128][8] bf16
 constexpr int kStages = 6;
 constexpr int kMaxSteps = 1024;                                  // program steps per layer (constant memory)
 constexpr int kMaxGroups = 15;
 constexpr int kThreads = 224;
 constexpr int kSmemBytes = kMaxDataBytes + kStages * kTileBytes + 512;
-constexpr int kShift[kHarmonics] = {-36, 0, 36, 57, 72, 84, 93, 101};
 // step word of a slot: [0,14) A start-address offset >> 4, [15] first MMA into that accumulator; kNoUse = the
 // slot's frequency tile does not use this step's weight tile
 constexpr uint32_t kUseFirstAcc = 1u << 15, kNoUse = 0xffffffffu;
@@ -77,10 +77,12 @@ static inline float bf2f(uint16_t h) {
   return f;
 }
 
-TcConvSpec tc_contour_spec() { return TcConvSpec{3, 39, 1, 1, 19, 8, 16, 264}; }
-TcConvSpec tc_onset_spec() { return TcConvSpec{5, 5, 3, 2, 1, 32, 4, 88}; }
+//                                      KH KW SF PT PL COUT FLT WOUT n_ci  shifts                              bins ch8 rows/win lead epi taps
+TcConvSpec tc_contour_spec() { return {3, 39, 1, 1, 19, 8, 16, 264, 8, {-36, 0, 36, 57, 72, 84, 93, 101}, 309, 40, 174, 2, 0, 0}; }
+TcConvSpec tc_onset_spec() { return {5, 5, 3, 2, 1, 32, 4, 88, 8, {-36, 0, 36, 57, 72, 84, 93, 101}, 309, 40, 174, 2, 1, 9}; }
+TcConvSpec tc_note_spec() { return {7, 7, 3, 3, 2, 32, 4, 88, 1, {0, 0, 0, 0, 0, 0, 0, 0}, 264, 34, 175, 3, 2, 21}; }
 
-void TcConvPlan::build(const TcConvSpec& sp, const float* W /* [COUT][8][KH][KW] */) {
+void TcConvPlan::build(const TcConvSpec& sp, const float* W /* [COUT][n_ci][KH][KW] */) {
   using namespace tc;
   spec = sp;
   tiles.clear();
@@ -104,7 +106,7 @@ void TcConvPlan::build(const TcConvSpec& sp, const float* W /* [COUT][8][KH][KW]
     for (size_t i = 0; i < keys.size(); ++i)
       if (keys[i].ci == k.ci && keys[i].dt == k.dt && keys[i].off == k.off && keys[i].variant == k.variant) return (int)i;
     keys.push_back(k);
-    const int s = kShift[k.ci];
+    const int s = sp.shifts[k.ci];
     const size_t base = tiles.size();
     tiles.resize(base + kTileBytes / 2, 0);
     for (int kk = 0; kk < 16; ++kk) {
@@ -119,7 +121,7 @@ void TcConvPlan::build(const TcConvSpec& sp, const float* W /* [COUT][8][KH][KW]
           } else if (k.variant == 2) {  // chunk straddles g = 264
             keep = (16 * ((kContourBins + s) / 16) + kk - s) < kContourBins;
           }
-          if (keep) w = W[((co * 8 + k.ci) * sp.KH + k.dt) * sp.KW + df];
+          if (keep) w = W[((co * sp.n_ci + k.ci) * sp.KH + k.dt) * sp.KW + df];
         }
         const uint16_t hi = f2bf(w);
         const uint16_t lo = f2bf(w - bf2f(hi));
@@ -150,8 +152,8 @@ void TcConvPlan::build(const TcConvSpec& sp, const float* W /* [COUT][8][KH][KW]
       int tile, slot, q, dt;
     };
     std::vector<Use> uses;
-    for (int ci = 0; ci < 8; ++ci) {
-      const int s = kShift[ci];
+    for (int ci = 0; ci < sp.n_ci; ++ci) {
+      const int s = sp.shifts[ci];
       for (int dt = 0; dt < sp.KH; ++dt) {
         for (int off = -160; off <= 480; ++off) {
           for (int variant = 0; variant < 3; ++variant) {
@@ -161,18 +163,18 @@ void TcConvPlan::build(const TcConvSpec& sp, const float* W /* [COUT][8][KH][KW]
               const int num = off + sp.SF * sp.FLT * ft;
               if (num < 0 || num % 16 != 0) continue;
               const int q = num / 16;
-              if (q >= 20) continue;
+              if (q >= sp.chunks8 / 2) continue;
               bool any = false;
               for (int kk = 0; kk < 16 && !any; ++kk)
                 for (int fl = 0; fl < sp.FLT && !any; ++fl) {
                   const int u = 16 * q + kk, f = ft * sp.FLT + fl, gg = u - s;
                   const int df = gg - sp.SF * f + sp.PL;
-                  if (df >= 0 && df < sp.KW && gg >= 0 && gg < kContourBins && u < kCqtBins && f < sp.WOUT) any = true;
+                  if (df >= 0 && df < sp.KW && gg >= 0 && gg < kContourBins && u < sp.data_bins && f < sp.WOUT) any = true;
                 }
               if (!any) continue;
               int need = 0;
               if (s > 0 && s % 16 != 0 && q == s / 16) need = 1;
-              if (kContourBins + s < 320 && (kContourBins + s) % 16 != 0 && q == (kContourBins + s) / 16) need = 2;
+              if (kContourBins + s < sp.chunks8 * 8 && (kContourBins + s) % 16 != 0 && q == (kContourBins + s) / 16) need = 2;
               if (need != variant) continue;
               uses.push_back(Use{find_or_add(Key{ci, dt, off, variant}), slot, q, dt});
             }
@@ -208,13 +210,33 @@ void TcConvPlan::build(const TcConvSpec& sp, const float* W /* [COUT][8][KH][KW]
 // The MMA programs live in constant memory: the issuing warp indexes them with warp-uniform values, so the words,
 // the descriptors derived from them and the loop state stay in uniform registers (no per-use R2UR traffic).
 // They depend only on the layer geometry (TcConvSpec), not on the weights.
-__constant__ uint32_t c_prog[2][2][tc::kMaxSteps];  // [layer][slot][step]
-__constant__ int c_tile_seq[2][tc::kMaxSteps];       // [layer][step] -> weight tile id
-__constant__ int c_group_step_off[2][tc::kMaxGroups + 1];
-__constant__ int c_group_ft[2][2 * tc::kMaxGroups];
+__constant__ uint32_t c_prog[3][2][tc::kMaxSteps];  // [layer][slot][step]
+__constant__ int c_tile_seq[3][tc::kMaxSteps];       // [layer][step] -> weight tile id
+__constant__ int c_group_step_off[3][tc::kMaxGroups + 1];
+__constant__ int c_group_ft[3][2 * tc::kMaxGroups];
+// epilogue constants: conv1 bias and the weights of the fused channel reduction (conv2), [channel][tap]
+__constant__ float c_bias1[3][32];
+__constant__ float c_red_onset[32][9];
+__constant__ float c_red_note[32][21];
+
+void tc_upload_epilogue(const float* contour1_b, const float* onset1_b, const float* note1_b, const float* onset2_w,
+                        const float* note2_w, cudaStream_t st) {
+  float b[3][32] = {};
+  for (int i = 0; i < 8; ++i) b[0][i] = contour1_b[i];
+  for (int i = 0; i < 32; ++i) b[1][i] = onset1_b[i], b[2][i] = note1_b[i];
+  float ro[32][9], rn[32][21];
+  for (int c = 0; c < 32; ++c) {
+    for (int t = 0; t < 9; ++t) ro[c][t] = onset2_w[(1 + c) * 9 + t];  // channel 0 of onset conv2 is the note input
+    for (int t = 0; t < 21; ++t) rn[c][t] = note2_w[c * 21 + t];
+  }
+  cudaMemcpyToSymbolAsync(c_bias1, b, sizeof(b), 0, cudaMemcpyHostToDevice, st);
+  cudaMemcpyToSymbolAsync(c_red_onset, ro, sizeof(ro), 0, cudaMemcpyHostToDevice, st);
+  cudaMemcpyToSymbolAsync(c_red_note, rn, sizeof(rn), 0, cudaMemcpyHostToDevice, st);
+  cudaStreamSynchronize(st);
+}
 
 int tc_upload_program(int layer, const TcConvPlan& pl, cudaStream_t st) {
-  if (layer < 0 || layer > 1 || (int)pl.tile_seq.size() > tc::kMaxSteps - 1 || pl.n_groups > tc::kMaxGroups) return -1;
+  if (layer < 0 || layer > 2 || (int)pl.tile_seq.size() > tc::kMaxSteps - 1 || pl.n_groups > tc::kMaxGroups) return -1;
   for (int sl = 0; sl < 2; ++sl)
     cudaMemcpyToSymbolAsync(c_prog, pl.slot_words[sl].data(), pl.slot_words[sl].size() * 4,
                             ((size_t)layer * 2 + sl) * tc::kMaxSteps * 4, cudaMemcpyHostToDevice, st);
@@ -345,35 +367,31 @@ __device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&v)[3
         "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
       : "r"(taddr));
 }
-__device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, uint32_t (&v)[8]) {
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
-               : "r"(taddr));
-}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ------------------------------------------------------------------------------------------------
-// y (fp32, [B][172][309]) -> bf16 hi/lo planes in the k-chunk-major row layout the MMA reads:
-//   yhl[plane][q8 (40)][row d (rows_total)][8],  d = 2 + b*174 + t, every other row zero.
+// src (fp32, [B][172][bins]) -> bf16 hi/lo planes in the k-chunk-major row layout the MMA reads:
+//   dst[plane][q8 (chunks8)][row d (rows_total)][8],  d = lead + b*rows_per_window + t, every other row zero.
+// Used for y (309 bins -> 40 chunks) and for the contour posteriorgram (264 bins -> 34 chunks).
 // ------------------------------------------------------------------------------------------------
-__global__ void y_split_kernel(const float* __restrict__ y, __nv_bfloat16* __restrict__ yhl, int n_windows,
-                               int rows_total) {
+__global__ void split_kernel(const float* __restrict__ src, int bins, __nv_bfloat16* __restrict__ dst, int n_windows,
+                             int rows_total, int chunks8, int rows_per_window, int lead) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // one (row, q8) per thread
-  const long long total = (long long)rows_total * tc::kChunks8;
+  const long long total = (long long)rows_total * chunks8;
   if (idx >= total) return;
   const int d = (int)(idx % rows_total);  // rows fastest: 16-byte stores of a warp are contiguous
   const int q8 = (int)(idx / rows_total);
   float v[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) v[j] = 0.f;
-  const int m = d - tc::kLeadRows;
+  const int m = d - lead;
   if (m >= 0) {
-    const int b = m / tc::kRowsPerWindow, t = m - b * tc::kRowsPerWindow;
+    const int b = m / rows_per_window, t = m - b * rows_per_window;
     if (b < n_windows && t < kFrames) {
-      const float* src = y + ((size_t)b * kFrames + t) * kCqtBins + q8 * 8;
+      const float* p = src + ((size_t)b * kFrames + t) * bins + q8 * 8;
 #pragma unroll
       for (int j = 0; j < 8; ++j)
-        if (q8 * 8 + j < kCqtBins) v[j] = __ldg(src + j);
+        if (q8 * 8 + j < bins) v[j] = __ldg(p + j);
     }
   }
   __align__(16) __nv_bfloat16 hi[8], lo[8];
@@ -382,28 +400,57 @@ __global__ void y_split_kernel(const float* __restrict__ y, __nv_bfloat16* __res
     hi[j] = __float2bfloat16_rn(v[j]);
     lo[j] = __float2bfloat16_rn(v[j] - __bfloat162float(hi[j]));
   }
-  const size_t plane = (size_t)tc::kChunks8 * rows_total * 8;
+  const size_t plane = (size_t)chunks8 * rows_total * 8;
   const size_t off = ((size_t)q8 * rows_total + d) * 8;
-  *reinterpret_cast<uint4*>(yhl + off) = *reinterpret_cast<const uint4*>(hi);
-  *reinterpret_cast<uint4*>(yhl + plane + off) = *reinterpret_cast<const uint4*>(lo);
+  *reinterpret_cast<uint4*>(dst + off) = *reinterpret_cast<const uint4*>(hi);
+  *reinterpret_cast<uint4*>(dst + plane + off) = *reinterpret_cast<const uint4*>(lo);
 }
 
 // ------------------------------------------------------------------------------------------------
 // The tensor-core kernel
 // ------------------------------------------------------------------------------------------------
 struct TcArgs {
-  const __nv_bfloat16* yhl;     // [2][40][rows_total][8]
+  const __nv_bfloat16* data;    // [2][chunks8][rows_total][8]
   const uint16_t* tiles;        // [n_tiles][8192 B]
-  const int* tile_seq;          // per step: tile id
-  const float* bias;            // [COUT]
-  int layer;                    // which constant-memory program (0 contour, 1 onset)
-  float* out;                   // [B][COUT][172][WOUT]  (planar, like the FP32 path)
+  float* out;                   // EPI 0: [B][172][WOUT][COUT] channels-last ; EPI 1/2: [B][taps][172][WOUT] planar
+  int layer;                    // which constant-memory program (0 contour, 1 onset, 2 note)
   int rows_total, n_mtiles, n_windows;
   int n_groups, n_split;        // an item covers groups [s*n_groups/n_split, (s+1)*n_groups/n_split)
-  int data_rows, row0;          // tile rows (128 + KH - 1); first data row of M-tile 0 (= 2 - PT)
+  int data_rows, row0;          // tile rows (128 + KH - 1); first data row of M-tile 0 (= lead - PT)
+  int chunks8, rows_per_window;
   int cout, flt, wout;
 };
 
+// Fused channel reduction of the epilogue for taps [T0, T0 + TN): for the 4 bins of the tile (one 32-column slab of 32
+// channels each) acc[fl][tp] = sum_c relu(v[c] + bias[c]) * w2[c][T0 + tp]; then TN float4 stores along frequency.
+// The taps are processed in chunks (TN <= 9) to bound the live accumulators; TMEM re-reads are cheap.
+template <int LAYER, int TAPS, int T0, int TN>
+__device__ __forceinline__ void reduce_store(uint32_t taddr, const float (&red)[32][TAPS], float* dst, size_t tap_pitch,
+                                             bool live) {
+  float acc[4][TN];
+#pragma unroll
+  for (int fl = 0; fl < 4; ++fl) {
+    uint32_t v[32];
+    tmem_ld32_nowait(taddr + fl * 32, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int tp = 0; tp < TN; ++tp) acc[fl][tp] = 0.f;
+#pragma unroll
+    for (int c = 0; c < 32; ++c) {
+      const float o = fmaxf(__uint_as_float(v[c]) + c_bias1[LAYER][c], 0.f);
+#pragma unroll
+      for (int tp = 0; tp < TN; ++tp) acc[fl][tp] = fmaf(o, red[c][T0 + tp], acc[fl][tp]);
+    }
+  }
+  if (live) {
+#pragma unroll
+    for (int tp = 0; tp < TN; ++tp)
+      *reinterpret_cast<float4*>(dst + (size_t)(T0 + tp) * tap_pitch) =
+          make_float4(acc[0][tp], acc[1][tp], acc[2][tp], acc[3][tp]);
+  }
+}
+
+template <int EPI>
 __global__ void __launch_bounds__(tc::kThreads, 1) conv_tc_kernel(const TcArgs a) {
   using namespace tc;
   extern __shared__ __align__(128) unsigned char smem[];
@@ -421,7 +468,7 @@ __global__ void __launch_bounds__(tc::kThreads, 1) conv_tc_kernel(const TcArgs a
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const uint32_t lbo = (uint32_t)a.data_rows * 16u;
-  const uint32_t plane_bytes = kChunks8 * lbo;
+  const uint32_t plane_bytes = (uint32_t)a.chunks8 * lbo;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) {
@@ -451,7 +498,7 @@ __global__ void __launch_bounds__(tc::kThreads, 1) conv_tc_kernel(const TcArgs a
     // ------------------------------ producer ------------------------------
     if (lane == 0) {
       uint32_t stage = 0, ph_w = 0, ph_d = 0;
-      const size_t plane_elems = (size_t)kChunks8 * a.rows_total * 8;
+      const size_t plane_elems = (size_t)a.chunks8 * a.rows_total * 8;
       for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
         const int mt = it / a.n_split, sp = it % a.n_split;
         const int g0 = sp * a.n_groups / a.n_split, g1 = (sp + 1) * a.n_groups / a.n_split;
@@ -459,8 +506,8 @@ __global__ void __launch_bounds__(tc::kThreads, 1) conv_tc_kernel(const TcArgs a
         mbar_expect_tx(data_full, 2 * plane_bytes);
         const size_t row = (size_t)mt * kMTile + a.row0;
         for (int p = 0; p < 2; ++p)
-          for (int c = 0; c < kChunks8; ++c)
-            bulk_g2s(s_data + p * plane_bytes + c * lbo, a.yhl + p * plane_elems + ((size_t)c * a.rows_total + row) * 8,
+          for (int c = 0; c < a.chunks8; ++c)
+            bulk_g2s(s_data + p * plane_bytes + c * lbo, a.data + p * plane_elems + ((size_t)c * a.rows_total + row) * 8,
                      lbo, data_full);
         ph_d ^= 1;
         const int s0 = c_group_step_off[a.layer][g0], s1 = c_group_step_off[a.layer][g1];
@@ -531,20 +578,14 @@ __global__ void __launch_bounds__(tc::kThreads, 1) conv_tc_kernel(const TcArgs a
     // ------------------------------ epilogue (warps 2..5) ------------------------------
     const int quad = warp & 3;  // TMEM lane quadrant this warp may access
     const int row = quad * 32 + lane;
-    float* s_bias = reinterpret_cast<float*>(tmem_slot + 2);  // 32 floats behind the barriers
-    if (warp == 2) s_bias[lane] = __ldg(a.bias + (lane % a.cout));
-    asm volatile("bar.sync 1, 128;" ::: "memory");
     uint32_t ph_t[2] = {0, 0};
     uint32_t gcount = 0;
-    const size_t chan_pitch = (size_t)kFrames * a.wout;  // planar output [B][COUT][172][WOUT]
-    const int cshift = (a.cout == 8) ? 0 : 1;           // column of (fl, co): COUT = 8 -> fl*8 + co ; 32 -> fl*32 + co
     for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
       const int mt = it / a.n_split, sp = it % a.n_split;
       const int g0 = sp * a.n_groups / a.n_split, g1 = (sp + 1) * a.n_groups / a.n_split;
       const int m = mt * kMTile + row;
-      const int b = m / kRowsPerWindow, t = m - b * kRowsPerWindow;
+      const int b = m / a.rows_per_window, t = m - b * a.rows_per_window;
       const bool live = (b < a.n_windows) && (t < kFrames);
-      float* orow = a.out + (size_t)b * a.cout * chan_pitch + (size_t)t * a.wout;
       for (int g = g0; g < g1; ++g) {
         const uint32_t buf = gcount & 1u;
         mbar_wait(tmem_full + buf, ph_t[buf]);
@@ -555,39 +596,39 @@ __global__ void __launch_bounds__(tc::kThreads, 1) conv_tc_kernel(const TcArgs a
           const int ft = c_group_ft[a.layer][2 * g + slot];
           if (ft < 0) continue;
           const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * 256u + (uint32_t)slot * 128u;
-          // one pass = 4 consecutive bins x 8 channels: 4 passes cover the 128 columns of the tile
+          if constexpr (EPI == 0) {
+            // contour: 16 bins x 8 channels, bias + ReLU, channels-last rows of 128 contiguous floats
+            const int n_valid = min(a.flt, a.wout - ft * a.flt) * a.cout;
+            float* dst = a.out + ((size_t)b * kFrames + t) * ((size_t)a.wout * a.cout) + (size_t)ft * 128;
 #pragma unroll 1
-          for (int pass = 0; pass < 4; ++pass) {
-            uint32_t v[32];  // v[fq * 8 + c] : bin quad index fq, channel c of the block
-            int f, co0;
-            if (cshift == 0) {  // COUT = 8: 32 consecutive columns are 4 bins x 8 channels
-              tmem_ld32_nowait(taddr + pass * 32, v);
-              f = ft * 16 + pass * 4;
-              co0 = 0;
-            } else {  // COUT = 32: the tile is 4 bins x 32 channels; take 8 channels of each bin
-              uint32_t(&v0)[8] = *reinterpret_cast<uint32_t(*)[8]>(&v[0]);
-              uint32_t(&v1)[8] = *reinterpret_cast<uint32_t(*)[8]>(&v[8]);
-              uint32_t(&v2)[8] = *reinterpret_cast<uint32_t(*)[8]>(&v[16]);
-              uint32_t(&v3)[8] = *reinterpret_cast<uint32_t(*)[8]>(&v[24]);
-              tmem_ld8_nowait(taddr + 0 * 32 + pass * 8, v0);
-              tmem_ld8_nowait(taddr + 1 * 32 + pass * 8, v1);
-              tmem_ld8_nowait(taddr + 2 * 32 + pass * 8, v2);
-              tmem_ld8_nowait(taddr + 3 * 32 + pass * 8, v3);
-              f = ft * 4;
-              co0 = pass * 8;
-            }
-            tmem_ld_wait();
-            if (live && f < a.wout) {
+            for (int c4 = 0; c4 < 4; ++c4) {
+              uint32_t v[32];
+              tmem_ld32_nowait(taddr + c4 * 32, v);
+              tmem_ld_wait();
+              if (live) {
 #pragma unroll
-              for (int c = 0; c < 8; ++c) {
-                const float bv = s_bias[(co0 + c) & 31];
-                float4 o;
-                o.x = fmaxf(__uint_as_float(v[0 * 8 + c]) + bv, 0.f);
-                o.y = fmaxf(__uint_as_float(v[1 * 8 + c]) + bv, 0.f);
-                o.z = fmaxf(__uint_as_float(v[2 * 8 + c]) + bv, 0.f);
-                o.w = fmaxf(__uint_as_float(v[3 * 8 + c]) + bv, 0.f);
-                *reinterpret_cast<float4*>(orow + (size_t)(co0 + c) * chan_pitch + f) = o;
+                for (int i = 0; i < 8; ++i) {
+                  float4 o;
+                  o.x = fmaxf(__uint_as_float(v[4 * i + 0]) + c_bias1[0][(4 * i + 0) & 7], 0.f);
+                  o.y = fmaxf(__uint_as_float(v[4 * i + 1]) + c_bias1[0][(4 * i + 1) & 7], 0.f);
+                  o.z = fmaxf(__uint_as_float(v[4 * i + 2]) + c_bias1[0][(4 * i + 2) & 7], 0.f);
+                  o.w = fmaxf(__uint_as_float(v[4 * i + 3]) + c_bias1[0][(4 * i + 3) & 7], 0.f);
+                  if (c4 * 32 + 4 * i < n_valid) reinterpret_cast<float4*>(dst + c4 * 32)[i] = o;
+                }
               }
+            }
+          } else {
+            // onset / note: the tile is 4 bins x 32 channels; reduce the channels against the next conv's weights
+            constexpr int TAPS = (EPI == 1) ? 9 : 21;
+            const size_t tap_pitch = (size_t)kFrames * a.wout;
+            float* dst = a.out + (size_t)b * TAPS * tap_pitch + (size_t)t * a.wout + ft * 4;
+            if constexpr (EPI == 1) {
+              reduce_store<1, 9, 0, 5>(taddr, c_red_onset, dst, tap_pitch, live);
+              reduce_store<1, 9, 5, 4>(taddr, c_red_onset, dst, tap_pitch, live);
+            } else {
+              reduce_store<2, 21, 0, 7>(taddr, c_red_note, dst, tap_pitch, live);
+              reduce_store<2, 21, 7, 7>(taddr, c_red_note, dst, tap_pitch, live);
+              reduce_store<2, 21, 14, 7>(taddr, c_red_note, dst, tap_pitch, live);
             }
           }
         }
@@ -607,34 +648,35 @@ __global__ void __launch_bounds__(tc::kThreads, 1) conv_tc_kernel(const TcArgs a
 }
 
 // ------------------------------------------------------------------------------------------------
-int tc_rows_total(int n_windows) {
-  const int rows = n_windows * tc::kRowsPerWindow;
+int tc_rows_total(int n_windows, int rows_per_window) {
+  const int rows = n_windows * rows_per_window;
   const int n_mtiles = (rows + tc::kMTile - 1) / tc::kMTile;
-  return n_mtiles * tc::kMTile + 4;
+  return n_mtiles * tc::kMTile + 8;
 }
 
 void tc_setup() {
-  cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes);
+  cudaFuncSetAttribute(conv_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes);
+  cudaFuncSetAttribute(conv_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes);
+  cudaFuncSetAttribute(conv_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes);
 }
 
-void launch_y_split(const float* y, __nv_bfloat16* yhl, int n_windows, cudaStream_t st) {
-  const int rows_total = tc_rows_total(n_windows);
-  const long long cells = (long long)rows_total * tc::kChunks8;
-  y_split_kernel<<<(unsigned)((cells + 255) / 256), 256, 0, st>>>(y, yhl, n_windows, rows_total);
+void launch_split(const float* src, __nv_bfloat16* dst, const TcConvSpec& sp, int n_windows, cudaStream_t st) {
+  const int rows_total = tc_rows_total(n_windows, sp.rows_per_window);
+  const long long cells = (long long)rows_total * sp.chunks8;
+  split_kernel<<<(unsigned)((cells + 255) / 256), 256, 0, st>>>(src, sp.data_bins, dst, n_windows, rows_total, sp.chunks8,
+                                                               sp.rows_per_window, sp.lead_rows);
 }
 
-void launch_conv_tc(const __nv_bfloat16* yhl, const TcConvDev& dev, const float* bias, float* out_nhwc, int n_windows,
-                    int n_sms, cudaStream_t st) {
+void launch_conv_tc(const __nv_bfloat16* data, const TcConvDev& dev, float* out, int n_windows, int n_sms,
+                    cudaStream_t st) {
   const TcConvSpec& sp = dev.spec;
   TcArgs a;
-  a.yhl = yhl;
+  a.data = data;
   a.tiles = dev.tiles;
-  a.tile_seq = dev.tile_seq;
-  a.bias = bias;
+  a.out = out;
   a.layer = dev.layer;
-  a.out = out_nhwc;
-  a.rows_total = tc_rows_total(n_windows);
-  a.n_mtiles = (a.rows_total - 4) / tc::kMTile;
+  a.rows_total = tc_rows_total(n_windows, sp.rows_per_window);
+  a.n_mtiles = (a.rows_total - 8) / tc::kMTile;
   a.n_windows = n_windows;
   a.n_groups = dev.n_groups;
   // few M-tiles (small batches): split the frequency groups of an M-tile over several CTAs
@@ -643,13 +685,20 @@ void launch_conv_tc(const __nv_bfloat16* yhl, const TcConvDev& dev, const float*
   if (split > dev.n_groups) split = dev.n_groups;
   a.n_split = split;
   a.data_rows = tc::kMTile + sp.KH - 1;
-  a.row0 = tc::kLeadRows - sp.PT;
+  a.row0 = sp.lead_rows - sp.PT;
+  a.chunks8 = sp.chunks8;
+  a.rows_per_window = sp.rows_per_window;
   a.cout = sp.COUT;
   a.flt = sp.FLT;
   a.wout = sp.WOUT;
   const int n_items = a.n_mtiles * a.n_split;
   const int grid = n_items < n_sms ? n_items : n_sms;
-  conv_tc_kernel<<<grid, tc::kThreads, tc::kSmemBytes, st>>>(a);
+  if (sp.epi == 0)
+    conv_tc_kernel<0><<<grid, tc::kThreads, tc::kSmemBytes, st>>>(a);
+  else if (sp.epi == 1)
+    conv_tc_kernel<1><<<grid, tc::kThreads, tc::kSmemBytes, st>>>(a);
+  else
+    conv_tc_kernel<2><<<grid, tc::kThreads, tc::kSmemBytes, st>>>(a);
 }
 
 }  // namespace bp

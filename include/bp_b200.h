@@ -150,7 +150,8 @@ int bp_transcribe_device(bp_model_t* m, const float* d_audio, const int64_t* h_s
 /* ---- introspection used by tests / profiling ----------------------------------------------------
  * Copies an internal activation of the most recent bp_forward_* call for window 0..n-1 to host.
  * which: 0 = CQT log-magnitude after normalisation+BN (n,172,309); 1 = contour conv1 output
- * (n,8,172,264); 2 = note conv1 output (n,32,172,88); 3 = onset conv1 output (n,32,172,88).
+ * (n,8,172,264); 2 = note conv1 output (n,32,172,88); 3 = onset conv1 output (n,32,172,88) — 2 and 3 exist only on
+ * the FP32 path (bp_model_set_path(m, 0)): the tensor-core path reduces them in the epilogue and never stores them.
  * Only valid when the batch fitted in one internal chunk (n <= bp_model_chunk_windows). */
 int bp_debug_activation(bp_model_t* m, int which, float* h_out, int64_t n_windows);
 int64_t bp_model_chunk_windows(const bp_model_t* m);
@@ -159,8 +160,8 @@ int64_t bp_model_chunk_windows(const bp_model_t* m);
 int bp_model_set_path(bp_model_t* m, int path);
 
 /* Host-only (no GPU needed): builds the tensor-core plan (split-bf16 Toeplitz weight tiles and the per-group MMA
- * programs, csrc/tc_conv.cu) of the contour conv (which = 0, w = [8][8][3][39]) or the onset conv (which = 1,
- * w = [32][8][5][5]) so that tests can emulate the program on the CPU.  sizes[4] = {n_tiles, n_steps, n_uses,
+ * programs, csrc/tc_conv.cu) of the contour conv (which = 0, w = [8][8][3][39]), the onset conv (which = 1,
+ * w = [32][8][5][5]) or the note conv (which = 2, w = [32][1][7][7]) so that tests can emulate the program on the CPU.  sizes[4] = {n_tiles, n_steps, n_uses,
  * n_groups}; pass NULL arrays to query sizes first.  tiles: n_tiles x 4096 bf16 ([plane hi/lo][k-chunk 2][n 128][8]);
  * slot_words: [2][n_steps]; group_step_off has n_groups + 1 entries, group_ft n_groups x 2. */
 int bp_debug_tc_plan(int which, const float* w, int32_t* sizes, uint16_t* tiles, int32_t* tile_seq, uint32_t* slot_words,

@@ -42,12 +42,23 @@ def test_forward_vs_oracle_including_activations(model, weights_np):
     from oracle import model_ref
 
     x = _edge_windows()
-    got = model.predict(x[:, :, None])
     ref = model_ref.forward(x, weights_np, return_intermediates=True)
     lib = _lib.load()
     n = x.shape[0]
-    for which, key, shape, tol in ((0, "_y", (n, 172, 309), 2e-4), (1, "_c1", (n, 8, 172, 264), 5e-4),
-                                   (2, "_n1", (n, 32, 172, 88), 5e-4), (3, "_o1", (n, 32, 172, 88), 5e-4)):
+    model.set_path(0)  # the FP32 path materialises every activation; the tensor-core path fuses the 32-channel ones away
+    try:
+        fp32 = model.predict(x[:, :, None])
+        for which, key, shape, tol in ((2, "_n1", (n, 32, 172, 88), 5e-4), (3, "_o1", (n, 32, 172, 88), 5e-4)):
+            buf = np.empty(shape, np.float32)
+            lib.bp_debug_activation(model.handle, which, buf.ctypes.data, n)
+            err = np.abs(buf - ref[key]).max()
+            assert err < tol, f"FP32 path activation {key}: max-abs {err:.3e}"
+        for k in ("note", "onset", "contour"):
+            assert np.abs(fp32[k] - ref[k]).max() < POST_TOL, f"FP32 path {k}"
+    finally:
+        model.set_path(1)
+    got = model.predict(x[:, :, None])
+    for which, key, shape, tol in ((0, "_y", (n, 172, 309), 2e-4), (1, "_c1", (n, 8, 172, 264), 5e-4)):
         buf = np.empty(shape, np.float32)
         lib.bp_debug_activation(model.handle, which, buf.ctypes.data, n)
         err = np.abs(buf - ref[key]).max()

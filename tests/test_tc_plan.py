@@ -12,6 +12,7 @@ from oracle import model_ref
 SPECS = {  # which: (weights key, KH, KW, SF, PT, PL, COUT, FLT, WOUT)
     0: ("contour1_w", 3, 39, 1, 1, 19, 8, 16, 264),
     1: ("onset1_w", 5, 5, 3, 2, 1, 32, 4, 88),
+    2: ("note1_w", 7, 7, 3, 3, 2, 32, 4, 88),  # single input channel: the contour posteriorgram (264 bins)
 }
 
 
@@ -37,7 +38,7 @@ def _plan(which, w):
     return tiles, tile_seq, slot_words, gso, gft, n_uses
 
 
-@pytest.mark.parametrize("which", [0, 1])
+@pytest.mark.parametrize("which", [0, 1, 2])
 def test_tc_program_reproduces_convolution(weights_np, which):
     key, KH, KW, SF, PT, PL, COUT, FLT, WOUT = SPECS[which]
     w = weights_np[key]
@@ -48,10 +49,11 @@ def test_tc_program_reproduces_convolution(weights_np, which):
     t_full = (tf[:, 0] + tf[:, 1]).transpose(0, 1, 3, 2).reshape(len(tiles), 16, 128)  # [tile][k][n]
     rng = np.random.default_rng(which)
     n_t = 40
-    y = rng.standard_normal((n_t, 309))
+    bins = 309 if which < 2 else 264
+    y = rng.standard_normal((n_t, bins))
     # the kernel's tile row (i + dt) holds input frame i + dt - PT
     ypad = np.zeros((n_t + KH - 1, 320))
-    ypad[PT : PT + n_t, :309] = y
+    ypad[PT : PT + n_t, :bins] = y
     n_ft = (WOUT + FLT - 1) // FLT
     out = np.zeros((n_t, n_ft * 128))
     lbo16 = 128 + KH - 1  # the program is built for 128-row M-tiles
@@ -82,7 +84,7 @@ def test_tc_program_reproduces_convolution(weights_np, which):
                 seen_ft.add(int(gft[g, slot]))
     assert seen_ft == set(range(n_ft)) and used == n_uses
     got = out.reshape(n_t, n_ft * FLT, COUT)[:, :WOUT]  # n = fl * COUT + co
-    h = model_ref.harmonic_stack(torch.from_numpy(y)[None])  # (1,8,T,264)
+    h = model_ref.harmonic_stack(torch.from_numpy(y)[None]) if which < 2 else torch.from_numpy(y)[None, None]
     ref = F.conv2d(F.pad(h, (PL, PL, PT, PT)), torch.from_numpy(w.astype(np.float64)), stride=(1, SF))[0].numpy()
     assert ref.shape == (COUT, n_t, WOUT)
     err = np.abs(got - ref.transpose(1, 2, 0)).max()
@@ -90,7 +92,7 @@ def test_tc_program_reproduces_convolution(weights_np, which):
 
 
 def test_tc_program_statistics(weights_np):
-    for which in (0, 1):
+    for which in (0, 1, 2):
         key = SPECS[which][0]
         tiles, tile_seq, slot_words, gso, gft, n_uses = _plan(which, weights_np[key])
         assert (tile_seq >= 0).all() and (tile_seq < len(tiles)).all()
