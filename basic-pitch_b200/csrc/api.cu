@@ -281,10 +281,11 @@ int ensure_forward_ws(bp_model* m, int nb) {
   CK(m->n1.reserve((size_t)nb * 32 * kFrames * kPitches));
   CK(m->o1.reserve((size_t)nb * 32 * kFrames * kPitches));
   CK(m->minmax.reserve((size_t)nb * 2));
-  CK(m->yhl.reserve((size_t)2 * 40 * 8 * tc_rows_total(nb, tc_contour_spec().rows_per_window)));
+  // split layouts use the row stride of a full chunk whatever the batch size (see launch_conv_tc)
+  CK(m->yhl.reserve((size_t)2 * 40 * 8 * tc_rows_total(m->chunk, tc_contour_spec().rows_per_window)));
   {
     const TcConvSpec ns = tc_note_spec();
-    const size_t need = (size_t)2 * ns.chunks8 * 8 * tc_rows_total(nb, ns.rows_per_window);
+    const size_t need = (size_t)2 * ns.chunks8 * 8 * tc_rows_total(m->chunk, ns.rows_per_window);
     const __nv_bfloat16* before = m->chl.p;
     CK(m->chl.reserve(need));
     if (m->chl.p != before || m->chl_zeroed < m->chl.cap) {  // separator rows / pad bins are never written: zero once
@@ -332,22 +333,23 @@ int forward_chunk(bp_model* m, const float* audio, const WinDesc* desc, int nb, 
   }
   if (m->path == 1) {
     const TcConvSpec cs = tc_contour_spec(), ns = tc_note_spec();
-    launch_split(m->y.p, m->yhl.p, cs, nb, st);
+    const int ystride = tc_rows_total(m->chunk, cs.rows_per_window), cstride = tc_rows_total(m->chunk, ns.rows_per_window);
+    launch_split(m->y.p, m->yhl.p, cs, nb, ystride, st);
     {
       ProfScope ps(m, 0, st);
-      launch_conv_tc(m->yhl.p, m->tc_contour.dev, m->c1.p, nb, m->n_sms, st);
+      launch_conv_tc(m->yhl.p, m->tc_contour.dev, m->c1.p, nb, ystride, m->n_sms, st);
     }
     {
       ProfScope ps(m, 4, st);
-      launch_contour2_tc(m->c1.p, m->cw, contour, m->chl.p, tc_rows_total(nb, ns.rows_per_window), nb, st);
+      launch_contour2_tc(m->c1.p, m->cw, contour, m->chl.p, cstride, nb, st);
     }
     {
       ProfScope ps(m, 1, st);
-      launch_conv_tc(m->yhl.p, m->tc_onset.dev, m->o1.p, nb, m->n_sms, st);  // -> 9 tap planes
+      launch_conv_tc(m->yhl.p, m->tc_onset.dev, m->o1.p, nb, ystride, m->n_sms, st);  // -> 9 tap planes
     }
     {
       ProfScope ps(m, 4, st);
-      launch_conv_tc(m->chl.p, m->tc_note.dev, m->n1.p, nb, m->n_sms, st);  // -> 21 tap planes
+      launch_conv_tc(m->chl.p, m->tc_note.dev, m->n1.p, nb, cstride, m->n_sms, st);  // -> 21 tap planes
       launch_note_tapsum(m->n1.p, m->cw, note, nb, st);
       launch_onset_tapsum(m->o1.p, note, m->cw, onset, nb, st);
     }

@@ -36,8 +36,9 @@
 //               a single issuing warp at this MMA size): program words from constant memory, descriptors are
 //               base + precomputed offset, 3 x tcgen05.mma per step by one elected lane, tcgen05.commit frees the
 //               weight stage / publishes the accumulators
-//   warps 2-5   epilogue: tcgen05.ld the accumulator columns, + bias, ReLU, then either a channels-last store
-//               (contour) or the fused 32 -> taps reduction with planar float4 stores (onset, note)
+//   warps 2-5, 7-10  epilogue, one warpgroup-like set of 4 warps (= the 4 TMEM lane quadrants) per accumulator slot:
+//               tcgen05.ld the accumulator columns, + bias, ReLU, then either a channels-last store (contour) or
+//               the fused 32 -> taps reduction with planar float4 stores (onset, note)
 #include <cuda_bf16.h>
 
 #include <vector>
@@ -53,7 +54,7 @@ constexpr int kTileBytes = 8192;                                 // weight tile:
 constexpr int kStages = 6;
 constexpr int kMaxSteps = 1024;                                  // program steps per layer (constant memory)
 constexpr int kMaxGroups = 15;
-constexpr int kThreads = 224;
+constexpr int kThreads = 352;  // 11 warps: producer, 2 MMA issuers, 2 x 4 epilogue warps
 constexpr int kSmemBytes = kMaxDataBytes + kStages * kTileBytes + 512;
 // step word of a slot: [0,14) A start-address offset >> 4, [15] first MMA into that accumulator; kNoUse = the
 // slot's frequency tile does not use this step's weight tile
@@ -375,12 +376,12 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // Used for y (309 bins -> 40 chunks) and for the contour posteriorgram (264 bins -> 34 chunks).
 // ------------------------------------------------------------------------------------------------
 __global__ void split_kernel(const float* __restrict__ src, int bins, __nv_bfloat16* __restrict__ dst, int n_windows,
-                             int rows_total, int chunks8, int rows_per_window, int lead) {
+                             int rows_used, int rows_total /* stride */, int chunks8, int rows_per_window, int lead) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // one (row, q8) per thread
-  const long long total = (long long)rows_total * chunks8;
+  const long long total = (long long)rows_used * chunks8;
   if (idx >= total) return;
-  const int d = (int)(idx % rows_total);  // rows fastest: 16-byte stores of a warp are contiguous
-  const int q8 = (int)(idx / rows_total);
+  const int d = (int)(idx % rows_used);  // rows fastest: 16-byte stores of a warp are contiguous
+  const int q8 = (int)(idx / rows_used);
   float v[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) v[j] = 0.f;
@@ -479,7 +480,7 @@ __global__ void __launch_bounds__(tc::kThreads, 1) conv_tc_kernel(const TcArgs a
     mbar_init(data_empty, 2);
     for (int i = 0; i < 2; ++i) {
       mbar_init(tmem_full + i, 2);
-      mbar_init(tmem_empty + i, 4);
+      mbar_init(tmem_empty + i, 8);  // one arrival per epilogue warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -575,8 +576,9 @@ __global__ void __launch_bounds__(tc::kThreads, 1) conv_tc_kernel(const TcArgs a
       umma_commit_pred(data_empty, leader);  // the data tile may be overwritten
     }
   } else {
-    // ------------------------------ epilogue (warps 2..5) ------------------------------
+    // ------------------------------ epilogue (warps 2..5 -> slot 0, warps 7..10 -> slot 1) ------------------------------
     const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    const int slot = (warp >= 7) ? 1 : 0;
     const int row = quad * 32 + lane;
     uint32_t ph_t[2] = {0, 0};
     uint32_t gcount = 0;
@@ -591,10 +593,8 @@ __global__ void __launch_bounds__(tc::kThreads, 1) conv_tc_kernel(const TcArgs a
         mbar_wait(tmem_full + buf, ph_t[buf]);
         ph_t[buf] ^= 1;
         tc_fence_after();
-#pragma unroll 1
-        for (int slot = 0; slot < 2; ++slot) {
-          const int ft = c_group_ft[a.layer][2 * g + slot];
-          if (ft < 0) continue;
+        const int ft = c_group_ft[a.layer][2 * g + slot];
+        if (ft >= 0) {
           const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * 256u + (uint32_t)slot * 128u;
           if constexpr (EPI == 0) {
             // contour: 16 bins x 8 channels, bias + ReLU, channels-last rows of 128 contiguous floats
@@ -626,9 +626,11 @@ __global__ void __launch_bounds__(tc::kThreads, 1) conv_tc_kernel(const TcArgs a
               reduce_store<1, 9, 0, 5>(taddr, c_red_onset, dst, tap_pitch, live);
               reduce_store<1, 9, 5, 4>(taddr, c_red_onset, dst, tap_pitch, live);
             } else {
-              reduce_store<2, 21, 0, 7>(taddr, c_red_note, dst, tap_pitch, live);
-              reduce_store<2, 21, 7, 7>(taddr, c_red_note, dst, tap_pitch, live);
-              reduce_store<2, 21, 14, 7>(taddr, c_red_note, dst, tap_pitch, live);
+              reduce_store<2, 21, 0, 4>(taddr, c_red_note, dst, tap_pitch, live);
+              reduce_store<2, 21, 4, 4>(taddr, c_red_note, dst, tap_pitch, live);
+              reduce_store<2, 21, 8, 4>(taddr, c_red_note, dst, tap_pitch, live);
+              reduce_store<2, 21, 12, 4>(taddr, c_red_note, dst, tap_pitch, live);
+              reduce_store<2, 21, 16, 5>(taddr, c_red_note, dst, tap_pitch, live);
             }
           }
         }
@@ -660,23 +662,24 @@ void tc_setup() {
   cudaFuncSetAttribute(conv_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes);
 }
 
-void launch_split(const float* src, __nv_bfloat16* dst, const TcConvSpec& sp, int n_windows, cudaStream_t st) {
-  const int rows_total = tc_rows_total(n_windows, sp.rows_per_window);
-  const long long cells = (long long)rows_total * sp.chunks8;
-  split_kernel<<<(unsigned)((cells + 255) / 256), 256, 0, st>>>(src, sp.data_bins, dst, n_windows, rows_total, sp.chunks8,
-                                                               sp.rows_per_window, sp.lead_rows);
+void launch_split(const float* src, __nv_bfloat16* dst, const TcConvSpec& sp, int n_windows, int rows_stride,
+                  cudaStream_t st) {
+  const int rows_used = tc_rows_total(n_windows, sp.rows_per_window);  // <= rows_stride
+  const long long cells = (long long)rows_used * sp.chunks8;
+  split_kernel<<<(unsigned)((cells + 255) / 256), 256, 0, st>>>(src, sp.data_bins, dst, n_windows, rows_used, rows_stride,
+                                                               sp.chunks8, sp.rows_per_window, sp.lead_rows);
 }
 
-void launch_conv_tc(const __nv_bfloat16* data, const TcConvDev& dev, float* out, int n_windows, int n_sms,
-                    cudaStream_t st) {
+void launch_conv_tc(const __nv_bfloat16* data, const TcConvDev& dev, float* out, int n_windows, int rows_stride,
+                    int n_sms, cudaStream_t st) {
   const TcConvSpec& sp = dev.spec;
   TcArgs a;
   a.data = data;
   a.tiles = dev.tiles;
   a.out = out;
   a.layer = dev.layer;
-  a.rows_total = tc_rows_total(n_windows, sp.rows_per_window);
-  a.n_mtiles = (a.rows_total - 8) / tc::kMTile;
+  a.rows_total = rows_stride;  // row stride of the split layout (fixed per model, independent of the batch)
+  a.n_mtiles = (tc_rows_total(n_windows, sp.rows_per_window) - 8) / tc::kMTile;
   a.n_windows = n_windows;
   a.n_groups = dev.n_groups;
   // few M-tiles (small batches): split the frequency groups of an M-tile over several CTAs
