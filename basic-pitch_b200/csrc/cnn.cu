@@ -311,31 +311,48 @@ __global__ void __launch_bounds__(Cfg::THREADS) conv1_kernel(In in, const float*
 
 // ------------------------------------------------------------------------------------------------
 // Second convs of the note / onset branches after the tensor-core epilogue has reduced the 32 channels:
-//   out[t][f] = sigmoid(bias + sum_{dt,df} P[dt*KW+df][t+dt-PT][f+df-PL] (+ sum x[t+dt-PT][f+df-PL] * wx[dt*KW+df]))
+//   out[t][f] = sigmoid(bias + sum_{dt,df} P[dt*KW+df][f+df-PL][t+dt-PT] (+ sum x[t+dt-PT][f+df-PL] * wx[dt*KW+df]))
+// P is time-fastest ([B][taps][88][172]); a CTA computes a 32 (t) x 32 (f) tile with t on the lanes (coalesced reads)
+// and transposes through shared memory for the frequency-fastest output.
 // ------------------------------------------------------------------------------------------------
 template <int KH, int KW, int PT, int PL, bool EXTRA>
-__global__ void tap_sum_kernel(const float* __restrict__ P /* [B][KH*KW][172][88] */, const float* __restrict__ x,
-                               const float* __restrict__ wx, const float* __restrict__ bias, float* __restrict__ out,
-                               int n_windows) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  const int b = blockIdx.y;
-  if (idx >= kFrames * kPitches) return;
-  const int t = idx / kPitches, f = idx - t * kPitches;
-  float acc = __ldg(bias);
-  const float* Pb = P + (size_t)b * KH * KW * kFrames * kPitches;
+__global__ void __launch_bounds__(256) tap_sum_kernel(const float* __restrict__ P, const float* __restrict__ x,
+                                                      const float* __restrict__ wx, const float* __restrict__ bias,
+                                                      float* __restrict__ out) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const int t0 = blockIdx.x * 32, f0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 8 warps
+  const float* Pb = P + (size_t)b * KH * KW * kPitches * kFrames;
+  const float bv = __ldg(bias);
 #pragma unroll
-  for (int dt = 0; dt < KH; ++dt) {
-    const int tt = t + dt - PT;
-    if ((unsigned)tt >= (unsigned)kFrames) continue;
+  for (int i = 0; i < 4; ++i) {
+    const int fl = ty + 8 * i;
+    const int f = f0 + fl, t = t0 + tx;
+    float acc = bv;
+    if (f < kPitches && t < kFrames) {
 #pragma unroll
-    for (int df = 0; df < KW; ++df) {
-      const int ff = f + df - PL;
-      if ((unsigned)ff >= (unsigned)kPitches) continue;
-      acc += __ldg(Pb + ((size_t)(dt * KW + df) * kFrames + tt) * kPitches + ff);
-      if (EXTRA) acc = fmaf(__ldg(x + ((size_t)b * kFrames + tt) * kPitches + ff), __ldg(wx + dt * KW + df), acc);
+      for (int dt = 0; dt < KH; ++dt) {
+        const int tt = t + dt - PT;
+        if ((unsigned)tt >= (unsigned)kFrames) continue;
+#pragma unroll
+        for (int df = 0; df < KW; ++df) {
+          const int ff = f + df - PL;
+          if ((unsigned)ff >= (unsigned)kPitches) continue;
+          acc += __ldg(Pb + ((size_t)(dt * KW + df) * kPitches + ff) * kFrames + tt);
+          if (EXTRA) acc = fmaf(__ldg(x + ((size_t)b * kFrames + tt) * kPitches + ff), __ldg(wx + dt * KW + df), acc);
+        }
+      }
     }
+    tile[fl][tx] = 1.f / (1.f + expf(-acc));
   }
-  out[((size_t)b * kFrames + t) * kPitches + f] = 1.f / (1.f + expf(-acc));
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int tl = ty + 8 * i;
+    const int t = t0 + tl, f = f0 + tx;
+    if (t < kFrames && f < kPitches) out[((size_t)b * kFrames + t) * kPitches + f] = tile[tx][tl];
+  }
 }
 
 //                           CIN CIC KH KW PT PL WOUT TR
@@ -394,13 +411,13 @@ void launch_contour2_tc(const float* c1, const CnnWeights& w, float* contour, __
                         SplitOut{chl, rows_total, sp.chunks8, sp.rows_per_window, sp.lead_rows});
 }
 void launch_note_tapsum(const float* p21, const CnnWeights& w, float* note, int n, cudaStream_t st) {
-  tap_sum_kernel<7, 3, 3, 1, false><<<dim3((kFrames * kPitches + 255) / 256, n), 256, 0, st>>>(p21, nullptr, nullptr,
-                                                                                               w.note2_b, note, n);
+  tap_sum_kernel<7, 3, 3, 1, false><<<dim3((kFrames + 31) / 32, (kPitches + 31) / 32, n), 256, 0, st>>>(
+      p21, nullptr, nullptr, w.note2_b, note);
 }
 void launch_onset_tapsum(const float* p9, const float* note, const CnnWeights& w, float* onset, int n, cudaStream_t st) {
   // channel 0 of the onset conv2 weights multiplies the note posteriorgram (models.py:305: concat[note, onset1])
-  tap_sum_kernel<3, 3, 1, 1, true><<<dim3((kFrames * kPitches + 255) / 256, n), 256, 0, st>>>(p9, note, w.onset2_wT,
-                                                                                              w.onset2_b, onset, n);
+  tap_sum_kernel<3, 3, 1, 1, true><<<dim3((kFrames + 31) / 32, (kPitches + 31) / 32, n), 256, 0, st>>>(
+      p9, note, w.onset2_wT, w.onset2_b, onset);
 }
 void launch_note1(const float* contour, const CnnWeights& w, float* n1, int n, cudaStream_t st) {
   launch<Note1Cfg>(PlanarIn<1, 264>{contour}, w.note1_wT, w.note1_b, n1, n, st);

@@ -413,7 +413,7 @@ __global__ void split_kernel(const float* __restrict__ src, int bins, __nv_bfloa
 struct TcArgs {
   const __nv_bfloat16* data;    // [2][chunks8][rows_total][8]
   const uint16_t* tiles;        // [n_tiles][8192 B]
-  float* out;                   // EPI 0: [B][172][WOUT][COUT] channels-last ; EPI 1/2: [B][taps][172][WOUT] planar
+  float* out;                   // EPI 0: [B][172][WOUT][COUT] channels-last ; EPI 1/2: [B][taps][WOUT][172] time-fastest
   int layer;                    // which constant-memory program (0 contour, 1 onset, 2 note)
   int rows_total, n_mtiles, n_windows;
   int n_groups, n_split;        // an item covers groups [s*n_groups/n_split, (s+1)*n_groups/n_split)
@@ -422,32 +422,33 @@ struct TcArgs {
   int cout, flt, wout;
 };
 
-// Fused channel reduction of the epilogue for taps [T0, T0 + TN): for the 4 bins of the tile (one 32-column slab of 32
-// channels each) acc[fl][tp] = sum_c relu(v[c] + bias[c]) * w2[c][T0 + tp]; then TN float4 stores along frequency.
-// The taps are processed in chunks (TN <= 9) to bound the live accumulators; TMEM re-reads are cheap.
+// Fused channel reduction of the epilogue: for each of the 4 bins of the tile (one 32-column slab = 32 channels)
+//   P[tap][f][t] = sum_c relu(v[c] + bias[c]) * w2[c][tap]
+// The output is time-fastest ([B][taps][WOUT][172]): the 32 lanes of a warp hold 32 consecutive frames, so every store
+// instruction writes one contiguous 128-byte run.  Weights and bias are constant-bank immediates of the FMAs.
+// Taps [T0, T0+TN) are handled per call: with few taps the compiler keeps the whole weight block in registers across
+// the bin loop, so small layers are split in two calls to stay inside the register budget (TMEM re-reads are cheap).
 template <int LAYER, int TAPS, int T0, int TN>
-__device__ __forceinline__ void reduce_store(uint32_t taddr, const float (&red)[32][TAPS], float* dst, size_t tap_pitch,
+__device__ __forceinline__ void reduce_store(uint32_t taddr, const float (&red)[32][TAPS], float* dst /* (b, tap 0, f0, t) */,
                                              bool live) {
-  float acc[4][TN];
-#pragma unroll
+#pragma unroll 1
   for (int fl = 0; fl < 4; ++fl) {
     uint32_t v[32];
     tmem_ld32_nowait(taddr + fl * 32, v);
     tmem_ld_wait();
+    float acc[TN];
 #pragma unroll
-    for (int tp = 0; tp < TN; ++tp) acc[fl][tp] = 0.f;
+    for (int tp = 0; tp < TN; ++tp) acc[tp] = 0.f;
 #pragma unroll
     for (int c = 0; c < 32; ++c) {
       const float o = fmaxf(__uint_as_float(v[c]) + c_bias1[LAYER][c], 0.f);
 #pragma unroll
-      for (int tp = 0; tp < TN; ++tp) acc[fl][tp] = fmaf(o, red[c][T0 + tp], acc[fl][tp]);
+      for (int tp = 0; tp < TN; ++tp) acc[tp] = fmaf(o, red[c][T0 + tp], acc[tp]);
     }
-  }
-  if (live) {
+    if (live) {
 #pragma unroll
-    for (int tp = 0; tp < TN; ++tp)
-      *reinterpret_cast<float4*>(dst + (size_t)(T0 + tp) * tap_pitch) =
-          make_float4(acc[0][tp], acc[1][tp], acc[2][tp], acc[3][tp]);
+      for (int tp = 0; tp < TN; ++tp) dst[((size_t)(T0 + tp) * kPitches + fl) * kFrames] = acc[tp];
+    }
   }
 }
 
@@ -620,17 +621,12 @@ __global__ void __launch_bounds__(tc::kThreads, 1) conv_tc_kernel(const TcArgs a
           } else {
             // onset / note: the tile is 4 bins x 32 channels; reduce the channels against the next conv's weights
             constexpr int TAPS = (EPI == 1) ? 9 : 21;
-            const size_t tap_pitch = (size_t)kFrames * a.wout;
-            float* dst = a.out + (size_t)b * TAPS * tap_pitch + (size_t)t * a.wout + ft * 4;
+            float* dst = a.out + ((size_t)b * TAPS * kPitches + (size_t)ft * 4) * kFrames + t;
             if constexpr (EPI == 1) {
-              reduce_store<1, 9, 0, 5>(taddr, c_red_onset, dst, tap_pitch, live);
-              reduce_store<1, 9, 5, 4>(taddr, c_red_onset, dst, tap_pitch, live);
+              reduce_store<1, 9, 0, 4>(taddr, c_red_onset, dst, live);
+              reduce_store<1, 9, 4, 5>(taddr, c_red_onset, dst, live);
             } else {
-              reduce_store<2, 21, 0, 4>(taddr, c_red_note, dst, tap_pitch, live);
-              reduce_store<2, 21, 4, 4>(taddr, c_red_note, dst, tap_pitch, live);
-              reduce_store<2, 21, 8, 4>(taddr, c_red_note, dst, tap_pitch, live);
-              reduce_store<2, 21, 12, 4>(taddr, c_red_note, dst, tap_pitch, live);
-              reduce_store<2, 21, 16, 5>(taddr, c_red_note, dst, tap_pitch, live);
+              reduce_store<2, 21, 0, 21>(taddr, c_red_note, dst, live);
             }
           }
         }
