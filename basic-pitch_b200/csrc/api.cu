@@ -132,6 +132,8 @@ __global__ void compact_notes_kernel(const long long* __restrict__ frame_off, co
 struct bp_model {
   int device = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;  // host->device audio copies of bp_transcribe_host run ahead of the compute stream
+  std::vector<cudaEvent_t> copy_ev;
   float* d_params = nullptr;
   float* d_derived = nullptr;
   double* d_gauss = nullptr;
@@ -440,6 +442,7 @@ int bp_model_create(const void* blob, size_t nbytes, int device, bp_model_t** ou
   bp_model* m = new bp_model();
   m->device = device;
   CK(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking));
   CK(cudaMalloc(&m->d_params, sizeof(float) * ParamLayout::total));
   CK(cudaMalloc(&m->d_derived, sizeof(float) * DerivedLayout::total));
   CK(cudaMalloc(&m->d_gauss, sizeof(double) * 51));
@@ -485,6 +488,8 @@ void bp_model_destroy(bp_model_t* m) {
   if (m->d_derived) cudaFree(m->d_derived);
   if (m->d_gauss) cudaFree(m->d_gauss);
   for (cudaEvent_t e : m->prof_ev) cudaEventDestroy(e);
+  for (cudaEvent_t e : m->copy_ev) cudaEventDestroy(e);
+  if (m->copy_stream) cudaStreamDestroy(m->copy_stream);
   if (m->stream) cudaStreamDestroy(m->stream);
   delete m;
 }
@@ -811,19 +816,66 @@ int bp_transcribe_host(bp_model_t* m, const float* h_audio, const int64_t* h_sam
                        const bp_decode_params_t* params, float* h_note, float* h_onset, float* h_contour,
                        int64_t* h_frame_off, bp_notes_t* notes) {
   if (!m || !h_sample_off || !h_frame_off || n_files < 0) return fail(BP_E_INVALID, "bp_transcribe_host: bad argument");
+  int rc = validate_params(params);
+  if (rc) return rc;
   DeviceGuard g(m->device);
   const int64_t n_samples = h_sample_off[n_files] - h_sample_off[0];
   cudaStream_t st = m->stream;
   CK(m->st_audio.reserve((size_t)std::max<int64_t>(n_samples, 1)));
-  if (n_samples > 0) {
-    if (!h_audio) return fail(BP_E_INVALID, "bp_transcribe_host: null audio");
-    CK(cudaMemcpyAsync(m->st_audio.p, h_audio + h_sample_off[0], sizeof(float) * n_samples, cudaMemcpyHostToDevice, st));
-  }
+  if (n_samples > 0 && !h_audio) return fail(BP_E_INVALID, "bp_transcribe_host: null audio");
   std::vector<int64_t> rel(n_files + 1);
+  int64_t total_frames = 0;
   for (int i = 0; i <= n_files; ++i) rel[i] = h_sample_off[i] - h_sample_off[0];
-  int rc = bp_transcribe_device(m, m->st_audio.p, rel.data(), n_files, params, h_frame_off, notes, st);
+  for (int i = 0; i < n_files; ++i) {
+    if (rel[i + 1] < rel[i]) return fail(BP_E_INVALID, "bp_transcribe_host: sample offsets must be non-decreasing");
+    total_frames += bp_num_frames(rel[i + 1] - rel[i]);
+  }
+  CK(m->st_note.reserve((size_t)total_frames * kPitches + 1));
+  CK(m->st_onset.reserve((size_t)total_frames * kPitches + 1));
+  CK(m->st_contour.reserve((size_t)total_frames * kContourBins + 1));
+
+  // Sub-batches of files (about 4 internal chunks of windows each): all host->device copies are queued on the copy
+  // stream up front, the compute stream waits for sub-batch k only, so the PCIe transfer of k+1.. overlaps the kernels.
+  std::vector<int> cut{0};
+  {
+    int64_t w = 0;
+    const int64_t limit = 4 * (int64_t)m->chunk;
+    for (int i = 0; i < n_files; ++i) {
+      w += bp_num_windows(rel[i + 1] - rel[i]);
+      if (w >= limit || i + 1 == n_files) {
+        cut.push_back(i + 1);
+        w = 0;
+      }
+    }
+  }
+  const size_t n_sub = cut.size() - 1;
+  while (m->copy_ev.size() < n_sub) {
+    cudaEvent_t e;
+    CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    m->copy_ev.push_back(e);
+  }
+  CK(cudaStreamSynchronize(st));  // st_audio may still be read by earlier work on the compute stream
+  for (size_t k = 0; k < n_sub; ++k) {
+    const int64_t s0 = rel[cut[k]], s1 = rel[cut[k + 1]];
+    if (s1 > s0)
+      CK(cudaMemcpyAsync(m->st_audio.p + s0, h_audio + h_sample_off[0] + s0, sizeof(float) * (s1 - s0),
+                         cudaMemcpyHostToDevice, m->copy_stream));
+    CK(cudaEventRecord(m->copy_ev[k], m->copy_stream));
+  }
+  h_frame_off[0] = 0;
+  std::vector<int64_t> sub_off;
+  for (size_t k = 0; k < n_sub; ++k) {
+    const int f0 = cut[k], f1 = cut[k + 1];
+    CK(cudaStreamWaitEvent(st, m->copy_ev[k], 0));
+    sub_off.assign(f1 - f0 + 1, 0);
+    const int64_t base = h_frame_off[f0];
+    rc = bp_run_inference_device(m, m->st_audio.p, rel.data() + f0, f1 - f0, m->st_note.p + base * kPitches,
+                                 m->st_onset.p + base * kPitches, m->st_contour.p + base * kContourBins, sub_off.data(), st);
+    if (rc) return rc;
+    for (int i = f0; i < f1; ++i) h_frame_off[i + 1] = base + sub_off[i - f0 + 1];
+  }
+  rc = bp_decode_device(m, m->st_note.p, m->st_onset.p, m->st_contour.p, h_frame_off, n_files, params, notes, st);
   if (rc) return rc;
-  const int64_t total_frames = h_frame_off[n_files];
   if (total_frames > 0) {
     if (h_note) CK(cudaMemcpyAsync(h_note, m->st_note.p, sizeof(float) * total_frames * kPitches, cudaMemcpyDeviceToHost, st));
     if (h_onset) CK(cudaMemcpyAsync(h_onset, m->st_onset.p, sizeof(float) * total_frames * kPitches, cudaMemcpyDeviceToHost, st));
