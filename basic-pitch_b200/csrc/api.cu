@@ -147,6 +147,7 @@ struct bp_model {
     DevBuf<uint16_t> tiles;
   } tc_contour, tc_onset, tc_note;
   DevBuf<__nv_bfloat16> yhl, chl;
+  DevBuf<float> cqt_wtc;  // split (3xTF32) kernel matrix of the tensor-core CQT
   size_t chl_zeroed = 0;  // elements of chl known to hold zeros in every row/bin the kernels never write
   int64_t launches = 0;
   // forward workspace (chunk windows)
@@ -270,6 +271,13 @@ int derive(bp_model* m, cudaStream_t st) {
     CK(cudaStreamSynchronize(st));
     L.dev = TcConvDev{pl.spec, L.tiles.p, pl.n_groups, l};
   }
+  {
+    std::vector<float> wtc;
+    build_cqt_tc_weights(hp.data() + ParamLayout::cqt_real, hp.data() + ParamLayout::cqt_imag, wtc);
+    CK(m->cqt_wtc.reserve(wtc.size()));
+    CK(cudaMemcpyAsync(m->cqt_wtc.p, wtc.data(), wtc.size() * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));
+  }
   tc_upload_epilogue(hp.data() + ParamLayout::contour1_b, hp.data() + ParamLayout::onset1_b,
                      hp.data() + ParamLayout::note1_b, hp.data() + ParamLayout::onset2_w, hp.data() + ParamLayout::note2_w, st);
   CKL();
@@ -329,8 +337,12 @@ int forward_chunk(bp_model* m, const float* audio, const WinDesc* desc, int nb, 
   }
   {
     ProfScope ps(m, 2, st);
-    launch_cqt(audio, desc, chain, m->d_derived + DerivedLayout::cqt_wt, m->d_params + ParamLayout::cqt_scale, m->y.p,
-               m->minmax.p, nb, st);
+    if (m->path == 1)
+      launch_cqt_tc(audio, desc, chain, m->cqt_wtc.p, m->d_params + ParamLayout::cqt_scale, m->y.p, m->minmax.p, nb,
+                    m->n_sms, st);
+    else
+      launch_cqt(audio, desc, chain, m->d_derived + DerivedLayout::cqt_wt, m->d_params + ParamLayout::cqt_scale, m->y.p,
+                 m->minmax.p, nb, st);
     launch_lognorm(m->y.p, m->minmax.p, m->d_params + ParamLayout::bn, nb, st);
   }
   if (m->path == 1) {
@@ -461,6 +473,7 @@ int bp_model_create(const void* blob, size_t nbytes, int device, bp_model_t** ou
                      P + ParamLayout::onset1_b,      D + DerivedLayout::onset2_wT, P + ParamLayout::onset2_b};
   cnn_setup();
   tc_setup();
+  cqt_tc_setup();
   m->n_sms = prop.multiProcessorCount;
   rc = derive(m, m->stream);
   if (rc) return rc;
@@ -483,6 +496,7 @@ void bp_model_destroy(bp_model_t* m) {
   m->d_bend_off.release(); m->d_bends.release();
   m->yhl.release();
   m->chl.release();
+  m->cqt_wtc.release();
   for (bp_model::TcLayer* L : {&m->tc_contour, &m->tc_onset, &m->tc_note}) L->tiles.release();
   if (m->d_params) cudaFree(m->d_params);
   if (m->d_derived) cudaFree(m->d_derived);

@@ -85,6 +85,12 @@ void launch_note_tapsum(const float* p21, const CnnWeights& w, float* note, int 
 void launch_onset_tapsum(const float* p9, const float* note, const CnnWeights& w, float* onset, int n_windows,
                          cudaStream_t st);
 
+// ---- cqt_tc.cu (tcgen05 kind::tf32 path of the constant-Q projection) ----------------------------
+void build_cqt_tc_weights(const float* cqt_real, const float* cqt_imag, std::vector<float>& out);
+void cqt_tc_setup();
+void launch_cqt_tc(const float* audio, const WinDesc* desc, const float* chain, const float* wtc, const float* scale,
+                   float* logmag, unsigned int* minmax, int n_windows, int n_sms, cudaStream_t st);
+
 // ---- unwrap (api.cu) / decode.cu ----------------------------------------------------------------
 struct DecodeParamsDev {
   double onset_thresh, frame_thresh;
