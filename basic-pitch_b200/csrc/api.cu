@@ -147,7 +147,7 @@ struct bp_model {
     DevBuf<uint16_t> tiles;
   } tc_contour, tc_onset, tc_note;
   DevBuf<__nv_bfloat16> yhl, chl;
-  DevBuf<float> cqt_wtc;  // split (3xTF32) kernel matrix of the tensor-core CQT
+  DevBuf<uint16_t> cqt_wtc;  // three-way bf16 split of the CQT kernel matrix (tensor-core path)
   size_t chl_zeroed = 0;  // elements of chl known to hold zeros in every row/bin the kernels never write
   int64_t launches = 0;
   // forward workspace (chunk windows)
@@ -272,10 +272,10 @@ int derive(bp_model* m, cudaStream_t st) {
     L.dev = TcConvDev{pl.spec, L.tiles.p, pl.n_groups, l};
   }
   {
-    std::vector<float> wtc;
+    std::vector<uint16_t> wtc;
     build_cqt_tc_weights(hp.data() + ParamLayout::cqt_real, hp.data() + ParamLayout::cqt_imag, wtc);
     CK(m->cqt_wtc.reserve(wtc.size()));
-    CK(cudaMemcpyAsync(m->cqt_wtc.p, wtc.data(), wtc.size() * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(m->cqt_wtc.p, wtc.data(), wtc.size() * 2, cudaMemcpyHostToDevice, st));
     CK(cudaStreamSynchronize(st));
   }
   tc_upload_epilogue(hp.data() + ParamLayout::contour1_b, hp.data() + ParamLayout::onset1_b,

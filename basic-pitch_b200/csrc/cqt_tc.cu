@@ -1,8 +1,10 @@
 // Constant-Q projection on the tensor cores: per octave the 172 x 256 x 72 contraction
 //   C[(b,t)][n] = sum_k xpad_o[b][t*hop_o + k] * W[k][n]          (n interleaves real / imaginary parts of 36 bins)
-// as tcgen05.mma kind::tf32 with the "3xTF32" split (x = hi + lo, products hi*hi + hi*lo + lo*hi, FP32 accumulation in
-// TMEM): a single TF32 or bf16 product is far from the 1e-3 bar for this stage, the
-// split reproduces FP32-class results.
+// as tcgen05.mma kind::f16 on a three-way bf16 split of both operands (x = hi + mid + lo, each round-to-nearest bf16;
+// the six products hi*hi, hi*mid, mid*hi, hi*lo, lo*hi, mid*mid are accumulated in FP32 in TMEM; the dropped terms are
+// below 2^-24 of |a||w|).  A single bf16 / TF32 product is far from the 1e-3 bar for this stage and even a two-way
+// split leaves ~1e-3 in the weak bins of the log spectrum (measured here with 3xTF32);
+// the three-way split reproduces FP32-class results.
 //
 // Replaces (together with the unchanged decimation chain) reference: basic_pitch/layers/nnaudio.py:216-256
 // (`get_cqt_complex`, reflect pad + two strided conv1d per octave), :642-661 (concat, sqrt(len) scaling, magnitude) and
@@ -12,12 +14,14 @@
 // descriptor can express for hop*4 B < 16 B or non-canonical pitches, so it is staged explicitly ("im2col" into the
 // canonical K-major core-matrix layout) by four producer warps that also do the reflect padding and the hi/lo split.
 //
-// item = (M-tile of 128 frames, octave); per item 4 K-chunks of 64 taps, each chunk = 8 k-steps x 3 products:
-//   warps 0-3   producers: gather 128 x 64 samples, split, st.shared into [plane][k/4][row][4] ; one lane bulk-copies
-//               the matching 40 KB slice of the split kernel matrix W (UBLKCP) ; fence.proxy.async ; mbarrier arrive
+// item = (M-tile of 128 frames, octave); per item 4 K-chunks of 64 taps, each chunk = 4 k-steps x 6 products:
+//   warps 0-3   producers: gather 128 x 64 samples, split, st.shared into [plane][k/8][row][8] ; one lane bulk-copies
+//               the matching 30 KB slice of the split kernel matrix W (UBLKCP) ; fence.proxy.async ; mbarrier arrive
 //   warp 4      MMA issuer (one elected lane): 24 tcgen05.mma per chunk, tcgen05.commit frees the stage / publishes TMEM
 //   warps 5-8   epilogue: tcgen05.ld 80 columns, magnitude * sqrt(len), log-power, store, per-window min/max (atomics)
-// Shared memory: 2 stages x (64 KB A + 40 KB W); TMEM: 2 accumulators of 128 x 80 (256 columns allocated).
+// Shared memory: 2 stages x (48 KB A + 30 KB W); TMEM: 2 accumulators of 128 x 80 (256 columns allocated).
+#include <cuda_bf16.h>
+
 #include <vector>
 
 #include "kernels.cuh"
@@ -29,49 +33,47 @@ namespace cq {
 constexpr int kMTile = 128;
 constexpr int kKc = 64;                          // taps per chunk
 constexpr int kN = 80;                           // 72 columns padded to a multiple of 16
-constexpr int kAPlane = (kKc / 4) * kMTile * 16;  // 32768 B : [16 k-chunks of 4][128 rows][16 B]
-constexpr int kWPlane = (kKc / 4) * kN * 16;      // 20480 B : [16][80][16 B]
-constexpr int kStageBytes = 2 * kAPlane + 2 * kWPlane;  // 106496
+constexpr int kAPlane = (kKc / 8) * kMTile * 16;  // 16384 B : [8 k-chunks of 8][128 rows][16 B]
+constexpr int kWPlane = (kKc / 8) * kN * 16;      // 10240 B : [8][80][16 B]
+constexpr int kStageBytes = 3 * kAPlane + 3 * kWPlane;  // 79872
 constexpr int kStages = 2;
 constexpr int kThreads = 288;
 constexpr int kSmemBytes = kStages * kStageBytes + 256;
 }  // namespace cq
 
-// kernel matrix, split and laid out per chunk: wtc[chunk 4][plane 2][k/4 16][n 80][4]
-void build_cqt_tc_weights(const float* cqt_real /* [36][256] */, const float* cqt_imag, std::vector<float>& out) {
-  out.assign((size_t)4 * 2 * 16 * cq::kN * 4, 0.f);
+static inline uint16_t f2bf_rn(float x) {
+  uint32_t u;
+  memcpy(&u, &x, 4);
+  u += 0x7fffu + ((u >> 16) & 1u);
+  return (uint16_t)(u >> 16);
+}
+static inline float bf2f_(uint16_t h) {
+  uint32_t u = (uint32_t)h << 16;
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+}
+
+// kernel matrix, three-way bf16 split, laid out per chunk: wtc[chunk 4][plane 3][k/8 8][n 80][8] (bf16)
+void build_cqt_tc_weights(const float* cqt_real /* [36][256] */, const float* cqt_imag, std::vector<uint16_t>& out) {
+  out.assign((size_t)4 * 3 * 8 * cq::kN * 8, 0);
   for (int k = 0; k < kTaps; ++k)
     for (int n = 0; n < 72; ++n) {
       const float w = (n & 1) ? cqt_imag[(n >> 1) * kTaps + k] : cqt_real[(n >> 1) * kTaps + k];
-      uint32_t u;
-      memcpy(&u, &w, 4);
-      u &= 0xffffe000u;  // TF32 keeps the top 19 bits
-      float hi;
-      memcpy(&hi, &u, 4);
-      const float lo = w - hi;
+      const uint16_t h = f2bf_rn(w);
+      const float r1 = w - bf2f_(h);
+      const uint16_t m = f2bf_rn(r1);
+      const uint16_t l = f2bf_rn(r1 - bf2f_(m));
       const int c = k / cq::kKc, kk = k % cq::kKc;
-      const size_t base = (size_t)c * 2 * 16 * cq::kN * 4;
-      const size_t off = ((size_t)(kk >> 2) * cq::kN + n) * 4 + (kk & 3);
-      out[base + off] = hi;
-      out[base + (size_t)16 * cq::kN * 4 + off] = lo;
+      const size_t plane = (size_t)8 * cq::kN * 8;
+      const size_t base = (size_t)c * 3 * plane;
+      const size_t off = ((size_t)(kk >> 3) * cq::kN + n) * 8 + (kk & 7);
+      out[base + off] = h;
+      out[base + plane + off] = m;
+      out[base + 2 * plane + off] = l;
     }
 }
 
-// instruction descriptor, kind::tf32: D = f32 (bit 4), A = B = TF32 (format 2 at bits 7, 10), both K-major
-__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                          uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
-      "}\n" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
 __device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&v)[16]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
@@ -85,7 +87,7 @@ struct CqtTcArgs {
   const float* audio;
   const WinDesc* desc;   // may be null: window b = audio + b*43844
   const float* chain;    // decimated signals x_1..x_8
-  const float* wtc;      // split kernel matrix, 4 chunks of 40 KB
+  const uint16_t* wtc;   // split kernel matrix (bf16), 4 chunks of 30 KB
   const float* scale;    // [309] sqrt(kernel length)
   float* logmag;         // [B][172][309]
   unsigned int* minmax;  // [B][2] ordered-uint min / max
@@ -159,17 +161,17 @@ __global__ void __launch_bounds__(cq::kThreads, 1) cqt_tc_kernel(const CqtTcArgs
         mbar_wait(empty + stage, ph ^ 1);
         unsigned char* sa = smem + stage * kStageBytes;
         if (threadIdx.x == 0) {
-          mbar_expect_tx_only(full + stage, 2 * kWPlane);  // the bulk copy of the W slice completes on the same barrier
-          bulk_g2s(sa + 2 * kAPlane, a.wtc + (size_t)c * (2 * kWPlane / 4), 2 * kWPlane, full + stage);
+          mbar_expect_tx_only(full + stage, 3 * kWPlane);  // the bulk copy of the W slice completes on the same barrier
+          bulk_g2s(sa + 3 * kAPlane, a.wtc + (size_t)c * (3 * kWPlane / 2), 3 * kWPlane, full + stage);
         }
         const int ib = i0 + c * kKc;
         const bool interior = live && ib >= lo && ib + kKc <= hi && ib >= 0 && ib + kKc <= len;
-#pragma unroll 4
-        for (int kc = 0; kc < kKc / 4; ++kc) {
-          float v[4];
+#pragma unroll 2
+        for (int kc = 0; kc < kKc / 8; ++kc) {
+          __align__(16) __nv_bfloat16 h[8], md[8], l[8];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            int idx = ib + 4 * kc + j;
+          for (int j = 0; j < 8; ++j) {
+            int idx = ib + 8 * kc + j;
             float x = 0.f;
             if (interior) {
               x = __ldg(src + idx);
@@ -178,19 +180,15 @@ __global__ void __launch_bounds__(cq::kThreads, 1) cqt_tc_kernel(const CqtTcArgs
               if (idx >= len) idx = 2 * (len - 1) - idx;
               if (idx >= lo && idx < hi) x = __ldg(src + idx);
             }
-            v[j] = x;
+            h[j] = __float2bfloat16_rn(x);
+            const float r1 = x - __bfloat162float(h[j]);
+            md[j] = __float2bfloat16_rn(r1);
+            l[j] = __float2bfloat16_rn(r1 - __bfloat162float(md[j]));
           }
-          float4 h, l;
-          h.x = __uint_as_float(__float_as_uint(v[0]) & 0xffffe000u);
-          h.y = __uint_as_float(__float_as_uint(v[1]) & 0xffffe000u);
-          h.z = __uint_as_float(__float_as_uint(v[2]) & 0xffffe000u);
-          h.w = __uint_as_float(__float_as_uint(v[3]) & 0xffffe000u);
-          l.x = v[0] - h.x;
-          l.y = v[1] - h.y;
-          l.z = v[2] - h.z;
-          l.w = v[3] - h.w;
-          *reinterpret_cast<float4*>(sa + (kc * kMTile + r) * 16) = h;
-          *reinterpret_cast<float4*>(sa + kAPlane + (kc * kMTile + r) * 16) = l;
+          const int o16 = (kc * kMTile + r) * 16;
+          *reinterpret_cast<uint4*>(sa + o16) = *reinterpret_cast<const uint4*>(h);
+          *reinterpret_cast<uint4*>(sa + kAPlane + o16) = *reinterpret_cast<const uint4*>(md);
+          *reinterpret_cast<uint4*>(sa + 2 * kAPlane + o16) = *reinterpret_cast<const uint4*>(l);
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the MMA
         mbar_arrive(full + stage);
@@ -202,7 +200,7 @@ __global__ void __launch_bounds__(cq::kThreads, 1) cqt_tc_kernel(const CqtTcArgs
     }
   } else if (warp == 4) {
     // ------------------------------ MMA issuer ------------------------------
-    constexpr uint32_t idesc = make_idesc_tf32(128, kN);
+    constexpr uint32_t idesc = make_idesc(128, kN);  // kind::f16, bf16 x bf16 -> f32
     const uint32_t leader = elect_one() ? 1u : 0u;
     uint32_t stage = 0, ph = 0, icount = 0;
     uint32_t ph_t[2] = {0, 0};
@@ -218,15 +216,19 @@ __global__ void __launch_bounds__(cq::kThreads, 1) cqt_tc_kernel(const CqtTcArgs
         const uint32_t sa = smem_u32(smem + stage * kStageBytes);
         if (leader) {
 #pragma unroll
-          for (int ks = 0; ks < kKc / 8; ++ks) {
-            // one k-step = 8 taps = two 16-byte k-chunks, LBO apart
-            const uint64_t a_hi = make_desc(sa + ks * 2 * (kMTile * 16), kMTile * 16, 128);
-            const uint64_t a_lo = make_desc(sa + kAPlane + ks * 2 * (kMTile * 16), kMTile * 16, 128);
-            const uint64_t b_hi = make_desc(sa + 2 * kAPlane + ks * 2 * (kN * 16), kN * 16, 128);
-            const uint64_t b_lo = make_desc(sa + 2 * kAPlane + kWPlane + ks * 2 * (kN * 16), kN * 16, 128);
-            umma_tf32(d, a_hi, b_hi, idesc, (c | ks) ? 1u : 0u);
-            umma_tf32(d, a_hi, b_lo, idesc, 1u);
-            umma_tf32(d, a_lo, b_hi, idesc, 1u);
+          for (int ks = 0; ks < kKc / 16; ++ks) {
+            // one k-step = 16 taps = two 16-byte k-chunks, LBO apart
+            const uint32_t ao = sa + ks * 2 * (kMTile * 16), bo = sa + 3 * kAPlane + ks * 2 * (kN * 16);
+            const uint64_t a_h = make_desc(ao, kMTile * 16, 128), a_m = make_desc(ao + kAPlane, kMTile * 16, 128),
+                           a_l = make_desc(ao + 2 * kAPlane, kMTile * 16, 128);
+            const uint64_t b_h = make_desc(bo, kN * 16, 128), b_m = make_desc(bo + kWPlane, kN * 16, 128),
+                           b_l = make_desc(bo + 2 * kWPlane, kN * 16, 128);
+            umma_bf16(d, a_h, b_h, idesc, (c | ks) ? 1u : 0u);
+            umma_bf16(d, a_h, b_m, idesc, 1u);
+            umma_bf16(d, a_m, b_h, idesc, 1u);
+            umma_bf16(d, a_h, b_l, idesc, 1u);
+            umma_bf16(d, a_l, b_h, idesc, 1u);
+            umma_bf16(d, a_m, b_m, idesc, 1u);
           }
           umma_commit(empty + stage);
         }
@@ -327,7 +329,7 @@ void cqt_tc_setup() {
   cudaFuncSetAttribute(cqt_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, cq::kSmemBytes);
 }
 
-void launch_cqt_tc(const float* audio, const WinDesc* desc, const float* chain, const float* wtc, const float* scale,
+void launch_cqt_tc(const float* audio, const WinDesc* desc, const float* chain, const uint16_t* wtc, const float* scale,
                    float* logmag, unsigned int* minmax, int n_windows, int n_sms, cudaStream_t st) {
   minmax_init_kernel2<<<(n_windows + 255) / 256, 256, 0, st>>>(minmax, n_windows);
   CqtTcArgs a;

@@ -85,10 +85,10 @@ void launch_note_tapsum(const float* p21, const CnnWeights& w, float* note, int 
 void launch_onset_tapsum(const float* p9, const float* note, const CnnWeights& w, float* onset, int n_windows,
                          cudaStream_t st);
 
-// ---- cqt_tc.cu (tcgen05 kind::tf32 path of the constant-Q projection) ----------------------------
-void build_cqt_tc_weights(const float* cqt_real, const float* cqt_imag, std::vector<float>& out);
+// ---- cqt_tc.cu (tcgen05 path of the constant-Q projection, three-way bf16 split) ----------------------------
+void build_cqt_tc_weights(const float* cqt_real, const float* cqt_imag, std::vector<uint16_t>& out);
 void cqt_tc_setup();
-void launch_cqt_tc(const float* audio, const WinDesc* desc, const float* chain, const float* wtc, const float* scale,
+void launch_cqt_tc(const float* audio, const WinDesc* desc, const float* chain, const uint16_t* wtc, const float* scale,
                    float* logmag, unsigned int* minmax, int n_windows, int n_sms, cudaStream_t st);
 
 // ---- unwrap (api.cu) / decode.cu ----------------------------------------------------------------
