@@ -15,10 +15,11 @@
 // canonical K-major core-matrix layout) by four producer warps that also do the reflect padding and the hi/lo split.
 //
 // item = (M-tile of 128 frames, octave); per item 4 K-chunks of 64 taps, each chunk = 4 k-steps x 6 products:
-//   warps 0-3   producers: gather 128 x 64 samples, split, st.shared into [plane][k/8][row][8] ; one lane bulk-copies
-//               the matching 30 KB slice of the split kernel matrix W (UBLKCP) ; fence.proxy.async ; mbarrier arrive
-//   warp 4      MMA issuer (one elected lane): 24 tcgen05.mma per chunk, tcgen05.commit frees the stage / publishes TMEM
-//   warps 5-8   epilogue: tcgen05.ld 80 columns, magnitude * sqrt(len), log-power, store, per-window min/max (atomics)
+//   warps 0-7   producers: gather 128 x 64 samples (128-bit loads where aligned), split, st.shared into
+//               [plane][k/8][row][8] ; one lane bulk-copies the matching 30 KB slice of the split kernel matrix W
+//               (UBLKCP) ; fence.proxy.async ; mbarrier arrive
+//   warp 8      MMA issuer (one elected lane): 24 tcgen05.mma per chunk, tcgen05.commit frees the stage / publishes TMEM
+//   warps 9-12  epilogue: tcgen05.ld 80 columns, magnitude * sqrt(len), log-power, store, per-window min/max (atomics)
 // Shared memory: 2 stages x (48 KB A + 30 KB W); TMEM: 2 accumulators of 128 x 80 (256 columns allocated).
 #include <cuda_bf16.h>
 
@@ -37,7 +38,8 @@ constexpr int kAPlane = (kKc / 8) * kMTile * 16;  // 16384 B : [8 k-chunks of 8]
 constexpr int kWPlane = (kKc / 8) * kN * 16;      // 10240 B : [8][80][16 B]
 constexpr int kStageBytes = 3 * kAPlane + 3 * kWPlane;  // 79872
 constexpr int kStages = 2;
-constexpr int kThreads = 288;
+constexpr int kProducers = 256;  // 8 producer warps: thread = (row, half of the 8 k-chunks)
+constexpr int kThreads = kProducers + 32 + 128;
 constexpr int kSmemBytes = kStages * kStageBytes + 256;
 }  // namespace cq
 
@@ -109,7 +111,7 @@ __global__ void __launch_bounds__(cq::kThreads, 1) cqt_tc_kernel(const CqtTcArgs
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) {
-      mbar_init(full + s, 128);
+      mbar_init(full + s, kProducers);
       mbar_init(empty + s, 1);
     }
     for (int i = 0; i < 2; ++i) {
@@ -118,7 +120,7 @@ __global__ void __launch_bounds__(cq::kThreads, 1) cqt_tc_kernel(const CqtTcArgs
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 4) {
+  if (warp == 8) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -130,9 +132,10 @@ __global__ void __launch_bounds__(cq::kThreads, 1) cqt_tc_kernel(const CqtTcArgs
   const int n_items = a.n_mtiles * kOctaves;
   const int total_frames = a.n_windows * kFrames;
 
-  if (warp < 4) {
-    // ------------------------------ producers: one row (frame) per thread ------------------------------
-    const int r = threadIdx.x;  // 0..127
+  if (warp < 8) {
+    // ------------------------------ producers: thread = (frame row, half of the k-chunks) ------------------------------
+    const int r = threadIdx.x & 127;
+    const int khalf = threadIdx.x >> 7;
     uint32_t stage = 0, ph = 0;
     for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
       const int mt = it / kOctaves, o = it % kOctaves;
@@ -166,24 +169,40 @@ __global__ void __launch_bounds__(cq::kThreads, 1) cqt_tc_kernel(const CqtTcArgs
         }
         const int ib = i0 + c * kKc;
         const bool interior = live && ib >= lo && ib + kKc <= hi && ib >= 0 && ib + kKc <= len;
-#pragma unroll 2
-        for (int kc = 0; kc < kKc / 8; ++kc) {
-          __align__(16) __nv_bfloat16 h[8], md[8], l[8];
+        const bool vec = interior && ((reinterpret_cast<uintptr_t>(src + ib) & 15) == 0);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            int idx = ib + 8 * kc + j;
-            float x = 0.f;
-            if (interior) {
-              x = __ldg(src + idx);
-            } else if (live) {
-              if (idx < 0) idx = -idx;
-              if (idx >= len) idx = 2 * (len - 1) - idx;
-              if (idx >= lo && idx < hi) x = __ldg(src + idx);
+        for (int q = 0; q < kKc / 16; ++q) {
+          const int kc = khalf * (kKc / 16) + q;
+          float x[8];
+          if (vec) {  // 16-byte aligned interior rows: two 128-bit loads
+            const float4 v0 = __ldg(reinterpret_cast<const float4*>(src + ib + 8 * kc));
+            const float4 v1 = __ldg(reinterpret_cast<const float4*>(src + ib + 8 * kc) + 1);
+            x[0] = v0.x; x[1] = v0.y; x[2] = v0.z; x[3] = v0.w;
+            x[4] = v1.x; x[5] = v1.y; x[6] = v1.z; x[7] = v1.w;
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              int idx = ib + 8 * kc + j;
+              float xv = 0.f;
+              if (interior) {
+                xv = __ldg(src + idx);
+              } else if (live) {
+                if (idx < 0) idx = -idx;
+                if (idx >= len) idx = 2 * (len - 1) - idx;
+                if (idx >= lo && idx < hi) xv = __ldg(src + idx);
+              }
+              x[j] = xv;
             }
-            h[j] = __float2bfloat16_rn(x);
-            const float r1 = x - __bfloat162float(h[j]);
-            md[j] = __float2bfloat16_rn(r1);
-            l[j] = __float2bfloat16_rn(r1 - __bfloat162float(md[j]));
+          }
+          __align__(16) __nv_bfloat162 h[4], md[4], l[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            h[j] = __floats2bfloat162_rn(x[2 * j], x[2 * j + 1]);
+            const float2 hf = __bfloat1622float2(h[j]);
+            const float r0 = x[2 * j] - hf.x, r1 = x[2 * j + 1] - hf.y;
+            md[j] = __floats2bfloat162_rn(r0, r1);
+            const float2 mf = __bfloat1622float2(md[j]);
+            l[j] = __floats2bfloat162_rn(r0 - mf.x, r1 - mf.y);
           }
           const int o16 = (kc * kMTile + r) * 16;
           *reinterpret_cast<uint4*>(sa + o16) = *reinterpret_cast<const uint4*>(h);
@@ -198,7 +217,7 @@ __global__ void __launch_bounds__(cq::kThreads, 1) cqt_tc_kernel(const CqtTcArgs
         }
       }
     }
-  } else if (warp == 4) {
+  } else if (warp == 8) {
     // ------------------------------ MMA issuer ------------------------------
     constexpr uint32_t idesc = make_idesc(128, kN);  // kind::f16, bf16 x bf16 -> f32
     const uint32_t leader = elect_one() ? 1u : 0u;
@@ -243,7 +262,7 @@ __global__ void __launch_bounds__(cq::kThreads, 1) cqt_tc_kernel(const CqtTcArgs
       ++icount;
     }
   } else {
-    // ------------------------------ epilogue (warps 5..8) ------------------------------
+    // ------------------------------ epilogue (warps 9..12) ------------------------------
     const int quad = warp & 3;
     const int row = quad * 32 + lane;
     uint32_t ph_t[2] = {0, 0};
@@ -312,7 +331,7 @@ __global__ void __launch_bounds__(cq::kThreads, 1) cqt_tc_kernel(const CqtTcArgs
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == 8) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256));
   }
 }
