@@ -250,6 +250,12 @@ def main():
         achieved = fam_flop * k_windows / (k_ms * 1e-3) / 1e12 if k_ms > 0 else None
         threads = host_threads()
         cpu_v, cpu_desc = cpu_baseline_bounded(args.cpu_seconds, threads)
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as fh:
+                traffic = json.load(fh)["dram_bytes_per_window"] * k_windows if args.profile_kernel == 0 else None
+        except (OSError, KeyError, ValueError):
+            pass
         value = world * args.steps * audio_s / (ms * 1e-3)
         line = {
             "metric": "audio_seconds_per_second", "value": value, "unit": "audio-s/s", "n_gpus": world, "steps": args.steps,
@@ -268,9 +274,10 @@ def main():
                     "api": "bp_transcribe_host (pinned host audio in, note events out)"},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"bound": "tensor", "kernel": {0: "contour conv 3x39 (conv_kernel<Contour1Cfg>)", 1: "onset conv 5x5", 2: "cqt", 3: "decimate"}.get(args.profile_kernel),
+            "roofline": {"bound": "tensor", "kernel": {0: "contour conv 8->8 3x39 (conv_tc_kernel<0>, tcgen05 split-bf16)", 1: "onset conv 8->32 5x5/3 (conv_tc_kernel<1>)", 2: "cqt + lognorm", 3: "decimation chain"}.get(args.profile_kernel),
                          "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": (achieved / peak_tf) if achieved else None,
-                         "traffic": None, "peak_source": peak_src, "avg_launch_ms": k_ms, "windows_per_launch": k_windows,
+                         "traffic": traffic, "traffic_unit": "DRAM bytes per launch (ncu, profiles/roofline_traffic.json)",
+                         "peak_source": peak_src, "avg_launch_ms": k_ms, "windows_per_launch": k_windows,
                          "flop_per_window": fam_flop},
             "cpu_baseline": {"value": cpu_v, "unit": "audio-s/s", "cores": threads, "kind": "port", "sample": cpu_desc},
         }  # fmt: skip
