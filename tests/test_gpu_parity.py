@@ -282,3 +282,60 @@ def test_transcribe_batch_equals_per_file(model):
         for k in o1[0]:
             np.testing.assert_array_equal(o1[0][k], outs[i][k], err_msg=k)
     assert sum(len(r["start"]) for r in res) > 20
+
+
+def test_dense_polyphony_batch_bit_exact(model):
+    """BASELINE configs[4]: 88-voice chords, several 10 s clips in one batch; decode (incl. pitch bends) bit-identical to
+    the oracle decode on the same GPU posteriorgrams."""
+    from basic_pitch_b200 import synth
+    from oracle import decode_ref
+
+    clips = [synth.dense_chords_clip(10.0, seed=7 + i) for i in range(3)]
+    outs, res, frames = model.transcribe_arrays(clips)
+    total = 0
+    for i in range(len(clips)):
+        with np.errstate(all="ignore"):
+            wb, ev = decode_ref.model_output_to_note_events({k: np.array(v) for k, v in outs[i].items()}, 0.5, 0.3)
+        exp = events_to_arrays(wb, ev)
+        got_wb = [(int(a), int(b), int(p), amp, None) for a, b, p, amp in zip(res[i]["start"], res[i]["end"], res[i]["pitch"], res[i]["amp"])]
+        from basic_pitch_b200 import note_creation as nc
+
+        got = events_to_arrays(got_wb, nc.note_events_from_arrays(res[i], frames[i]))
+        assert_events_equal(got, exp, ctx=f"chords clip {i}")
+        total += len(ev)
+    assert total > 300
+
+
+def test_predict_batch_and_error_paths(model, tmp_path):
+    import ctypes as C
+
+    from basic_pitch_b200 import _lib, synth
+    from basic_pitch_b200.inference import predict_batch
+
+    clips = [synth.tones_clip(2.0, seed=3), synth.random_notes_clip(4.0, seed=5)]
+    results = predict_batch(clips, model, multiple_pitch_bends=True)
+    assert len(results) == 2
+    for (out, midi, events), clip in zip(results, clips):
+        assert out["note"].shape[0] == int(len(clip) / 36164 * 142)
+        assert sum(len(i.notes) for i in midi.instruments) == len(events)
+    # capacity negotiation: a deliberately tiny note buffer reports the needed size
+    lib = _lib.load()
+    post = model.run_inference_arrays([clips[1]])[0]
+    notes, arrs = model._alloc_notes(1, 1, 1)
+    p = model._params(0.5, 0.3, 11, 11, True, True, True, 0, 88)
+    foff = np.array([0, post["note"].shape[0]], np.int64)
+    with pytest.raises(_lib.BpError) as e:
+        lib.bp_decode_host(model.handle, post["note"].ctypes.data, post["onset"].ctypes.data, post["contour"].ctypes.data,
+                           foff.ctypes.data, 1, C.byref(p), C.byref(notes))
+    assert e.value.code == _lib.BP_E_CAPACITY and "need" in str(e.value)
+    # the reference never terminates for frame_thresh < 0 with melodia; this build refuses
+    with pytest.raises(_lib.BpError) as e:
+        model.decode_arrays([post["note"]], [post["onset"]], [post["contour"]], frame_thresh=-0.1)
+    assert e.value.code == _lib.BP_E_INVALID
+    # and the frequency limits zero the caller's arrays like the reference does
+    from basic_pitch_b200 import note_creation as nc
+
+    out = {k: np.array(v) for k, v in post.items()}
+    nc.model_output_to_notes(out, 0.5, 0.3, min_freq=110.0, max_freq=880.0, model=model)
+    lo, hi = nc.frequency_to_column_range(110.0, 880.0)
+    assert not out["note"][:, :lo].any() and not out["onset"][:, hi:].any() and out["note"][:, lo:hi].any()
