@@ -853,8 +853,9 @@ int bp_transcribe_host(bp_model_t* m, const float* h_audio, const int64_t* h_sam
   std::vector<int> cut{0};
   {
     int64_t w = 0;
-    const int64_t limit = 4 * (int64_t)m->chunk;
     for (int i = 0; i < n_files; ++i) {
+      // the first sub-batch is small (its copy cannot be hidden), the others span about 4 internal chunks
+      const int64_t limit = (cut.size() == 1 ? 1 : 4) * (int64_t)m->chunk;
       w += bp_num_windows(rel[i + 1] - rel[i]);
       if (w >= limit || i + 1 == n_files) {
         cut.push_back(i + 1);

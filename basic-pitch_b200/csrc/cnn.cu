@@ -235,13 +235,13 @@ __global__ void __launch_bounds__(Cfg::THREADS) conv1_kernel(In in, const float*
     __syncthreads();
     if constexpr (In::kChannelsLast) {
       // channels-last input: every tile row is one contiguous run of NEED x CIN floats -> float4 loads
-      static_assert(Cfg::CIC == Cfg::CIN && Cfg::CIN % 4 == 0, "channels-last staging takes all channels in one pass");
-      constexpr int V = Cfg::CIN / 4;
+      static_assert(Cfg::CIC % 4 == 0, "channels-last staging moves float4 groups of channels");
+      constexpr int V = Cfg::CIC / 4;
       for (int e = tid; e < Cfg::ROWS * Cfg::NEED * V; e += Cfg::THREADS) {
         const int c4 = (e % V) * 4;
         const int x = (e / V) % Cfg::NEED;
         const int r = e / (V * Cfg::NEED);
-        const float4 v = in.load4(b, c4, t0 - Cfg::PT + r, f0 - Cfg::PL + x);
+        const float4 v = in.load4(b, c0 + c4, t0 - Cfg::PT + r, f0 - Cfg::PL + x);
         float* d = in_s + (c4 * Cfg::ROWS + r) * Cfg::RS + (x & 3) * Cfg::PH + (x >> 2);
         d[0] = v.x;
         d[Cfg::ROWS * Cfg::RS] = v.y;
@@ -357,7 +357,7 @@ __global__ void __launch_bounds__(256) tap_sum_kernel(const float* __restrict__ 
 
 //                           CIN CIC KH KW PT PL WOUT TR
 using Contour2Cfg1 = Conv1Cfg<8, 4, 5, 5, 2, 2, 264, 11>;
-using Contour2CfgN = Conv1Cfg<8, 8, 5, 5, 2, 2, 264, 5>;  // channels-last input
+using Contour2CfgN = Conv1Cfg<8, 4, 5, 5, 2, 2, 264, 11>;  // channels-last input, two passes of 4 channels
 using Note2Cfg1 = Conv1Cfg<32, 4, 7, 3, 3, 1, 88, 11>;
 using Onset2Cfg1 = Conv1Cfg<33, 3, 3, 3, 1, 1, 88, 11>;
 
