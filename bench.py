@@ -170,6 +170,10 @@ def main():
     if args.warmup < 3:
         args.warmup = 3
 
+    # NCCL prints its version banner on stdout at VERSION/INFO level; the contract is ONE JSON line on stdout
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"
+
     import torch
     import torch.distributed as dist
 
