@@ -147,6 +147,8 @@ struct bp_model {
     DevBuf<uint16_t> tiles;
   } tc_contour, tc_onset, tc_note;
   DevBuf<__nv_bfloat16> yhl, chl;
+  std::vector<float> h_params;  // host copy of the parameter block (weight-dependent __constant__ data is re-uploaded
+                                // from it whenever another model used the device's constant bank in between)
   DevBuf<uint16_t> cqt_wtc;  // three-way bf16 split of the CQT kernel matrix (tensor-core path)
   size_t chl_zeroed = 0;  // elements of chl known to hold zeros in every row/bin the kernels never write
   int64_t launches = 0;
@@ -174,6 +176,10 @@ struct bp_model {
 };
 
 namespace {
+
+// Weight-dependent data in __constant__ memory (FIR taps, conv1 biases, fused conv2 weights) is shared by all models
+// of a process on one device; remember whose values are resident.
+const bp_model* g_const_owner[64] = {};
 
 struct DeviceGuard {
   int prev = -1;
@@ -246,14 +252,23 @@ int parse_blob(const void* blob, size_t nbytes, std::vector<float>& params) {
   return BP_OK;
 }
 
+int upload_constants(bp_model* m, cudaStream_t st) {
+  const float* hp = m->h_params.data();
+  upload_lowpass(m->d_params + ParamLayout::lowpass, st);
+  tc_upload_epilogue(hp + ParamLayout::contour1_b, hp + ParamLayout::onset1_b, hp + ParamLayout::note1_b,
+                     hp + ParamLayout::onset2_w, hp + ParamLayout::note2_w, st);
+  CKL();
+  if (m->device >= 0 && m->device < 64) g_const_owner[m->device] = m;
+  return BP_OK;
+}
+
 int derive(bp_model* m, cudaStream_t st) {
   derive_kernel<<<(256 * 72 + 255) / 256, 256, 0, st>>>(m->d_params, m->d_derived);
   CKL();
-  upload_lowpass(m->d_params + ParamLayout::lowpass, st);
-  CKL();
   m->launches += 1;
   // tensor-core plans: split-bf16 Toeplitz weight tiles + MMA programs (host-built from the parameter block)
-  std::vector<float> hp(ParamLayout::total);
+  m->h_params.resize(ParamLayout::total);
+  std::vector<float>& hp = m->h_params;
   CK(cudaMemcpyAsync(hp.data(), m->d_params, sizeof(float) * ParamLayout::total, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
   const TcConvSpec specs[3] = {tc_contour_spec(), tc_onset_spec(), tc_note_spec()};
@@ -278,9 +293,7 @@ int derive(bp_model* m, cudaStream_t st) {
     CK(cudaMemcpyAsync(m->cqt_wtc.p, wtc.data(), wtc.size() * 2, cudaMemcpyHostToDevice, st));
     CK(cudaStreamSynchronize(st));
   }
-  tc_upload_epilogue(hp.data() + ParamLayout::contour1_b, hp.data() + ParamLayout::onset1_b,
-                     hp.data() + ParamLayout::note1_b, hp.data() + ParamLayout::onset2_w, hp.data() + ParamLayout::note2_w, st);
-  CKL();
+  return upload_constants(m, st);
   return BP_OK;
 }
 
@@ -331,6 +344,10 @@ int forward_chunk(bp_model* m, const float* audio, const WinDesc* desc, int nb, 
                   float* contour, cudaStream_t st) {
   float* chain = m->chain.p;
   if (m->profile_which >= 0) m->prof_windows += nb;
+  if (m->device >= 0 && m->device < 64 && g_const_owner[m->device] != m) {
+    int rc = upload_constants(m, st);
+    if (rc) return rc;
+  }
   {
     ProfScope ps(m, 3, st);
     for (int s = 0; s < 8; ++s) launch_decimate(audio, desc, chain, s, nb, st);
@@ -486,6 +503,7 @@ void bp_model_destroy(bp_model_t* m) {
   if (!m) return;
   DeviceGuard g(m->device);
   cudaDeviceSynchronize();
+  if (m->device >= 0 && m->device < 64 && g_const_owner[m->device] == m) g_const_owner[m->device] = nullptr;
   m->chain.release(); m->y.release(); m->c1.release(); m->n1.release(); m->o1.release();
   m->raw_note.release(); m->raw_onset.release(); m->raw_contour.release(); m->minmax.release();
   m->wdesc.release(); m->udesc.release(); m->st_audio.release(); m->st_note.release(); m->st_onset.release();

@@ -339,3 +339,27 @@ def test_predict_batch_and_error_paths(model, tmp_path):
     nc.model_output_to_notes(out, 0.5, 0.3, min_freq=110.0, max_freq=880.0, model=model)
     lo, hi = nc.frequency_to_column_range(110.0, 880.0)
     assert not out["note"][:, :lo].any() and not out["onset"][:, hi:].any() and out["note"][:, lo:hi].any()
+
+
+def test_two_models_with_different_weights_do_not_interfere(model, weights_np, tmp_path):
+    """Weight-dependent constants live in __constant__ memory shared by all models of a process on one device; the library
+    re-uploads them when the active model changes (the reference allows loading several model files side by side)."""
+    from basic_pitch_b200 import synth, weights
+    from basic_pitch_b200.inference import Model
+
+    w2 = {k: v.copy() for k, v in weights_np.items()}
+    w2["onset1_b"] = w2["onset1_b"] + 0.25
+    w2["note2_w"] = w2["note2_w"] * 0.5
+    w2["lowpass"] = w2["lowpass"][::-1].copy() * 0.9
+    path = tmp_path / "other.bpw"
+    path.write_bytes(weights.pack(w2))
+    other = Model(path)
+    x = synth.window_batch(3, seed=13)
+    a0 = model.predict(x)
+    b0 = other.predict(x)
+    a1 = model.predict(x)
+    b1 = other.predict(x)
+    for k in a0:
+        np.testing.assert_array_equal(a0[k], a1[k])
+        np.testing.assert_array_equal(b0[k], b1[k])
+    assert np.abs(a0["note"] - b0["note"]).max() > 1e-3 and np.abs(a0["onset"] - b0["onset"]).max() > 1e-3
