@@ -138,8 +138,8 @@ struct bp_model {
   float* d_derived = nullptr;
   double* d_gauss = nullptr;
   CnnWeights cw{};
-  int chunk = 217;  // 217 windows = 296 M-tiles of 128 rows = 2 per SM on 148 SMs
-  int path = 1;  // 0 = FP32 FFMA everywhere, 1 = tcgen05 contour conv
+  int chunk = 216;  // windows per launch sequence: the M-tiles of every tensor-core layer fill whole waves (bp_model_create)
+  int path = 1;  // 0 = FP32 FFMA everywhere, 1 = tcgen05 with fused epilogues, 2 = tcgen05 keeping the contour activations
   int n_sms = 148;
   struct TcLayer {
     TcConvPlan plan;
@@ -256,7 +256,7 @@ int upload_constants(bp_model* m, cudaStream_t st) {
   const float* hp = m->h_params.data();
   upload_lowpass(m->d_params + ParamLayout::lowpass, st);
   tc_upload_epilogue(hp + ParamLayout::contour1_b, hp + ParamLayout::onset1_b, hp + ParamLayout::note1_b,
-                     hp + ParamLayout::onset2_w, hp + ParamLayout::note2_w, st);
+                     hp + ParamLayout::onset2_w, hp + ParamLayout::note2_w, hp + ParamLayout::contour2_w, st);
   CKL();
   if (m->device >= 0 && m->device < 64) g_const_owner[m->device] = m;
   return BP_OK;
@@ -354,7 +354,7 @@ int forward_chunk(bp_model* m, const float* audio, const WinDesc* desc, int nb, 
   }
   {
     ProfScope ps(m, 2, st);
-    if (m->path == 1)
+    if (m->path >= 1)
       launch_cqt_tc(audio, desc, chain, m->cqt_wtc.p, m->d_params + ParamLayout::cqt_scale, m->y.p, m->minmax.p, nb,
                     m->n_sms, st);
     else
@@ -362,17 +362,20 @@ int forward_chunk(bp_model* m, const float* audio, const WinDesc* desc, int nb, 
                  m->minmax.p, nb, st);
     launch_lognorm(m->y.p, m->minmax.p, m->d_params + ParamLayout::bn, nb, st);
   }
-  if (m->path == 1) {
+  if (m->path >= 1) {
     const TcConvSpec cs = tc_contour_spec(), ns = tc_note_spec();
     const int ystride = tc_rows_total(m->chunk, cs.rows_per_window), cstride = tc_rows_total(m->chunk, ns.rows_per_window);
     launch_split(m->y.p, m->yhl.p, cs, nb, ystride, st);
     {
       ProfScope ps(m, 0, st);
-      launch_conv_tc(m->yhl.p, m->tc_contour.dev, m->c1.p, nb, ystride, m->n_sms, st);
+      launch_conv_tc(m->yhl.p, m->tc_contour.dev, m->c1.p, nb, ystride, m->n_sms, st, /*fuse_next=*/m->path == 1);
     }
     {
       ProfScope ps(m, 4, st);
-      launch_contour2_tc(m->c1.p, m->cw, contour, m->chl.p, cstride, nb, st);
+      if (m->path == 1)  // c1 holds the five time-tap planes of the fused conv2
+        launch_contour_tapsum(m->c1.p, m->cw, contour, m->chl.p, cstride, nb, st);
+      else
+        launch_contour2_tc(m->c1.p, m->cw, contour, m->chl.p, cstride, nb, st);
     }
     {
       ProfScope ps(m, 1, st);
@@ -492,6 +495,9 @@ int bp_model_create(const void* blob, size_t nbytes, int device, bp_model_t** ou
   tc_setup();
   cqt_tc_setup();
   m->n_sms = prop.multiProcessorCount;
+  // largest chunk whose 128-row M-tiles (175 rows per window in the note layer, 174 in the others) make at most two
+  // per SM: 216 windows on 148 SMs (217 would leave one M-tile for a third, almost empty wave of the note layer)
+  m->chunk = std::max(1, 2 * m->n_sms * 128 / tc_note_spec().rows_per_window);
   rc = derive(m, m->stream);
   if (rc) return rc;
   CK(cudaStreamSynchronize(m->stream));
@@ -549,7 +555,9 @@ int bp_model_refresh(bp_model_t* m) {
 
 int bp_model_set_path(bp_model_t* m, int path) {
   if (!m) return fail(BP_E_INVALID, "bp_model_set_path: null model");
-  if (path != 0 && path != 1) return fail(BP_E_INVALID, "bp_model_set_path: path must be 0 (FP32 FFMA) or 1 (tcgen05 contour conv)");
+  if (path < 0 || path > 2)
+    return fail(BP_E_INVALID, "bp_model_set_path: path must be 0 (FP32 FFMA), 1 (tcgen05, fused epilogues) or 2 (tcgen05, "
+                              "contour activations kept)");
   m->path = path;
   return BP_OK;
 }
@@ -978,12 +986,15 @@ int bp_debug_activation(bp_model_t* m, int which, float* h_out, int64_t n_window
     case 3: src = m->o1.p; per = (size_t)32 * kFrames * kPitches; break;
     default: return fail(BP_E_INVALID, "bp_debug_activation: unknown activation id");
   }
-  if (m->last_path == 1 && which >= 2)
-    return fail(BP_E_INVALID, "bp_debug_activation: the tensor-core path never materialises the 32-channel activations "
+  if (m->last_path >= 1 && which >= 2)
+    return fail(BP_E_INVALID, "bp_debug_activation: the tensor-core paths never materialise the 32-channel activations "
                               "(use bp_model_set_path(m, 0))");
+  if (m->last_path == 1 && which == 1)
+    return fail(BP_E_INVALID, "bp_debug_activation: path 1 reduces the contour activations in the epilogue "
+                              "(use bp_model_set_path(m, 2) or 0)");
   CK(cudaDeviceSynchronize());
   CK(cudaMemcpy(h_out, src, sizeof(float) * per * n_windows, cudaMemcpyDeviceToHost));
-  if (which == 1 && m->last_path == 1) {  // the tensor-core path keeps this activation channels-last: return NCHW
+  if (which == 1 && m->last_path == 2) {  // the tensor-core path keeps this activation channels-last: return NCHW
     std::vector<float> tmp(h_out, h_out + per * n_windows);
     for (int64_t b = 0; b < n_windows; ++b)
       for (int t = 0; t < kFrames; ++t)

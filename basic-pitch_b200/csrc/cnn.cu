@@ -355,6 +355,70 @@ __global__ void __launch_bounds__(256) tap_sum_kernel(const float* __restrict__ 
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Contour conv2 after the fused epilogue of the tensor-core contour conv (tc_conv.cu: contour_reduce_store):
+//   contour[t][f] = sigmoid(bias + sum_dt sum_{tiles ft', j: 16 ft' + j - 2 = f} Q[ft'][dt][j][t + dt - 2])
+// Every output bin has one term from its own 16-bin tile (j = f % 16 + 2) and, in the two outer bins on either side
+// of a tile, one from the neighbour's halo columns (j = 18, 19 / 0, 1).  Q is time-fastest; a CTA computes a
+// 32 (t) x 32 (f) tile with t on the lanes, transposes through shared memory, stores the posteriorgram and its bf16
+// hi/lo split in the row layout of the note conv's tensor-core kernel.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) contour_tapsum_kernel(const float* __restrict__ Q, const float* __restrict__ bias,
+                                                             float* __restrict__ out, SplitOut so) {
+  __shared__ float tile[32][33];
+  constexpr int kTiles = 17, kJ = 20;
+  const int b = blockIdx.z;
+  const int t0 = blockIdx.x * 32, f0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const float* Qb = Q + (size_t)b * kTiles * 5 * kJ * kFrames;
+  const float bv = __ldg(bias);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int fl = ty + 8 * i;
+    const int f = f0 + fl, t = t0 + tx;
+    float acc = bv;
+    if (f < kContourBins && t < kFrames) {
+      const int ft = f >> 4, r = f & 15;
+      const int ft2 = (r < 2) ? ft - 1 : ((r >= 14) ? ft + 1 : -1);  // neighbour whose halo covers this bin
+      const int j2 = (r < 2) ? r + 18 : r - 14;
+      const bool has2 = ft2 >= 0 && ft2 < kTiles;
+#pragma unroll
+      for (int dt = 0; dt < 5; ++dt) {
+        const int tt = t + dt - 2;
+        if ((unsigned)tt >= (unsigned)kFrames) continue;
+        acc += __ldg(Qb + ((size_t)(ft * 5 + dt) * kJ + r + 2) * kFrames + tt);
+        if (has2) acc += __ldg(Qb + ((size_t)(ft2 * 5 + dt) * kJ + j2) * kFrames + tt);
+      }
+    }
+    tile[fl][tx] = 1.f / (1.f + expf(-acc));
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int tl = ty + 8 * i;
+    const int t = t0 + tl, f = f0 + tx;
+    if (t < kFrames && f < kContourBins) out[((size_t)b * kFrames + t) * kContourBins + f] = tile[tx][tl];
+  }
+  if (so.planes && threadIdx.x < 128) {  // 32 frames x 4 chunks of 8 bins -> one 16-byte store per plane
+    const int tl = threadIdx.x & 31, c = threadIdx.x >> 5;
+    const int t = t0 + tl, f = f0 + 8 * c;
+    if (t < kFrames && f < kContourBins) {
+      __align__(16) __nv_bfloat16 hi[8], lo[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float o = tile[8 * c + j][tl];
+        hi[j] = __float2bfloat16_rn(o);
+        lo[j] = __float2bfloat16_rn(o - __bfloat162float(hi[j]));
+      }
+      const size_t d = (size_t)so.lead + (size_t)b * so.rows_per_window + t;
+      const size_t off = ((size_t)(f >> 3) * so.rows_total + d) * 8;
+      const size_t plane = (size_t)so.chunks8 * so.rows_total * 8;
+      *reinterpret_cast<uint4*>(so.planes + off) = *reinterpret_cast<const uint4*>(hi);
+      *reinterpret_cast<uint4*>(so.planes + plane + off) = *reinterpret_cast<const uint4*>(lo);
+    }
+  }
+}
+
 //                           CIN CIC KH KW PT PL WOUT TR
 using Contour2Cfg1 = Conv1Cfg<8, 4, 5, 5, 2, 2, 264, 11>;
 using Contour2CfgN = Conv1Cfg<8, 4, 5, 5, 2, 2, 264, 11>;  // channels-last input, two passes of 4 channels
@@ -409,6 +473,12 @@ void launch_contour2_tc(const float* c1, const CnnWeights& w, float* contour, __
   const TcConvSpec sp = tc_note_spec();
   launch1<Contour2CfgN>(NhwcIn<8, 264>{c1}, w.contour2_wT, w.contour2_b, contour, n, st,
                         SplitOut{chl, rows_total, sp.chunks8, sp.rows_per_window, sp.lead_rows});
+}
+void launch_contour_tapsum(const float* q, const CnnWeights& w, float* contour, __nv_bfloat16* chl, int rows_total, int n,
+                           cudaStream_t st) {
+  const TcConvSpec sp = tc_note_spec();
+  contour_tapsum_kernel<<<dim3((kFrames + 31) / 32, (kContourBins + 31) / 32, n), 256, 0, st>>>(
+      q, w.contour2_b, contour, SplitOut{chl, rows_total, sp.chunks8, sp.rows_per_window, sp.lead_rows});
 }
 void launch_note_tapsum(const float* p21, const CnnWeights& w, float* note, int n, cudaStream_t st) {
   tap_sum_kernel<7, 3, 3, 1, false><<<dim3((kFrames + 31) / 32, (kPitches + 31) / 32, n), 256, 0, st>>>(

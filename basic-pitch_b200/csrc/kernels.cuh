@@ -67,15 +67,19 @@ struct TcConvDev {
 };
 int tc_upload_program(int layer, const TcConvPlan& plan, cudaStream_t st);  // 0 on success
 void tc_upload_epilogue(const float* contour1_b, const float* onset1_b, const float* note1_b, const float* onset2_w,
-                        const float* note2_w, cudaStream_t st);
+                        const float* note2_w, const float* contour2_w, cudaStream_t st);
 int tc_rows_total(int n_windows, int rows_per_window);
 void tc_setup();
 void launch_split(const float* src, __nv_bfloat16* dst, const TcConvSpec& spec, int n_windows, int rows_stride,
                   cudaStream_t st);
 // rows_stride: row stride of the split layout (>= tc_rows_total(n_windows, ...)); fixed per model so that rows the
 // kernels never write (separators, pads) keep their zeros across batches of different size
+// fuse_next (contour layer only): reduce the output against the following conv in the epilogue (tap planes Q, see
+// contour_tapsum_kernel) instead of storing the channels-last activations
 void launch_conv_tc(const __nv_bfloat16* data, const TcConvDev& dev, float* out, int n_windows, int rows_stride, int n_sms,
-                    cudaStream_t st);
+                    cudaStream_t st, bool fuse_next = false);
+void launch_contour_tapsum(const float* q, const CnnWeights& w, float* contour, __nv_bfloat16* chl, int rows_total,
+                           int n_windows, cudaStream_t st);
 // contour conv2 on the channels-last output of the tensor-core contour conv; also emits the bf16 hi/lo split of the
 // contour posteriorgram in the layout of tc_note_spec()
 void launch_contour2_tc(const float* c1_nhwc, const CnnWeights& w, float* contour, __nv_bfloat16* chl, int rows_total,

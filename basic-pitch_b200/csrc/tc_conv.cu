@@ -41,6 +41,9 @@
 //               the fused 32 -> taps reduction with planar float4 stores (onset, note)
 #include <cuda_bf16.h>
 
+#include <algorithm>
+#include <cstring>
+#include <unordered_map>
 #include <vector>
 
 #include "kernels.cuh"
@@ -96,43 +99,43 @@ void TcConvPlan::build(const TcConvSpec& sp, const float* W /* [COUT][n_ci][KH][
   const int n_ft = (sp.WOUT + sp.FLT - 1) / sp.FLT;
   const int data_rows = kMTile + sp.KH - 1;
   const int lbo16 = data_rows;  // (rows * 16 B) >> 4
-  // frequency tiles d apart share weight tiles when SF*FLT*d is a multiple of 16 bins
+  // K = 16 steps start on 8-bin chunk boundaries (the k-chunk-major layout makes any chunk index a legal
+  // descriptor start), so frequency tiles d apart share weight tiles when SF*FLT*d is a multiple of 8 bins
   int stride = 1;
-  while ((sp.SF * sp.FLT * stride) % 16 != 0) ++stride;
+  while ((sp.SF * sp.FLT * stride) % 8 != 0) ++stride;
 
-  struct Key {
-    int ci, dt, off, variant;
-  };
-  std::vector<Key> keys;
-  auto find_or_add = [&](Key k) -> int {
-    for (size_t i = 0; i < keys.size(); ++i)
-      if (keys[i].ci == k.ci && keys[i].dt == k.dt && keys[i].off == k.off && keys[i].variant == k.variant) return (int)i;
-    keys.push_back(k);
-    const int s = sp.shifts[k.ci];
-    const size_t base = tiles.size();
-    tiles.resize(base + kTileBytes / 2, 0);
-    for (int kk = 0; kk < 16; ++kk) {
+  // weight tiles are de-duplicated by content (boundary clipping makes otherwise equal keys differ and vice versa)
+  std::unordered_map<uint64_t, std::vector<int>> by_hash;
+  int n_keys = 0;
+  std::vector<uint16_t> scratch(kTileBytes / 2);
+  // tile for input channel ci, time tap dt, relative offset off = (first bin of the step) - SF*FLT*ft; rows kk outside
+  // [clip_lo, clip_hi) are zero (bins outside the stacked image or owned by the neighbouring step)
+  auto find_or_add = [&](int ci, int dt, int off, int clip_lo, int clip_hi) -> int {
+    const int s = sp.shifts[ci];
+    bool any = false;
+    std::fill(scratch.begin(), scratch.end(), (uint16_t)0);
+    for (int kk = clip_lo; kk < clip_hi; ++kk) {
       for (int n = 0; n < 128; ++n) {
         const int fl = n / sp.COUT, co = n % sp.COUT;
-        const int df = k.off + kk - s - sp.SF * fl + sp.PL;
-        float w = 0.f;
-        if (df >= 0 && df < sp.KW) {
-          bool keep = true;
-          if (k.variant == 1) {  // chunk straddles g = 0: bins u < s lie outside the stacked image
-            keep = (16 * (s / 16) + kk - s) >= 0;
-          } else if (k.variant == 2) {  // chunk straddles g = 264
-            keep = (16 * ((kContourBins + s) / 16) + kk - s) < kContourBins;
-          }
-          if (keep) w = W[((co * sp.n_ci + k.ci) * sp.KH + k.dt) * sp.KW + df];
-        }
+        const int df = off + kk - s - sp.SF * fl + sp.PL;
+        if (df < 0 || df >= sp.KW) continue;
+        const float w = W[((co * sp.n_ci + ci) * sp.KH + dt) * sp.KW + df];
         const uint16_t hi = f2bf(w);
         const uint16_t lo = f2bf(w - bf2f(hi));
         const size_t o = (size_t)(kk >> 3) * 128 * 8 + (size_t)n * 8 + (kk & 7);
-        tiles[base + o] = hi;
-        tiles[base + 2048 + o] = lo;
+        scratch[o] = hi;
+        scratch[2048 + o] = lo;
+        any = true;
       }
     }
-    return (int)keys.size() - 1;
+    if (!any) return -1;
+    uint64_t h = 1469598103934665603ull;
+    for (uint16_t v : scratch) h = (h ^ v) * 1099511628211ull;
+    for (int id : by_hash[h])
+      if (std::memcmp(tiles.data() + (size_t)id * (kTileBytes / 2), scratch.data(), kTileBytes) == 0) return id;
+    tiles.insert(tiles.end(), scratch.begin(), scratch.end());
+    by_hash[h].push_back(n_keys);
+    return n_keys++;
   };
 
   // groups: pairs {ft, ft + stride} (or singles)
@@ -151,50 +154,53 @@ void TcConvPlan::build(const TcConvSpec& sp, const float* W /* [COUT][n_ci][KH][
     group_ft.push_back(ft_a);
     group_ft.push_back(ft_b);
     struct Use {
-      int tile, slot, q, dt;
+      int tile, slot, c8, dt, off;
     };
     std::vector<Use> uses;
     for (int ci = 0; ci < sp.n_ci; ++ci) {
       const int s = sp.shifts[ci];
       for (int dt = 0; dt < sp.KH; ++dt) {
-        for (int off = -160; off <= 480; ++off) {
-          for (int variant = 0; variant < 3; ++variant) {
-            for (int slot = 0; slot < 2; ++slot) {
-              const int ft = fts[slot];
-              if (ft < 0) continue;
-              const int num = off + sp.SF * sp.FLT * ft;
-              if (num < 0 || num % 16 != 0) continue;
-              const int q = num / 16;
-              if (q >= sp.chunks8 / 2) continue;
-              bool any = false;
-              for (int kk = 0; kk < 16 && !any; ++kk)
-                for (int fl = 0; fl < sp.FLT && !any; ++fl) {
-                  const int u = 16 * q + kk, f = ft * sp.FLT + fl, gg = u - s;
-                  const int df = gg - sp.SF * f + sp.PL;
-                  if (df >= 0 && df < sp.KW && gg >= 0 && gg < kContourBins && u < sp.data_bins && f < sp.WOUT) any = true;
-                }
-              if (!any) continue;
-              int need = 0;
-              if (s > 0 && s % 16 != 0 && q == s / 16) need = 1;
-              if (kContourBins + s < sp.chunks8 * 8 && (kContourBins + s) % 16 != 0 && q == (kContourBins + s) / 16) need = 2;
-              if (need != variant) continue;
-              uses.push_back(Use{find_or_add(Key{ci, dt, off, variant}), slot, q, dt});
+        std::vector<Use> cand;
+        for (int slot = 0; slot < 2; ++slot) {
+          const int ft = fts[slot];
+          if (ft < 0) continue;
+          // data bins u = g + s this frequency tile reads through channel ci (g inside the stacked image)
+          int lo = 1 << 30, hi = -1;
+          for (int fl = 0; fl < sp.FLT; ++fl) {
+            const int f = ft * sp.FLT + fl;
+            if (f >= sp.WOUT) continue;
+            for (int df = 0; df < sp.KW; ++df) {
+              const int gg = sp.SF * f - sp.PL + df, u = gg + s;
+              if (gg < 0 || gg >= kContourBins || u < 0 || u >= sp.data_bins) continue;
+              lo = std::min(lo, u);
+              hi = std::max(hi, u + 1);
             }
           }
+          for (int c8 = lo >= hi ? sp.chunks8 : lo / 8; 8 * c8 < hi; c8 += 2) {
+            const int c = std::min(c8, sp.chunks8 - 2);  // both k-chunks of the step must exist in the data tile
+            const int v_lo = std::max(8 * c8, s);  // bins below 8*c8 belong to the previous step
+            const int v_hi = std::min(8 * c + 16, s + kContourBins);
+            const int off = 8 * c - sp.SF * sp.FLT * ft;
+            const int tile = find_or_add(ci, dt, off, std::max(0, v_lo - 8 * c), std::min(16, v_hi - 8 * c));
+            if (tile >= 0) cand.push_back(Use{tile, slot, c, dt, off});
+          }
         }
+        std::stable_sort(cand.begin(), cand.end(), [](const Use& a, const Use& b) {
+          return a.off != b.off ? a.off < b.off : (a.tile != b.tile ? a.tile < b.tile : a.slot < b.slot);
+        });
+        uses.insert(uses.end(), cand.begin(), cand.end());
       }
     }
     bool seen[2] = {false, false};
     size_t i = 0;
     while (i < uses.size()) {
       size_t j = i;
-      while (j < uses.size() && uses[j].tile == uses[i].tile) ++j;
+      while (j < uses.size() && uses[j].tile == uses[i].tile && (j == i || uses[j].slot != uses[j - 1].slot)) ++j;
       tile_seq.push_back(uses[i].tile);
       uint32_t w[2] = {kNoUse, kNoUse};
       for (size_t u = i; u < j; ++u) {
         const int sl = uses[u].slot;
-        // a (tile, frequency tile) pair determines the chunk q, so a slot uses a tile at most once
-        w[sl] = (uint32_t)(2 * uses[u].q * lbo16 + uses[u].dt);
+        w[sl] = (uint32_t)(uses[u].c8 * lbo16 + uses[u].dt);  // A start offset >> 4: chunk c8, row dt
         if (!seen[sl]) w[sl] |= kUseFirstAcc;
         seen[sl] = true;
         ++n_uses;
@@ -205,7 +211,7 @@ void TcConvPlan::build(const TcConvSpec& sp, const float* W /* [COUT][n_ci][KH][
     }
     group_step_off.push_back((int)tile_seq.size());
   }
-  n_tiles = (int)keys.size();
+  n_tiles = n_keys;
   n_groups = (int)group_ft.size() / 2;
 }
 
@@ -220,9 +226,10 @@ __constant__ int c_group_ft[3][2 * tc::kMaxGroups];
 __constant__ float c_bias1[3][32];
 __constant__ float c_red_onset[32][9];
 __constant__ float c_red_note[32][21];
+__constant__ float c_red_contour[5][8][5];  // contour conv2 [dt][channel][df]
 
 void tc_upload_epilogue(const float* contour1_b, const float* onset1_b, const float* note1_b, const float* onset2_w,
-                        const float* note2_w, cudaStream_t st) {
+                        const float* note2_w, const float* contour2_w, cudaStream_t st) {
   float b[3][32] = {};
   for (int i = 0; i < 8; ++i) b[0][i] = contour1_b[i];
   for (int i = 0; i < 32; ++i) b[1][i] = onset1_b[i], b[2][i] = note1_b[i];
@@ -231,6 +238,11 @@ void tc_upload_epilogue(const float* contour1_b, const float* onset1_b, const fl
     for (int t = 0; t < 9; ++t) ro[c][t] = onset2_w[(1 + c) * 9 + t];  // channel 0 of onset conv2 is the note input
     for (int t = 0; t < 21; ++t) rn[c][t] = note2_w[c * 21 + t];
   }
+  float rc[5][8][5];
+  for (int c = 0; c < 8; ++c)
+    for (int dt = 0; dt < 5; ++dt)
+      for (int df = 0; df < 5; ++df) rc[dt][c][df] = contour2_w[(c * 5 + dt) * 5 + df];  // [1][8][5][5]
+  cudaMemcpyToSymbolAsync(c_red_contour, rc, sizeof(rc), 0, cudaMemcpyHostToDevice, st);
   cudaMemcpyToSymbolAsync(c_bias1, b, sizeof(b), 0, cudaMemcpyHostToDevice, st);
   cudaMemcpyToSymbolAsync(c_red_onset, ro, sizeof(ro), 0, cudaMemcpyHostToDevice, st);
   cudaMemcpyToSymbolAsync(c_red_note, rn, sizeof(rn), 0, cudaMemcpyHostToDevice, st);
@@ -329,6 +341,70 @@ __device__ __forceinline__ void reduce_store(uint32_t taddr, const float (&red)[
     if (live) {
 #pragma unroll
       for (int tp = 0; tp < TN; ++tp) dst[((size_t)(T0 + tp) * kPitches + fl) * kFrames] = acc[tp];
+    }
+  }
+}
+
+// Fused contour conv2 (8 -> 1 channels, 5 x 5 taps, models.py:252-259) in the contour epilogue.  A tile holds 16 bins
+// x 8 channels of relu(conv1) for one frame per thread; the channel and frequency taps are reduced in the thread,
+//   Q[dt][j][t] = sum_{c, df} relu(conv1)[c][t][16 ft + j - df] * w2[c][dt][df]      j = 0 .. 19  (bins 16 ft - 2 + j),
+// and the five time taps are summed by contour_tapsum_kernel (cnn.cu), which also adds the four halo columns of the
+// neighbouring tiles.  Q is time-fastest ([B][17 tiles][5][20][172]), so every store is a contiguous 128-byte run,
+// and 19 % smaller than the channels-last activations it replaces; the 8-channel image never reaches HBM.
+// Pass 0 applies bias + ReLU (and zeroes the bins >= 264 of the last tile) in place in TMEM; the dt loop is not
+// unrolled, so only the 40 weights of one time tap are live.
+__device__ __forceinline__ void contour_quad(const uint32_t (&v)[32], const float (&w)[8][5], float (&acc)[20], int c4) {
+#pragma unroll
+  for (int bl = 0; bl < 4; ++bl)
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const float o = __uint_as_float(v[bl * 8 + c]);
+#pragma unroll
+      for (int df = 0; df < 5; ++df) acc[4 * c4 + bl + (4 - df)] = fmaf(o, w[c][df], acc[4 * c4 + bl + (4 - df)]);
+    }
+}
+
+__device__ __forceinline__ void contour_reduce_store(uint32_t taddr, int n_valid /* live columns of the tile */,
+                                                     float* dst /* (b, ft, dt 0, j 0, t) */, bool live) {
+#pragma unroll 1
+  for (int c4 = 0; c4 < 4; ++c4) {
+    uint32_t v[32];
+    tmem_ld32_nowait(taddr + c4 * 32, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      const float o = fmaxf(__uint_as_float(v[i]) + c_bias1[0][i & 7], 0.f);
+      v[i] = (c4 * 32 + i < n_valid) ? __float_as_uint(o) : 0u;
+    }
+    tmem_st32(taddr + c4 * 32, v);
+  }
+  tmem_st_wait();
+#pragma unroll 1
+  for (int dt = 0; dt < 5; ++dt) {
+    float w[8][5];
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+#pragma unroll
+      for (int df = 0; df < 5; ++df) w[c][df] = c_red_contour[dt][c][df];
+    float acc[20];
+#pragma unroll
+    for (int j = 0; j < 20; ++j) acc[j] = 0.f;
+    uint32_t v0[32], v1[32];
+    tmem_ld32_nowait(taddr, v0);
+    tmem_ld_wait();
+    tmem_ld32_nowait(taddr + 32, v1);
+    contour_quad(v0, w, acc, 0);
+    tmem_ld_wait();
+    tmem_ld32_nowait(taddr + 64, v0);
+    contour_quad(v1, w, acc, 1);
+    tmem_ld_wait();
+    tmem_ld32_nowait(taddr + 96, v1);
+    contour_quad(v0, w, acc, 2);
+    tmem_ld_wait();
+    contour_quad(v1, w, acc, 3);
+    if (live) {
+#pragma unroll
+      for (int j = 0; j < 20; ++j) dst[(size_t)(dt * 20 + j) * kFrames] = acc[j];
     }
   }
 }
@@ -499,6 +575,10 @@ __global__ void __launch_bounds__(tc::kThreads, 1) conv_tc_kernel(const TcArgs a
                 }
               }
             }
+          } else if constexpr (EPI == 3) {
+            const int n_valid = min(a.flt, a.wout - ft * a.flt) * a.cout;
+            float* dst = a.out + ((size_t)b * 17 + ft) * (5 * 20 * kFrames) + t;
+            contour_reduce_store(taddr, n_valid, dst, live);
           } else {
             // onset / note: the tile is 4 bins x 32 channels; reduce the channels against the next conv's weights
             constexpr int TAPS = (EPI == 1) ? 9 : 21;
@@ -537,6 +617,7 @@ void tc_setup() {
   cudaFuncSetAttribute(conv_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes);
   cudaFuncSetAttribute(conv_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes);
   cudaFuncSetAttribute(conv_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes);
+  cudaFuncSetAttribute(conv_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes);
 }
 
 void launch_split(const float* src, __nv_bfloat16* dst, const TcConvSpec& sp, int n_windows, int rows_stride,
@@ -548,7 +629,7 @@ void launch_split(const float* src, __nv_bfloat16* dst, const TcConvSpec& sp, in
 }
 
 void launch_conv_tc(const __nv_bfloat16* data, const TcConvDev& dev, float* out, int n_windows, int rows_stride,
-                    int n_sms, cudaStream_t st) {
+                    int n_sms, cudaStream_t st, bool fuse_next) {
   const TcConvSpec& sp = dev.spec;
   TcArgs a;
   a.data = data;
@@ -559,10 +640,16 @@ void launch_conv_tc(const __nv_bfloat16* data, const TcConvDev& dev, float* out,
   a.n_mtiles = (tc_rows_total(n_windows, sp.rows_per_window) - 8) / tc::kMTile;
   a.n_windows = n_windows;
   a.n_groups = dev.n_groups;
-  // few M-tiles (small batches): split the frequency groups of an M-tile over several CTAs
+  // An item is (M-tile, one of `split` runs of frequency groups).  Pick the split that minimises the number of waves
+  // times the work per item, the data-tile load counted as half a group: full chunks run unsplit, partial chunks and
+  // small batches spread over all SMs.
   int split = 1;
-  if (a.n_mtiles < n_sms) split = (n_sms + a.n_mtiles - 1) / a.n_mtiles;
-  if (split > dev.n_groups) split = dev.n_groups;
+  double best = 1e30;
+  for (int s = 1; s <= dev.n_groups; ++s) {
+    const int waves = (a.n_mtiles * s + n_sms - 1) / n_sms;
+    const double cost = waves * ((dev.n_groups + s - 1) / s + 0.5);
+    if (cost < best - 1e-9) best = cost, split = s;
+  }
   a.n_split = split;
   a.data_rows = tc::kMTile + sp.KH - 1;
   a.row0 = sp.lead_rows - sp.PT;
@@ -573,7 +660,9 @@ void launch_conv_tc(const __nv_bfloat16* data, const TcConvDev& dev, float* out,
   a.wout = sp.WOUT;
   const int n_items = a.n_mtiles * a.n_split;
   const int grid = n_items < n_sms ? n_items : n_sms;
-  if (sp.epi == 0)
+  if (sp.epi == 0 && fuse_next)
+    conv_tc_kernel<3><<<grid, tc::kThreads, tc::kSmemBytes, st>>>(a);
+  else if (sp.epi == 0)
     conv_tc_kernel<0><<<grid, tc::kThreads, tc::kSmemBytes, st>>>(a);
   else if (sp.epi == 1)
     conv_tc_kernel<1><<<grid, tc::kThreads, tc::kSmemBytes, st>>>(a);

@@ -96,7 +96,8 @@ class Model:
         return self._h
 
     def set_path(self, path: int) -> None:
-        """0 = FP32 FFMA kernels everywhere (on-device accuracy reference), 1 = tcgen05 tensor-core contour conv (default)."""
+        """0 = FP32 FFMA kernels everywhere (on-device accuracy reference), 1 = tcgen05 tensor-core kernels with fused
+        epilogues (default), 2 = tcgen05 kernels keeping the 8-channel contour activations (for activation-level tests)."""
         self._lib.bp_model_set_path(self._h, int(path))
 
     @property

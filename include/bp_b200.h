@@ -151,12 +151,15 @@ int bp_transcribe_device(bp_model_t* m, const float* d_audio, const int64_t* h_s
  * Copies an internal activation of the most recent bp_forward_* call for window 0..n-1 to host.
  * which: 0 = CQT log-magnitude after normalisation+BN (n,172,309); 1 = contour conv1 output
  * (n,8,172,264); 2 = note conv1 output (n,32,172,88); 3 = onset conv1 output (n,32,172,88) — 2 and 3 exist only on
- * the FP32 path (bp_model_set_path(m, 0)): the tensor-core path reduces them in the epilogue and never stores them.
+ * the FP32 path (bp_model_set_path(m, 0)) and 1 on paths 0 and 2: the tensor-core kernels reduce these activations
+ * against the following convolution in their epilogues and never store them.
  * Only valid when the batch fitted in one internal chunk (n <= bp_model_chunk_windows). */
 int bp_debug_activation(bp_model_t* m, int which, float* h_out, int64_t n_windows);
 int64_t bp_model_chunk_windows(const bp_model_t* m);
-/* Selects the arithmetic path of the convolution stack: 0 = FP32 FFMA kernels, 1 = tensor-core
- * (tcgen05, split-bf16 operands, FP32 accumulate) for the contour and onset convolutions.  Default: 1. */
+/* Selects the arithmetic path: 0 = FP32 FFMA kernels everywhere; 1 = tensor-core kernels (tcgen05, split-bf16
+ * operands, FP32 accumulate) for the constant-Q projection and the three wide convolutions, each with the following
+ * single-output convolution reduced in its epilogue (default); 2 = as 1 but the contour convolution stores its
+ * 8-channel activations (bp_debug_activation which = 1). */
 int bp_model_set_path(bp_model_t* m, int path);
 
 /* Host-only (no GPU needed): builds the tensor-core plan (split-bf16 Toeplitz weight tiles and the per-group MMA

@@ -58,14 +58,27 @@ def test_forward_vs_oracle_including_activations(model, weights_np):
             assert np.abs(fp32[k] - ref[k]).max() < POST_TOL, f"FP32 path {k}"
     finally:
         model.set_path(1)
+    # tensor-core paths: 2 keeps the contour activations (channels-last), 1 (the default) reduces them against the
+    # next conv inside the epilogue.  The log-magnitude differs from the fp32 oracle mostly in bins near the 1e-10
+    # power floor (split-operand MMA accumulation order); what is held to 1e-4 below are the posteriorgrams
+    try:
+        model.set_path(2)
+        unfused = model.predict(x[:, :, None])
+        for which, key, shape, tol in ((0, "_y", (n, 172, 309), 1e-3), (1, "_c1", (n, 8, 172, 264), 2e-3)):
+            buf = np.empty(shape, np.float32)
+            lib.bp_debug_activation(model.handle, which, buf.ctypes.data, n)
+            err = np.abs(buf - ref[key]).max()
+            assert err < tol, f"activation {key}: max-abs {err:.3e}"
+        for k in ("note", "onset", "contour"):
+            assert np.abs(unfused[k] - ref[k]).max() < POST_TOL, f"tensor-core path 2, {k}"
+    finally:
+        model.set_path(1)
     got = model.predict(x[:, :, None])
-    for which, key, shape, tol in ((0, "_y", (n, 172, 309), 1e-3), (1, "_c1", (n, 8, 172, 264), 2e-3)):
-        # tensor-core path: the log-magnitude differs from the fp32 oracle mostly in bins near the 1e-10 power floor
-        # (split-operand MMA accumulation order); what is held to 1e-4 below are the posteriorgrams
-        buf = np.empty(shape, np.float32)
-        lib.bp_debug_activation(model.handle, which, buf.ctypes.data, n)
-        err = np.abs(buf - ref[key]).max()
-        assert err < tol, f"activation {key}: max-abs {err:.3e}"
+    buf = np.empty((n, 172, 309), np.float32)
+    lib.bp_debug_activation(model.handle, 0, buf.ctypes.data, n)
+    assert np.abs(buf - ref["_y"]).max() < 1e-3
+    with pytest.raises(Exception):  # path 1 never materialises the 8-channel image
+        lib.bp_debug_activation(model.handle, 1, np.empty((n, 8, 172, 264), np.float32).ctypes.data, n)
     for k in ("note", "onset", "contour"):
         assert got[k].shape == ref[k].shape and got[k].dtype == np.float32
         err = np.abs(got[k] - ref[k]).max()
@@ -87,18 +100,22 @@ def test_tensor_core_contour_conv_matches_fp32_path(model):
             c_ref = np.empty((min(n, 128), 8, 172, 264), np.float32)
             if n <= 128:
                 lib.bp_debug_activation(model.handle, 1, c_ref.ctypes.data, n)
-            model.set_path(1)
-            got = model.predict(x)
+            model.set_path(2)
+            got2 = model.predict(x)
             if n <= 128:
                 c_got = np.empty_like(c_ref)
                 lib.bp_debug_activation(model.handle, 1, c_got.ctypes.data, n)
                 err = np.abs(c_got - c_ref).max()
                 assert err < 5e-4, f"contour conv activation: max-abs {err:.3e} (n={n})"
+            model.set_path(1)
+            got = model.predict(x)
         finally:
             model.set_path(1)
         for k in ref:
             err = np.abs(got[k] - ref[k]).max()
-            assert err < 1e-4, f"{k}: tensor-core vs FP32 path max-abs {err:.3e} (n={n})"
+            assert err < 1e-4, f"{k}: tensor-core (fused) vs FP32 path max-abs {err:.3e} (n={n})"
+            err = np.abs(got2[k] - ref[k]).max()
+            assert err < 1e-4, f"{k}: tensor-core (unfused) vs FP32 path max-abs {err:.3e} (n={n})"
 
 
 def test_vocadito_golden_posteriorgrams(model, golden_dir, weights_np):

@@ -69,14 +69,13 @@ def test_tc_program_reproduces_convolution(weights_np, which):
                 used += 1
                 aoff16, first_acc = wd & 0x3FFF, (wd >> 15) & 1
                 assert wd >> 16 == 0
-                q2, dt = divmod(aoff16, lbo16)
-                assert q2 % 2 == 0 and dt < KH
-                q = q2 // 2
+                c8, dt = divmod(aoff16, lbo16)  # 8-bin chunk index of the step's first k-chunk, time tap
+                assert dt < KH and 8 * c8 + 16 <= 320
                 ft = int(gft[g, slot])
                 assert ft >= 0
                 assert bool(first_acc) == (slot not in first_seen)
                 first_seen.add(slot)
-                a = ypad[dt : dt + n_t, 16 * q : 16 * q + 16]
+                a = ypad[dt : dt + n_t, 8 * c8 : 8 * c8 + 16]
                 out[:, 128 * ft : 128 * ft + 128] += a @ t_full[tile_seq[step]]
         for slot in (0, 1):
             if gft[g, slot] >= 0:
@@ -96,4 +95,5 @@ def test_tc_program_statistics(weights_np):
         key = SPECS[which][0]
         tiles, tile_seq, slot_words, gso, gft, n_uses = _plan(which, weights_np[key])
         assert (tile_seq >= 0).all() and (tile_seq < len(tiles)).all()
+        print(which, "tiles", len(tiles), "steps", len(tile_seq), "uses", n_uses)
         assert len(tiles) < 700 and n_uses < 2200
