@@ -15,11 +15,12 @@
 // canonical K-major core-matrix layout) by four producer warps that also do the reflect padding and the hi/lo split.
 //
 // item = (M-tile of 128 frames, octave); per item 4 K-chunks of 64 taps, each chunk = 4 k-steps x 6 products:
-//   warps 0-7   producers: gather 128 x 64 samples (128-bit loads where aligned), split, st.shared into
+//   warps 4-11  producers: gather 128 x 64 samples (128-bit loads where aligned), split, st.shared into
 //               [plane][k/8][row][8] ; one lane bulk-copies the matching 30 KB slice of the split kernel matrix W
 //               (UBLKCP) ; fence.proxy.async ; mbarrier arrive
-//   warp 8      MMA issuer (one elected lane): 24 tcgen05.mma per chunk, tcgen05.commit frees the stage / publishes TMEM
-//   warps 9-12  epilogue: tcgen05.ld 80 columns, magnitude * sqrt(len), log-power, store, per-window min/max (atomics)
+//   warp 12     MMA issuer (one elected lane): 24 tcgen05.mma per chunk, tcgen05.commit frees the stage / publishes TMEM
+//   warps 0-3   epilogue: tcgen05.ld 80 columns, magnitude * sqrt(len), log-power, store, per-window min/max (atomics)
+// (the issue arbiter prefers high warp ids: the MMA issuer and the producers, which bound the kernel, outrank the epilogue)
 // Shared memory: 2 stages x (48 KB A + 30 KB W); TMEM: 2 accumulators of 128 x 80 (256 columns allocated).
 #include <cuda_bf16.h>
 
@@ -106,8 +107,9 @@ __global__ void __launch_bounds__(cq::kThreads, 1) cqt_tc_kernel(const CqtTcArgs
   uint64_t* tmem_empty = tmem_full + 2;       // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);  // broadcast: warp-uniform role branches and loop state
   const int lane = threadIdx.x & 31;
+  constexpr int kMmaWarp = 12;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) {
@@ -120,7 +122,7 @@ __global__ void __launch_bounds__(cq::kThreads, 1) cqt_tc_kernel(const CqtTcArgs
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 8) {
+  if (warp == kMmaWarp) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -132,10 +134,11 @@ __global__ void __launch_bounds__(cq::kThreads, 1) cqt_tc_kernel(const CqtTcArgs
   const int n_items = a.n_mtiles * kOctaves;
   const int total_frames = a.n_windows * kFrames;
 
-  if (warp < 8) {
+  if (warp >= 4 && warp < kMmaWarp) {
     // ------------------------------ producers: thread = (frame row, half of the k-chunks) ------------------------------
-    const int r = threadIdx.x & 127;
-    const int khalf = threadIdx.x >> 7;
+    const int ptid = threadIdx.x - 128;  // producer thread 0..255
+    const int r = ptid & 127;
+    const int khalf = ptid >> 7;
     uint32_t stage = 0, ph = 0;
     for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
       const int mt = it / kOctaves, o = it % kOctaves;
@@ -163,7 +166,7 @@ __global__ void __launch_bounds__(cq::kThreads, 1) cqt_tc_kernel(const CqtTcArgs
       for (int c = 0; c < kTaps / kKc; ++c) {
         mbar_wait(empty + stage, ph ^ 1);
         unsigned char* sa = smem + stage * kStageBytes;
-        if (threadIdx.x == 0) {
+        if (ptid == 0) {
           mbar_expect_tx_only(full + stage, 3 * kWPlane);  // the bulk copy of the W slice completes on the same barrier
           bulk_g2s(sa + 3 * kAPlane, a.wtc + (size_t)c * (3 * kWPlane / 2), 3 * kWPlane, full + stage);
         }
@@ -217,7 +220,7 @@ __global__ void __launch_bounds__(cq::kThreads, 1) cqt_tc_kernel(const CqtTcArgs
         }
       }
     }
-  } else if (warp == 8) {
+  } else if (warp == kMmaWarp) {
     // ------------------------------ MMA issuer ------------------------------
     constexpr uint32_t idesc = make_idesc(128, kN);  // kind::f16, bf16 x bf16 -> f32
     const uint32_t leader = elect_one() ? 1u : 0u;
@@ -262,7 +265,7 @@ __global__ void __launch_bounds__(cq::kThreads, 1) cqt_tc_kernel(const CqtTcArgs
       ++icount;
     }
   } else {
-    // ------------------------------ epilogue (warps 9..12) ------------------------------
+    // ------------------------------ epilogue (warps 0..3) ------------------------------
     const int quad = warp & 3;
     const int row = quad * 32 + lane;
     uint32_t ph_t[2] = {0, 0};
@@ -331,7 +334,7 @@ __global__ void __launch_bounds__(cq::kThreads, 1) cqt_tc_kernel(const CqtTcArgs
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) {
+  if (warp == kMmaWarp) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256));
   }
 }

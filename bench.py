@@ -29,7 +29,8 @@ if ROOT not in sys.path:
 CLIP_SECONDS = 10.0
 SR = 22050
 FLOP_PER_WINDOW = 1_048_159_296
-CONTOUR1_FLOP_PER_WINDOW = 680_030_208  # the dominant kernel (3x39 conv, 8->8 channels)
+CONTOUR1_FLOP_PER_WINDOW = 680_030_208  # the dominant kernel (3x39 conv, 8->8 channels) ...
+CONTOUR2_FLOP_PER_WINDOW = 18_163_200  # ... whose epilogue also does the MACs of the 5x5 8->1 conv (2 x 200 x 172 x 264)
 
 
 def make_clips(n_clips: int, seed0: int):
@@ -250,7 +251,7 @@ def main():
         peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if peaks else "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)"
         k_ms = tot.value / max(nint.value, 1)
         k_windows = nwin.value / max(nint.value, 1)
-        fam_flop = {0: CONTOUR1_FLOP_PER_WINDOW, 1: 193_740_800, 2: 57_065_472, 3: 22_359_552}.get(args.profile_kernel, 0)
+        fam_flop = {0: CONTOUR1_FLOP_PER_WINDOW + CONTOUR2_FLOP_PER_WINDOW, 1: 193_740_800, 2: 57_065_472, 3: 22_359_552}.get(args.profile_kernel, 0)
         achieved = fam_flop * k_windows / (k_ms * 1e-3) / 1e12 if k_ms > 0 else None
         threads = host_threads()
         cpu_v, cpu_desc = cpu_baseline_bounded(args.cpu_seconds, threads)
@@ -278,7 +279,7 @@ def main():
                     "api": "bp_transcribe_host (pinned host audio in, note events out)"},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"bound": "tensor", "kernel": {0: "contour conv 8->8 3x39 (conv_tc_kernel<0>, tcgen05 split-bf16)", 1: "onset conv 8->32 5x5/3 (conv_tc_kernel<1>)", 2: "cqt + lognorm", 3: "decimation chain"}.get(args.profile_kernel),
+            "roofline": {"bound": "tensor", "kernel": {0: "contour conv 8->8 3x39 + fused conv2 8->1 5x5 (conv_tc_kernel<3>, tcgen05 split-bf16)", 1: "onset conv 8->32 5x5/3 (conv_tc_kernel<1>)", 2: "cqt + lognorm", 3: "decimation chain"}.get(args.profile_kernel),
                          "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": (achieved / peak_tf) if achieved else None,
                          "traffic": traffic, "traffic_unit": "DRAM bytes per launch (ncu, profiles/roofline_traffic.json)",
                          "peak_source": peak_src, "avg_launch_ms": k_ms, "windows_per_launch": k_windows,
