@@ -169,7 +169,7 @@ struct bp_model {
   int64_t last_forward_n = 0;
   int last_path = 0;
   // optional per-kernel timing (bench.py roofline): CUDA events around one kernel family
-  int profile_which = -1;  // -1 off; 0 contour1, 1 onset1, 2 cqt, 3 decimate chain, 4 small convs
+  int profile_which = -1;  // -1 off; 0 contour1, 1 onset1, 2 cqt, 3 decimate chain, 4 small convs, 5 decode, 6 note finish
   std::vector<cudaEvent_t> prof_ev;
   size_t prof_used = 0;
   int64_t prof_windows = 0;
@@ -753,7 +753,10 @@ int bp_decode_device(bp_model_t* m, const float* d_note, const float* d_onset, c
     b.note_end = m->slot_end.p;
     b.note_pitch = m->slot_pitch.p;
     b.overflow = m->overflow.p;
-    launch_decode_notes(d_note, d_onset, b, n_files, total_frames, dp, st);
+    {
+      ProfScope ps(m, 5, st);
+      launch_decode_notes(d_note, d_onset, b, n_files, total_frames, dp, st);
+    }
     CKL();
     m->launches += total_frames > 0 ? 3 : 1;
     int overflow = 0;
@@ -806,8 +809,11 @@ int bp_decode_device(bp_model_t* m, const float* d_note, const float* d_onset, c
   if (with_bends && n_bends > 0 && !notes->bends) return fail(BP_E_INVALID, "bp_decode_device: bends array missing");
   CK(m->d_bends.reserve((size_t)n_bends + 1));
   CK(cudaMemcpyAsync(m->d_bend_off.p, notes->bend_off, sizeof(int) * (n_notes + 1), cudaMemcpyHostToDevice, st));
-  launch_note_finish(d_note, d_contour, m->d_note_base.p, m->d_start.p, m->d_end.p, m->d_pitch.p, m->d_amp.p,
-                     m->d_bend_off.p, m->d_bends.p, (int)n_notes, with_bends, m->d_gauss, st);
+  {
+    ProfScope ps(m, 6, st);
+    launch_note_finish(d_note, d_contour, m->d_note_base.p, m->d_start.p, m->d_end.p, m->d_pitch.p, m->d_amp.p,
+                       m->d_bend_off.p, m->d_bends.p, (int)n_notes, with_bends, m->d_gauss, st);
+  }
   CKL();
   m->launches += 1;
   CK(cudaMemcpyAsync(notes->amplitude, m->d_amp.p, sizeof(float) * n_notes, cudaMemcpyDeviceToHost, st));
@@ -949,7 +955,7 @@ int bp_debug_tc_plan(int which, const float* w, int32_t* sizes, uint16_t* tiles,
 
 int bp_model_profile(bp_model_t* m, int which) {
   if (!m) return fail(BP_E_INVALID, "bp_model_profile: null model");
-  if (which < -1 || which > 4) return fail(BP_E_INVALID, "bp_model_profile: unknown kernel family");
+  if (which < -1 || which > 6) return fail(BP_E_INVALID, "bp_model_profile: unknown kernel family");
   m->profile_which = which;
   m->prof_used = 0;
   m->prof_windows = 0;

@@ -227,24 +227,36 @@ __constant__ int c_group_step_off[3][tc::kMaxGroups + 1];
 __constant__ int c_group_ft[3][2 * tc::kMaxGroups];
 // epilogue constants: conv1 bias and the weights of the fused channel reduction (conv2), [channel][tap]
 __constant__ float c_bias1[3][32];
-__constant__ float c_red_onset[32][9];
-__constant__ float c_red_note[32][21];
-__constant__ float c_red_contour[5][8][5];  // contour conv2 [dt][channel][df]
+// (tap pairs for the packed FMAs: onset 9 taps -> 5 pairs, note 21 -> 11 pairs, the odd last one padded with 0)
+__constant__ float2 c_red_onset[32][5];
+__constant__ float2 c_red_note[32][11];
+// contour conv2 [dt][channel][6 pairs]: an input bin at even offset bl feeds the output pairs (bl,bl+1), (bl+2,bl+3),
+// (bl+4,bl+5) with weights (w4,w3), (w2,w1), (w0,0); at odd bl the pairs (bl-1,bl), (bl+1,bl+2), (bl+3,bl+4) with
+// (0,w4), (w3,w2), (w1,w0)   [output offset j = bl + 4 - df]
+__constant__ float2 c_red_contour[5][8][6];
 
 void tc_upload_epilogue(const float* contour1_b, const float* onset1_b, const float* note1_b, const float* onset2_w,
                         const float* note2_w, const float* contour2_w, cudaStream_t st) {
   float b[3][32] = {};
   for (int i = 0; i < 8; ++i) b[0][i] = contour1_b[i];
   for (int i = 0; i < 32; ++i) b[1][i] = onset1_b[i], b[2][i] = note1_b[i];
-  float ro[32][9], rn[32][21];
+  float2 ro[32][5], rn[32][11];
   for (int c = 0; c < 32; ++c) {
-    for (int t = 0; t < 9; ++t) ro[c][t] = onset2_w[(1 + c) * 9 + t];  // channel 0 of onset conv2 is the note input
-    for (int t = 0; t < 21; ++t) rn[c][t] = note2_w[c * 21 + t];
+    // channel 0 of onset conv2 is the note input (models.py:305: concat[note, onset1])
+    for (int t = 0; t < 10; ++t) (&ro[c][0].x)[t] = t < 9 ? onset2_w[(1 + c) * 9 + t] : 0.f;
+    for (int t = 0; t < 22; ++t) (&rn[c][0].x)[t] = t < 21 ? note2_w[c * 21 + t] : 0.f;
   }
-  float rc[5][8][5];
+  float2 rc[5][8][6];
   for (int c = 0; c < 8; ++c)
-    for (int dt = 0; dt < 5; ++dt)
-      for (int df = 0; df < 5; ++df) rc[dt][c][df] = contour2_w[(c * 5 + dt) * 5 + df];  // [1][8][5][5]
+    for (int dt = 0; dt < 5; ++dt) {
+      const float* w = contour2_w + (c * 5 + dt) * 5;  // [1][8][5][5], w[df]
+      rc[dt][c][0] = make_float2(w[4], w[3]);
+      rc[dt][c][1] = make_float2(w[2], w[1]);
+      rc[dt][c][2] = make_float2(w[0], 0.f);
+      rc[dt][c][3] = make_float2(0.f, w[4]);
+      rc[dt][c][4] = make_float2(w[3], w[2]);
+      rc[dt][c][5] = make_float2(w[1], w[0]);
+    }
   cudaMemcpyToSymbolAsync(c_red_contour, rc, sizeof(rc), 0, cudaMemcpyHostToDevice, st);
   cudaMemcpyToSymbolAsync(c_bias1, b, sizeof(b), 0, cudaMemcpyHostToDevice, st);
   cudaMemcpyToSymbolAsync(c_red_onset, ro, sizeof(ro), 0, cudaMemcpyHostToDevice, st);
@@ -321,29 +333,39 @@ struct TcArgs {
 // Fused channel reduction of the epilogue: for each of the 4 bins of the tile (one 32-column slab = 32 channels)
 //   P[tap][f][t] = sum_c relu(v[c] + bias[c]) * w2[c][tap]
 // The output is time-fastest ([B][taps][WOUT][172]): the 32 lanes of a warp hold 32 consecutive frames, so every store
-// instruction writes one contiguous 128-byte run.  Weights and bias are constant-bank immediates of the FMAs.
-// Taps [T0, T0+TN) are handled per call: with few taps the compiler keeps the whole weight block in registers across
-// the bin loop, so small layers are split in two calls to stay inside the register budget (TMEM re-reads are cheap).
-template <int LAYER, int TAPS, int T0, int TN>
-__device__ __forceinline__ void reduce_store(uint32_t taddr, const float (&red)[32][TAPS], float* dst /* (b, tap 0, f0, t) */,
-                                             bool live) {
+// instruction writes one contiguous 128-byte run.  Two taps per packed FMA; the weight pairs are uniform-register
+// operands loaded from constant memory at static offsets (LDCU.128), so no weight lives in a vector register.
+template <int LAYER, int TAPS>
+__device__ __forceinline__ void reduce_store(uint32_t taddr, const float2 (&red)[32][(TAPS + 1) / 2],
+                                             float* dst /* (b, tap 0, f0, t) */, bool live) {
+  constexpr int TP2 = (TAPS + 1) / 2;
+  // two bins per iteration: every weight pair fetched from constant memory (LDCU) feeds two packed FMAs
 #pragma unroll 1
-  for (int fl = 0; fl < 4; ++fl) {
-    uint32_t v[32];
-    tmem_ld32_nowait(taddr + fl * 32, v);
+  for (int fl = 0; fl < 4; fl += 2) {
+    uint32_t v0[32], v1[32];
+    tmem_ld32_nowait(taddr + fl * 32, v0);
+    tmem_ld32_nowait(taddr + fl * 32 + 32, v1);
     tmem_ld_wait();
-    float acc[TN];
+    float2 acc0[TP2], acc1[TP2];
 #pragma unroll
-    for (int tp = 0; tp < TN; ++tp) acc[tp] = 0.f;
+    for (int tp = 0; tp < TP2; ++tp) acc0[tp] = acc1[tp] = make_float2(0.f, 0.f);
 #pragma unroll
     for (int c = 0; c < 32; ++c) {
-      const float o = fmaxf(__uint_as_float(v[c]) + c_bias1[LAYER][c], 0.f);
+      const float o0 = fmaxf(__uint_as_float(v0[c]) + c_bias1[LAYER][c], 0.f);
+      const float o1 = fmaxf(__uint_as_float(v1[c]) + c_bias1[LAYER][c], 0.f);
 #pragma unroll
-      for (int tp = 0; tp < TN; ++tp) acc[tp] = fmaf(o, red[c][T0 + tp], acc[tp]);
+      for (int tp = 0; tp < TP2; ++tp) {
+        const float2 w = red[c][tp];
+        ffma2(acc0[tp], o0, w);
+        ffma2(acc1[tp], o1, w);
+      }
     }
     if (live) {
 #pragma unroll
-      for (int tp = 0; tp < TN; ++tp) dst[((size_t)(T0 + tp) * kPitches + fl) * kFrames] = acc[tp];
+      for (int tp = 0; tp < TAPS; ++tp) {
+        dst[((size_t)tp * kPitches + fl) * kFrames] = (tp & 1) ? acc0[tp >> 1].y : acc0[tp >> 1].x;
+        dst[((size_t)tp * kPitches + fl + 1) * kFrames] = (tp & 1) ? acc1[tp >> 1].y : acc1[tp >> 1].x;
+      }
     }
   }
 }
@@ -356,14 +378,22 @@ __device__ __forceinline__ void reduce_store(uint32_t taddr, const float (&red)[
 // and 19 % smaller than the channels-last activations it replaces; the 8-channel image never reaches HBM.
 // Pass 0 applies bias + ReLU (and zeroes the bins >= 264 of the last tile) in place in TMEM; the dt loop is not
 // unrolled, so only the 40 weights of one time tap are live.
-__device__ __forceinline__ void contour_quad(const uint32_t (&v)[32], const float (&w)[8][5], float (&acc)[20], int c4) {
+__device__ __forceinline__ void contour_quad(const uint32_t (&v)[32], int dt, float2 (&acc)[10], int c4) {
 #pragma unroll
   for (int bl = 0; bl < 4; ++bl)
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
       const float o = __uint_as_float(v[bl * 8 + c]);
-#pragma unroll
-      for (int df = 0; df < 5; ++df) acc[4 * c4 + bl + (4 - df)] = fmaf(o, w[c][df], acc[4 * c4 + bl + (4 - df)]);
+      const int j2 = (4 * c4 + bl) >> 1;  // pair index of output offsets (2 j2, 2 j2 + 1)
+      if ((bl & 1) == 0) {
+        ffma2(acc[j2], o, c_red_contour[dt][c][0]);
+        ffma2(acc[j2 + 1], o, c_red_contour[dt][c][1]);
+        ffma2(acc[j2 + 2], o, c_red_contour[dt][c][2]);
+      } else {
+        ffma2(acc[j2], o, c_red_contour[dt][c][3]);
+        ffma2(acc[j2 + 1], o, c_red_contour[dt][c][4]);
+        ffma2(acc[j2 + 2], o, c_red_contour[dt][c][5]);
+      }
     }
 }
 
@@ -384,30 +414,25 @@ __device__ __forceinline__ void contour_reduce_store(uint32_t taddr, int n_valid
   tmem_st_wait();
 #pragma unroll 1
   for (int dt = 0; dt < 5; ++dt) {
-    float w[8][5];
+    float2 acc[10];  // output offsets j = 0 .. 19 as pairs
 #pragma unroll
-    for (int c = 0; c < 8; ++c)
-#pragma unroll
-      for (int df = 0; df < 5; ++df) w[c][df] = c_red_contour[dt][c][df];
-    float acc[20];
-#pragma unroll
-    for (int j = 0; j < 20; ++j) acc[j] = 0.f;
+    for (int j = 0; j < 10; ++j) acc[j] = make_float2(0.f, 0.f);
     uint32_t v0[32], v1[32];
     tmem_ld32_nowait(taddr, v0);
     tmem_ld_wait();
     tmem_ld32_nowait(taddr + 32, v1);
-    contour_quad(v0, w, acc, 0);
+    contour_quad(v0, dt, acc, 0);
     tmem_ld_wait();
     tmem_ld32_nowait(taddr + 64, v0);
-    contour_quad(v1, w, acc, 1);
+    contour_quad(v1, dt, acc, 1);
     tmem_ld_wait();
     tmem_ld32_nowait(taddr + 96, v1);
-    contour_quad(v0, w, acc, 2);
+    contour_quad(v0, dt, acc, 2);
     tmem_ld_wait();
-    contour_quad(v1, w, acc, 3);
+    contour_quad(v1, dt, acc, 3);
     if (live) {
 #pragma unroll
-      for (int j = 0; j < 20; ++j) dst[(size_t)(dt * 20 + j) * kFrames] = acc[j];
+      for (int j = 0; j < 20; ++j) dst[(size_t)(dt * 20 + j) * kFrames] = (j & 1) ? acc[j >> 1].y : acc[j >> 1].x;
     }
   }
 }
@@ -593,10 +618,9 @@ __global__ void __launch_bounds__(tc::kThreads, 1) conv_tc_kernel(const TcArgs a
             constexpr int TAPS = (EPI == 1) ? 9 : 21;
             float* dst = a.out + ((size_t)b * TAPS * kPitches + (size_t)ft * 4) * kFrames + t;
             if constexpr (EPI == 1) {
-              reduce_store<1, 9, 0, 4>(taddr, c_red_onset, dst, live);
-              reduce_store<1, 9, 4, 5>(taddr, c_red_onset, dst, live);
+              reduce_store<1, 9>(taddr, c_red_onset, dst, live);
             } else {
-              reduce_store<2, 21, 0, 21>(taddr, c_red_note, dst, live);
+              reduce_store<2, 21>(taddr, c_red_note, dst, live);
             }
           }
         }

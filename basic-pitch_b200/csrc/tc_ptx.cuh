@@ -127,6 +127,18 @@ __device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&v)[3
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// Packed FP32 FMA (FFMA2): d.{x,y} += o * w.{x,y}.  One issue slot for two FMAs; with the scalar broadcast in a register and
+// the weight pair in a uniform register (constant memory, static offset) the epilogue FMA streams need half the issue
+// slots of scalar FFMAs — what the fused epilogues compete for with the MMA-issuing warps.
+__device__ __forceinline__ void ffma2(float2& d, float o, float2 w) {
+  unsigned long long dd, oo, ww;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(dd) : "f"(d.x), "f"(d.y));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(oo) : "f"(o));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(ww) : "f"(w.x), "f"(w.y));
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(dd) : "l"(oo), "l"(ww));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(dd));
+}
+
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
   asm volatile(
       "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "

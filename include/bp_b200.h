@@ -172,7 +172,8 @@ int bp_debug_tc_plan(int which, const float* w, int32_t* sizes, uint16_t* tiles,
 
 /* Per-kernel device timing for the roofline line of bench.py: records CUDA events on the launching
  * stream around every launch of one kernel family (0 = contour conv 3x39, 1 = onset conv 5x5,
- * 2 = CQT projection + log-normalise, 3 = decimation chain, 4 = the remaining small convs;
+ * 2 = CQT projection + log-normalise, 3 = decimation chain, 4 = the remaining small convs,
+ * 5 = decode (prep / candidates / sequential loops), 6 = amplitudes + pitch bends;
  * -1 = off, the default) and resets the accumulators.  bp_model_profile_read synchronises the device
  * and returns the summed interval time, the number of intervals and the windows processed. */
 int bp_model_profile(bp_model_t* m, int which);
