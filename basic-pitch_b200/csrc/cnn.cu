@@ -310,37 +310,51 @@ __global__ void __launch_bounds__(Cfg::THREADS) conv1_kernel(In in, const float*
 }
 
 // ------------------------------------------------------------------------------------------------
-// Second convs of the note / onset branches after the tensor-core epilogue has reduced the 32 channels:
-//   out[t][f] = sigmoid(bias + sum_{dt,df} P[dt*KW+df][f+df-PL][t+dt-PT] (+ sum x[t+dt-PT][f+df-PL] * wx[dt*KW+df]))
-// P is time-fastest ([B][taps][88][172]); a CTA computes a 32 (t) x 32 (f) tile with t on the lanes (coalesced reads)
-// and transposes through shared memory for the frequency-fastest output.
+// The single-output second convolutions (contour conv2 models.py:254-262, note conv2 :282-290, onset conv2 :305-313)
+// after the fused epilogues of the tensor-core kernels (tc_conv.cu).  Those reduce channels and frequency taps inside
+// the thread that owns a frame and emit, per frequency tile of FLT bins, KH time-tap planes of J = FLT + 2*HALO output
+// offsets (J - FLT halo columns belong to the neighbouring tiles), time-fastest:  Q[B][tiles][KH][J][172].  Left here:
+//   out[t][f] = sigmoid(bias + sum_dt ( Q[ft][dt][r + HALO][t + dt - PT] + Q[neighbour][dt][r + HALO -/+ FLT][..] )
+//                       (+ sum_{dt,df} x[t + dt - PT][f + df - 1] * wx[dt*3 + df]   -- onset: the note input channel) )
+// with ft = f / FLT, r = f % FLT, the neighbour term only for the HALO outer bins on either side of a tile.
+// A CTA computes a 32 (t) x 32 (f) tile with t on the lanes (coalesced 128-byte reads), transposes through shared
+// memory for the frequency-fastest posteriorgram, and (contour) also stores the bf16 hi/lo split in the row layout of
+// the note conv's tensor-core kernel.
 // ------------------------------------------------------------------------------------------------
-template <int KH, int KW, int PT, int PL, bool EXTRA>
-__global__ void __launch_bounds__(256) tap_sum_kernel(const float* __restrict__ P, const float* __restrict__ x,
-                                                      const float* __restrict__ wx, const float* __restrict__ bias,
-                                                      float* __restrict__ out) {
+template <int FLT, int HALO, int KH, int PT, int WOUT, bool EXTRA, bool SPLIT>
+__global__ void __launch_bounds__(256) halo_tapsum_kernel(const float* __restrict__ Q, const float* __restrict__ x,
+                                                          const float* __restrict__ wx, const float* __restrict__ bias,
+                                                          float* __restrict__ out, SplitOut so) {
   __shared__ float tile[32][33];
+  constexpr int kTiles = (WOUT + FLT - 1) / FLT, kJ = FLT + 2 * HALO;
   const int b = blockIdx.z;
   const int t0 = blockIdx.x * 32, f0 = blockIdx.y * 32;
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 8 warps
-  const float* Pb = P + (size_t)b * KH * KW * kPitches * kFrames;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const float* Qb = Q + (size_t)b * kTiles * KH * kJ * kFrames;
   const float bv = __ldg(bias);
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int fl = ty + 8 * i;
     const int f = f0 + fl, t = t0 + tx;
     float acc = bv;
-    if (f < kPitches && t < kFrames) {
+    if (f < WOUT && t < kFrames) {
+      const int ft = f / FLT, r = f % FLT;
+      const int ft2 = (r < HALO) ? ft - 1 : ((r >= FLT - HALO) ? ft + 1 : -1);  // neighbour whose halo covers this bin
+      const int j2 = (r < HALO) ? r + HALO + FLT : r + HALO - FLT;
+      const bool has2 = ft2 >= 0 && ft2 < kTiles;
 #pragma unroll
       for (int dt = 0; dt < KH; ++dt) {
         const int tt = t + dt - PT;
         if ((unsigned)tt >= (unsigned)kFrames) continue;
+        acc += __ldg(Qb + ((size_t)(ft * KH + dt) * kJ + r + HALO) * kFrames + tt);
+        if (has2) acc += __ldg(Qb + ((size_t)(ft2 * KH + dt) * kJ + j2) * kFrames + tt);
+        if (EXTRA) {
 #pragma unroll
-        for (int df = 0; df < KW; ++df) {
-          const int ff = f + df - PL;
-          if ((unsigned)ff >= (unsigned)kPitches) continue;
-          acc += __ldg(Pb + ((size_t)(dt * KW + df) * kPitches + ff) * kFrames + tt);
-          if (EXTRA) acc = fmaf(__ldg(x + ((size_t)b * kFrames + tt) * kPitches + ff), __ldg(wx + dt * KW + df), acc);
+          for (int df = 0; df < 3; ++df) {
+            const int ff = f + df - 1;
+            if ((unsigned)ff < (unsigned)WOUT)
+              acc = fmaf(__ldg(x + ((size_t)b * kFrames + tt) * WOUT + ff), __ldg(wx + dt * 3 + df), acc);
+          }
         }
       }
     }
@@ -351,58 +365,12 @@ __global__ void __launch_bounds__(256) tap_sum_kernel(const float* __restrict__ 
   for (int i = 0; i < 4; ++i) {
     const int tl = ty + 8 * i;
     const int t = t0 + tl, f = f0 + tx;
-    if (t < kFrames && f < kPitches) out[((size_t)b * kFrames + t) * kPitches + f] = tile[tx][tl];
+    if (t < kFrames && f < WOUT) out[((size_t)b * kFrames + t) * WOUT + f] = tile[tx][tl];
   }
-}
-
-// ------------------------------------------------------------------------------------------------
-// Contour conv2 after the fused epilogue of the tensor-core contour conv (tc_conv.cu: contour_reduce_store):
-//   contour[t][f] = sigmoid(bias + sum_dt sum_{tiles ft', j: 16 ft' + j - 2 = f} Q[ft'][dt][j][t + dt - 2])
-// Every output bin has one term from its own 16-bin tile (j = f % 16 + 2) and, in the two outer bins on either side
-// of a tile, one from the neighbour's halo columns (j = 18, 19 / 0, 1).  Q is time-fastest; a CTA computes a
-// 32 (t) x 32 (f) tile with t on the lanes, transposes through shared memory, stores the posteriorgram and its bf16
-// hi/lo split in the row layout of the note conv's tensor-core kernel.
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) contour_tapsum_kernel(const float* __restrict__ Q, const float* __restrict__ bias,
-                                                             float* __restrict__ out, SplitOut so) {
-  __shared__ float tile[32][33];
-  constexpr int kTiles = 17, kJ = 20;
-  const int b = blockIdx.z;
-  const int t0 = blockIdx.x * 32, f0 = blockIdx.y * 32;
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const float* Qb = Q + (size_t)b * kTiles * 5 * kJ * kFrames;
-  const float bv = __ldg(bias);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int fl = ty + 8 * i;
-    const int f = f0 + fl, t = t0 + tx;
-    float acc = bv;
-    if (f < kContourBins && t < kFrames) {
-      const int ft = f >> 4, r = f & 15;
-      const int ft2 = (r < 2) ? ft - 1 : ((r >= 14) ? ft + 1 : -1);  // neighbour whose halo covers this bin
-      const int j2 = (r < 2) ? r + 18 : r - 14;
-      const bool has2 = ft2 >= 0 && ft2 < kTiles;
-#pragma unroll
-      for (int dt = 0; dt < 5; ++dt) {
-        const int tt = t + dt - 2;
-        if ((unsigned)tt >= (unsigned)kFrames) continue;
-        acc += __ldg(Qb + ((size_t)(ft * 5 + dt) * kJ + r + 2) * kFrames + tt);
-        if (has2) acc += __ldg(Qb + ((size_t)(ft2 * 5 + dt) * kJ + j2) * kFrames + tt);
-      }
-    }
-    tile[fl][tx] = 1.f / (1.f + expf(-acc));
-  }
-  __syncthreads();
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int tl = ty + 8 * i;
-    const int t = t0 + tl, f = f0 + tx;
-    if (t < kFrames && f < kContourBins) out[((size_t)b * kFrames + t) * kContourBins + f] = tile[tx][tl];
-  }
-  if (so.planes && threadIdx.x < 128) {  // 32 frames x 4 chunks of 8 bins -> one 16-byte store per plane
+  if (SPLIT && so.planes && threadIdx.x < 128) {  // 32 frames x 4 chunks of 8 bins -> one 16-byte store per plane
     const int tl = threadIdx.x & 31, c = threadIdx.x >> 5;
     const int t = t0 + tl, f = f0 + 8 * c;
-    if (t < kFrames && f < kContourBins) {
+    if (t < kFrames && f < WOUT) {
       __align__(16) __nv_bfloat16 hi[8], lo[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
@@ -477,17 +445,18 @@ void launch_contour2_tc(const float* c1, const CnnWeights& w, float* contour, __
 void launch_contour_tapsum(const float* q, const CnnWeights& w, float* contour, __nv_bfloat16* chl, int rows_total, int n,
                            cudaStream_t st) {
   const TcConvSpec sp = tc_note_spec();
-  contour_tapsum_kernel<<<dim3((kFrames + 31) / 32, (kContourBins + 31) / 32, n), 256, 0, st>>>(
-      q, w.contour2_b, contour, SplitOut{chl, rows_total, sp.chunks8, sp.rows_per_window, sp.lead_rows});
+  halo_tapsum_kernel<16, 2, 5, 2, kContourBins, false, true>
+      <<<dim3((kFrames + 31) / 32, (kContourBins + 31) / 32, n), 256, 0, st>>>(
+          q, nullptr, nullptr, w.contour2_b, contour, SplitOut{chl, rows_total, sp.chunks8, sp.rows_per_window, sp.lead_rows});
 }
-void launch_note_tapsum(const float* p21, const CnnWeights& w, float* note, int n, cudaStream_t st) {
-  tap_sum_kernel<7, 3, 3, 1, false><<<dim3((kFrames + 31) / 32, (kPitches + 31) / 32, n), 256, 0, st>>>(
-      p21, nullptr, nullptr, w.note2_b, note);
+void launch_note_tapsum(const float* q, const CnnWeights& w, float* note, int n, cudaStream_t st) {
+  halo_tapsum_kernel<4, 1, 7, 3, kPitches, false, false><<<dim3((kFrames + 31) / 32, (kPitches + 31) / 32, n), 256, 0, st>>>(
+      q, nullptr, nullptr, w.note2_b, note, SplitOut{nullptr, 0, 0, 0, 0});
 }
-void launch_onset_tapsum(const float* p9, const float* note, const CnnWeights& w, float* onset, int n, cudaStream_t st) {
+void launch_onset_tapsum(const float* q, const float* note, const CnnWeights& w, float* onset, int n, cudaStream_t st) {
   // channel 0 of the onset conv2 weights multiplies the note posteriorgram (models.py:305: concat[note, onset1])
-  tap_sum_kernel<3, 3, 1, 1, true><<<dim3((kFrames + 31) / 32, (kPitches + 31) / 32, n), 256, 0, st>>>(
-      p9, note, w.onset2_wT, w.onset2_b, onset);
+  halo_tapsum_kernel<4, 1, 3, 1, kPitches, true, false><<<dim3((kFrames + 31) / 32, (kPitches + 31) / 32, n), 256, 0, st>>>(
+      q, note, w.onset2_wT, w.onset2_b, onset, SplitOut{nullptr, 0, 0, 0, 0});
 }
 void launch_note1(const float* contour, const CnnWeights& w, float* n1, int n, cudaStream_t st) {
   launch<Note1Cfg>(PlanarIn<1, 264>{contour}, w.note1_wT, w.note1_b, n1, n, st);

@@ -75,7 +75,7 @@ void launch_split(const float* src, __nv_bfloat16* dst, const TcConvSpec& spec, 
 // rows_stride: row stride of the split layout (>= tc_rows_total(n_windows, ...)); fixed per model so that rows the
 // kernels never write (separators, pads) keep their zeros across batches of different size
 // fuse_next (contour layer only): reduce the output against the following conv in the epilogue (tap planes Q, see
-// contour_tapsum_kernel) instead of storing the channels-last activations
+// halo_tapsum_kernel) instead of storing the channels-last activations
 void launch_conv_tc(const __nv_bfloat16* data, const TcConvDev& dev, float* out, int n_windows, int rows_stride, int n_sms,
                     cudaStream_t st, bool fuse_next = false);
 void launch_contour_tapsum(const float* q, const CnnWeights& w, float* contour, __nv_bfloat16* chl, int rows_total,

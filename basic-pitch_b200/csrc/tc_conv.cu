@@ -10,7 +10,7 @@
 // One kernel template, three specs (TcConvSpec).  For the two 32-channel layers the epilogue also applies the
 // channel reduction of the following single-output conv (onset conv2 models.py:305-313, note conv2 :282-290):
 // it emits P[tap][t][f] = sum_c relu(conv1)[c][t][f] * w2[c][tap], so the 32-channel activations never reach
-// HBM and the second conv degenerates to a 9- / 21-tap shifted sum (cnn.cu: tap_sum_kernel).
+// HBM and the second conv degenerates to a sum of 3 / 7 time-tap planes (cnn.cu: halo_tapsum_kernel).
 //
 // Formulation ("Toeplitz along frequency on 16-bin aligned chunks")
 //   rows  m = b*174 + t            time frames of all windows of the chunk, two zero rows between windows
@@ -227,9 +227,10 @@ __constant__ int c_group_step_off[3][tc::kMaxGroups + 1];
 __constant__ int c_group_ft[3][2 * tc::kMaxGroups];
 // epilogue constants: conv1 bias and the weights of the fused channel reduction (conv2), [channel][tap]
 __constant__ float c_bias1[3][32];
-// (tap pairs for the packed FMAs: onset 9 taps -> 5 pairs, note 21 -> 11 pairs, the odd last one padded with 0)
-__constant__ float2 c_red_onset[32][5];
-__constant__ float2 c_red_note[32][11];
+// onset / note conv2 weights as pairs of time taps for the packed FMAs: [channel][df][pair p] = (w2[c][2p][df], w2[c][2p+1][df])
+// (onset 3 time taps -> 2 pairs, note 7 -> 4 pairs, the odd last one padded with 0)
+__constant__ float2 c_red_onset[32][3][2];
+__constant__ float2 c_red_note[32][3][4];
 // contour conv2 [dt][channel][6 pairs]: an input bin at even offset bl feeds the output pairs (bl,bl+1), (bl+2,bl+3),
 // (bl+4,bl+5) with weights (w4,w3), (w2,w1), (w0,0); at odd bl the pairs (bl-1,bl), (bl+1,bl+2), (bl+3,bl+4) with
 // (0,w4), (w3,w2), (w1,w0)   [output offset j = bl + 4 - df]
@@ -240,12 +241,13 @@ void tc_upload_epilogue(const float* contour1_b, const float* onset1_b, const fl
   float b[3][32] = {};
   for (int i = 0; i < 8; ++i) b[0][i] = contour1_b[i];
   for (int i = 0; i < 32; ++i) b[1][i] = onset1_b[i], b[2][i] = note1_b[i];
-  float2 ro[32][5], rn[32][11];
-  for (int c = 0; c < 32; ++c) {
-    // channel 0 of onset conv2 is the note input (models.py:305: concat[note, onset1])
-    for (int t = 0; t < 10; ++t) (&ro[c][0].x)[t] = t < 9 ? onset2_w[(1 + c) * 9 + t] : 0.f;
-    for (int t = 0; t < 22; ++t) (&rn[c][0].x)[t] = t < 21 ? note2_w[c * 21 + t] : 0.f;
-  }
+  float2 ro[32][3][2], rn[32][3][4];
+  for (int c = 0; c < 32; ++c)
+    for (int df = 0; df < 3; ++df) {
+      // channel 0 of onset conv2 is the note input (models.py:305: concat[note, onset1]); weights [1][C][KH][3]
+      for (int dt = 0; dt < 4; ++dt) (&ro[c][df][0].x)[dt] = dt < 3 ? onset2_w[(1 + c) * 9 + dt * 3 + df] : 0.f;
+      for (int dt = 0; dt < 8; ++dt) (&rn[c][df][0].x)[dt] = dt < 7 ? note2_w[c * 21 + dt * 3 + df] : 0.f;
+    }
   float2 rc[5][8][6];
   for (int c = 0; c < 8; ++c)
     for (int dt = 0; dt < 5; ++dt) {
@@ -330,50 +332,72 @@ struct TcArgs {
   int cout, flt, wout;
 };
 
-// Fused channel reduction of the epilogue: for each of the 4 bins of the tile (one 32-column slab = 32 channels)
-//   P[tap][f][t] = sum_c relu(v[c] + bias[c]) * w2[c][tap]
-// The output is time-fastest ([B][taps][WOUT][172]): the 32 lanes of a warp hold 32 consecutive frames, so every store
-// instruction writes one contiguous 128-byte run.  Two taps per packed FMA; the weight pairs are uniform-register
-// operands loaded from constant memory at static offsets (LDCU.128), so no weight lives in a vector register.
-template <int LAYER, int TAPS>
-__device__ __forceinline__ void reduce_store(uint32_t taddr, const float2 (&red)[32][(TAPS + 1) / 2],
-                                             float* dst /* (b, tap 0, f0, t) */, bool live) {
-  constexpr int TP2 = (TAPS + 1) / 2;
-  // two bins per iteration: every weight pair fetched from constant memory (LDCU) feeds two packed FMAs
-#pragma unroll 1
-  for (int fl = 0; fl < 4; fl += 2) {
-    uint32_t v0[32], v1[32];
-    tmem_ld32_nowait(taddr + fl * 32, v0);
-    tmem_ld32_nowait(taddr + fl * 32 + 32, v1);
-    tmem_ld_wait();
-    float2 acc0[TP2], acc1[TP2];
+// Fused second conv of the onset / note branch (32 -> 1 channels, KH x 3 taps, models.py:305-313 / 282-290) in the
+// epilogue.  The tile is 4 bins x 32 channels of relu(conv1) for one frame per thread; channels and frequency taps are
+// reduced in the thread:
+//   Q[dt][j][t] = sum_{c, df} relu(conv1)[c][t][4 ft + j + df - 2] * w2[c][dt][df]     j = 0 .. 5  (bins 4 ft - 1 + j)
+// and the time taps (and the two halo columns of the neighbouring tiles) are summed by halo_tapsum_kernel (cnn.cu).
+// Q is time-fastest ([B][22 tiles][KH][6][172]): the 32 lanes of a warp hold 32 consecutive frames, so every store
+// writes one contiguous 128-byte run; it is half the size of one plane per (dt, df) tap.  Packed FMAs over pairs of
+// time taps; the weight pairs are uniform-register operands loaded from constant memory at static offsets (LDCU.128),
+// two bins per loaded pair, so no weight lives in a vector register.
+template <int LAYER, int KH>
+__device__ __forceinline__ void reduce_store(uint32_t taddr, const float2 (&red)[32][3][(KH + 1) / 2],
+                                             float* dst /* (b, ft, dt 0, j 0, t) */, bool live) {
+  constexpr int NP = (KH + 1) / 2;
+  // rolling window over the output offsets: half h (input bins 2h, 2h+1) touches j = 2h .. 2h+3 = accw[0..3]; after it
+  // j = 2h and 2h+1 are complete.  The half loop is not unrolled (the weights stay LDCU operands instead of registers).
+  float2 accw[4][NP];
 #pragma unroll
-    for (int tp = 0; tp < TP2; ++tp) acc0[tp] = acc1[tp] = make_float2(0.f, 0.f);
+  for (int k = 0; k < 4; ++k)
+#pragma unroll
+    for (int p = 0; p < NP; ++p) accw[k][p] = make_float2(0.f, 0.f);
+#pragma unroll 1
+  for (int h = 0; h < 2; ++h) {
+    uint32_t v0[32], v1[32];
+    tmem_ld32_nowait(taddr + h * 64, v0);
+    tmem_ld32_nowait(taddr + h * 64 + 32, v1);
+    tmem_ld_wait();
 #pragma unroll
     for (int c = 0; c < 32; ++c) {
       const float o0 = fmaxf(__uint_as_float(v0[c]) + c_bias1[LAYER][c], 0.f);
       const float o1 = fmaxf(__uint_as_float(v1[c]) + c_bias1[LAYER][c], 0.f);
 #pragma unroll
-      for (int tp = 0; tp < TP2; ++tp) {
-        const float2 w = red[c][tp];
-        ffma2(acc0[tp], o0, w);
-        ffma2(acc1[tp], o1, w);
-      }
+      for (int df = 0; df < 3; ++df)
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+          const float2 w = red[c][df][p];
+          ffma2(accw[2 - df][p], o0, w);  // input bin fl feeds output offset j = fl - df + 2
+          ffma2(accw[3 - df][p], o1, w);
+        }
     }
+    float* d = dst + (size_t)(2 * h) * kFrames;
     if (live) {
 #pragma unroll
-      for (int tp = 0; tp < TAPS; ++tp) {
-        dst[((size_t)tp * kPitches + fl) * kFrames] = (tp & 1) ? acc0[tp >> 1].y : acc0[tp >> 1].x;
-        dst[((size_t)tp * kPitches + fl + 1) * kFrames] = (tp & 1) ? acc1[tp >> 1].y : acc1[tp >> 1].x;
-      }
+      for (int dt = 0; dt < KH; ++dt)
+#pragma unroll
+        for (int k = 0; k < 2; ++k) d[(size_t)(dt * 6 + k) * kFrames] = (dt & 1) ? accw[k][dt >> 1].y : accw[k][dt >> 1].x;
     }
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+      accw[0][p] = accw[2][p];
+      accw[1][p] = accw[3][p];
+      accw[2][p] = accw[3][p] = make_float2(0.f, 0.f);
+    }
+  }
+  if (live) {  // j = 4, 5: the halo columns of the next tile
+#pragma unroll
+    for (int dt = 0; dt < KH; ++dt)
+#pragma unroll
+      for (int k = 0; k < 2; ++k)
+        dst[(size_t)(dt * 6 + 4 + k) * kFrames] = (dt & 1) ? accw[k][dt >> 1].y : accw[k][dt >> 1].x;
   }
 }
 
 // Fused contour conv2 (8 -> 1 channels, 5 x 5 taps, models.py:252-259) in the contour epilogue.  A tile holds 16 bins
 // x 8 channels of relu(conv1) for one frame per thread; the channel and frequency taps are reduced in the thread,
 //   Q[dt][j][t] = sum_{c, df} relu(conv1)[c][t][16 ft + j - df] * w2[c][dt][df]      j = 0 .. 19  (bins 16 ft - 2 + j),
-// and the five time taps are summed by contour_tapsum_kernel (cnn.cu), which also adds the four halo columns of the
+// and the five time taps are summed by halo_tapsum_kernel (cnn.cu), which also adds the four halo columns of the
 // neighbouring tiles.  Q is time-fastest ([B][17 tiles][5][20][172]), so every store is a contiguous 128-byte run,
 // and 19 % smaller than the channels-last activations it replaces; the 8-channel image never reaches HBM.
 // Pass 0 applies bias + ReLU (and zeroes the bins >= 264 of the last tile) in place in TMEM; the dt loop is not
@@ -614,13 +638,13 @@ __global__ void __launch_bounds__(tc::kThreads, 1) conv_tc_kernel(const TcArgs a
             float* dst = a.out + ((size_t)b * 17 + ft) * (5 * 20 * kFrames) + t;
             contour_reduce_store(taddr, n_valid, dst, live);
           } else {
-            // onset / note: the tile is 4 bins x 32 channels; reduce the channels against the next conv's weights
-            constexpr int TAPS = (EPI == 1) ? 9 : 21;
-            float* dst = a.out + ((size_t)b * TAPS * kPitches + (size_t)ft * 4) * kFrames + t;
+            // onset / note: the tile is 4 bins x 32 channels; reduce channels and frequency taps of the next conv
+            constexpr int KH2 = (EPI == 1) ? 3 : 7;
+            float* dst = a.out + ((size_t)b * 22 + ft) * (KH2 * 6 * kFrames) + t;
             if constexpr (EPI == 1) {
-              reduce_store<1, 9>(taddr, c_red_onset, dst, live);
+              reduce_store<1, 3>(taddr, c_red_onset, dst, live);
             } else {
-              reduce_store<2, 21>(taddr, c_red_note, dst, live);
+              reduce_store<2, 7>(taddr, c_red_note, dst, live);
             }
           }
         }
