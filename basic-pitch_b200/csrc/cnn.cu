@@ -327,38 +327,56 @@ __global__ void __launch_bounds__(256) halo_tapsum_kernel(const float* __restric
                                                           float* __restrict__ out, SplitOut so) {
   __shared__ float tile[32][33];
   constexpr int kTiles = (WOUT + FLT - 1) / FLT, kJ = FLT + 2 * HALO;
+  constexpr int kPlane = kJ * kFrames;  // one (tile, dt) plane
+  constexpr int kTapStep = kPlane + 1;  // next time tap: next plane, next input frame (t + dt - PT)
+  static_assert((FLT & (FLT - 1)) == 0, "FLT is a power of two");
   const int b = blockIdx.z;
   const int t0 = blockIdx.x * 32, f0 = blockIdx.y * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const float* Qb = Q + (size_t)b * kTiles * KH * kJ * kFrames;
+  const float* Qb = Q + (size_t)b * kTiles * KH * kPlane;
   const float bv = __ldg(bias);
+  const int t = t0 + tx;
+  unsigned dmask = 0;  // time taps whose input frame t + dt - PT exists
+#pragma unroll
+  for (int dt = 0; dt < KH; ++dt)
+    if ((unsigned)(t + dt - PT) < (unsigned)kFrames) dmask |= 1u << dt;
+  if (t >= kFrames) dmask = 0;
+  float wxr[EXTRA ? 9 : 1];
+  if (EXTRA) {
+#pragma unroll
+    for (int k = 0; k < 9; ++k) wxr[k] = __ldg(wx + k);
+  }
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int fl = ty + 8 * i;
-    const int f = f0 + fl, t = t0 + tx;
+    const int f = f0 + fl;
     float acc = bv;
-    if (f < WOUT && t < kFrames) {
+    if (f < WOUT && dmask) {
       const int ft = f / FLT, r = f % FLT;
+      const float* q = Qb + (ft * KH * kJ + r + HALO) * kFrames + (t - PT);
+#pragma unroll
+      for (int dt = 0; dt < KH; ++dt)
+        if ((dmask >> dt) & 1u) acc += __ldg(q + dt * kTapStep);
       const int ft2 = (r < HALO) ? ft - 1 : ((r >= FLT - HALO) ? ft + 1 : -1);  // neighbour whose halo covers this bin
-      const int j2 = (r < HALO) ? r + HALO + FLT : r + HALO - FLT;
-      const bool has2 = ft2 >= 0 && ft2 < kTiles;
+      if (ft2 >= 0 && ft2 < kTiles) {
+        const int j2 = (r < HALO) ? r + HALO + FLT : r + HALO - FLT;
+        const float* q2 = Qb + (ft2 * KH * kJ + j2) * kFrames + (t - PT);
 #pragma unroll
-      for (int dt = 0; dt < KH; ++dt) {
-        const int tt = t + dt - PT;
-        if ((unsigned)tt >= (unsigned)kFrames) continue;
-        acc += __ldg(Qb + ((size_t)(ft * KH + dt) * kJ + r + HALO) * kFrames + tt);
-        if (has2) acc += __ldg(Qb + ((size_t)(ft2 * KH + dt) * kJ + j2) * kFrames + tt);
-        if (EXTRA) {
+        for (int dt = 0; dt < KH; ++dt)
+          if ((dmask >> dt) & 1u) acc += __ldg(q2 + dt * kTapStep);
+      }
+      if (EXTRA) {
+        const float* xr = x + ((size_t)b * kFrames + (t - PT)) * WOUT + f - 1;
 #pragma unroll
-          for (int df = 0; df < 3; ++df) {
-            const int ff = f + df - 1;
-            if ((unsigned)ff < (unsigned)WOUT)
-              acc = fmaf(__ldg(x + ((size_t)b * kFrames + tt) * WOUT + ff), __ldg(wx + dt * 3 + df), acc);
+        for (int dt = 0; dt < KH; ++dt)
+          if ((dmask >> dt) & 1u) {
+#pragma unroll
+            for (int df = 0; df < 3; ++df)
+              if ((unsigned)(f + df - 1) < (unsigned)WOUT) acc = fmaf(__ldg(xr + dt * WOUT + df), wxr[dt * 3 + df], acc);
           }
-        }
       }
     }
-    tile[fl][tx] = 1.f / (1.f + expf(-acc));
+    tile[fl][tx] = __fdividef(1.f, 1.f + __expf(-acc));
   }
   __syncthreads();
 #pragma unroll

@@ -8,10 +8,11 @@
 // Semantics pinned in SURVEY.md Appendix B; oracle: oracle/decode_ref.py.
 //
 // Kernels
-//   decode_prep_kernel   all cells of the batch in parallel: "remaining energy" E (column-major per file,
-//                        frames with the pitch range applied), per-file max(onsets) and max(frame_diff)
-//   decode_cand_kernel   all cells in parallel: float64 inferred onsets, strict time peaks, threshold ->
-//                        one candidate bit per cell (warp ballot -> 32-bit words)
+//   decode_prep_kernel   tiles of 32 frames x 88 pitches staged in shared memory: "remaining energy" E (column-major
+//                        per file, frames with the pitch range applied, written frame-fastest), per-file
+//                        max(onsets) and max(frame_diff)
+//   decode_cand_kernel   same tiles + 1 halo frame: float64 inferred onsets (one division per cell), strict time
+//                        peaks, threshold -> one candidate bit per cell (warp ballot -> 32-bit words)
 //   decode_seq_kernel    one CTA per file: candidates in (time desc, pitch desc) order through the greedy
 //                        onset loop (warp-cooperative run-of-`energy_tol` scan + neighbour zeroing), then the
 //                        melodia loop with per-column maxima kept in shared memory
@@ -37,117 +38,165 @@ __device__ __forceinline__ float constrained(const float* __restrict__ m, long l
   return (f >= lo && f < hi) ? m[frame * kPitches + f] : 0.f;
 }
 
-// positive part of min(n[t]-n[t-1], n[t]-n[t-2]) in float64, zero history, rows 0,1 -> 0
-__device__ __forceinline__ double frame_diff(const float* __restrict__ note, long long base, int t, int f, int lo,
-                                             int hi) {
-  if (t < 2) return 0.0;
-  double a = (double)constrained(note, base + t, f, lo, hi);
-  double d1 = a - (double)constrained(note, base + t - 1, f, lo, hi);
-  double d2 = a - (double)constrained(note, base + t - 2, f, lo, hi);
-  double d = d1 < d2 ? d1 : d2;
+// ------------------------------------------------------------------------------------------------
+// Both cell-parallel kernels work on tiles of 32 consecutive frames of the batch (all 88 pitches) staged in shared
+// memory: row-major global reads, the transposed (frame-fastest) writes of E and the time neighbours of the peak pick
+// come from the tile.  A tile may straddle files; every row carries its own file.
+// ------------------------------------------------------------------------------------------------
+constexpr int kTileFrames = 32;
+
+struct RowInfo {
+  int file;        // -1: row outside the batch
+  int t, T;        // frame index inside the file, frames of the file
+  long long base;  // first frame of the file
+};
+
+__device__ __forceinline__ RowInfo row_info(const long long* __restrict__ frame_off, int n_files, long long g,
+                                            long long total) {
+  RowInfo r{-1, 0, 0, 0};
+  if (g >= 0 && g < total) {
+    r.file = find_file(frame_off, n_files, g);
+    r.base = frame_off[r.file];
+    r.T = (int)(frame_off[r.file + 1] - r.base);
+    r.t = (int)(g - r.base);
+  }
+  return r;
+}
+
+// positive part of min(n[t]-n[t-1], n[t]-n[t-2]) in float64 from three rows of the staged tile (t >= 2)
+__device__ __forceinline__ double frame_diff3(float a, float m1, float m2) {
+  const double d1 = (double)a - (double)m1, d2 = (double)a - (double)m2;
+  const double d = d1 < d2 ? d1 : d2;
   return d < 0.0 ? 0.0 : d;
 }
 
-// ------------------------------------------------------------------------------------------------
-__global__ void decode_prep_kernel(const float* __restrict__ note, const float* __restrict__ onset,
-                                   const long long* __restrict__ frame_off, int n_files, float* __restrict__ energy,
-                                   unsigned int* __restrict__ max_onset,          // [n_files] ordered-uint
-                                   unsigned long long* __restrict__ max_fd,       // [n_files] bits of a double >= 0
-                                   int lo, int hi) {
-  const long long total = frame_off[n_files] * kPitches;
-  const long long cell0 = (long long)blockIdx.x * blockDim.x;
-  const long long cell = cell0 + threadIdx.x;
-  __shared__ unsigned int s_mo[32];
-  __shared__ unsigned long long s_fd[32];
-  __shared__ int s_file_first, s_file_last;
-
-  if (threadIdx.x == 0) {
-    long long last_cell = cell0 + blockDim.x - 1;
-    if (last_cell >= total) last_cell = total - 1;
-    s_file_first = find_file(frame_off, n_files, cell0 / kPitches);
-    s_file_last = find_file(frame_off, n_files, last_cell / kPitches);
+__global__ void __launch_bounds__(256) decode_prep_kernel(const float* __restrict__ note, const float* __restrict__ onset,
+                                                          const long long* __restrict__ frame_off, int n_files,
+                                                          float* __restrict__ energy,
+                                                          unsigned int* __restrict__ max_onset,     // [n_files] ordered-uint
+                                                          unsigned long long* __restrict__ max_fd,  // [n_files] bits of a double >= 0
+                                                          int lo, int hi) {
+  __shared__ float s_n[kTileFrames + 2][kPitches + 1];  // rows g0-2 .. g0+31, pitch range applied
+  __shared__ RowInfo s_row[kTileFrames];
+  __shared__ unsigned int s_mo[8];
+  __shared__ unsigned long long s_fd[8];
+  const long long total = frame_off[n_files];
+  const long long g0 = (long long)blockIdx.x * kTileFrames;
+  const int nrows = (int)min((long long)kTileFrames, total - g0);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid < kTileFrames) s_row[tid] = row_info(frame_off, n_files, g0 + tid, total);
+  for (int idx = tid; idx < (kTileFrames + 2) * kPitches; idx += 256) {
+    const int rr = idx / kPitches, f = idx - rr * kPitches;
+    const long long g = g0 - 2 + rr;
+    s_n[rr][f] = (g >= 0 && g < total) ? constrained(note, g, f, lo, hi) : 0.f;
   }
   __syncthreads();
-
+  const bool one_file = s_row[0].file == s_row[nrows - 1].file;
   unsigned int mo = 0u;  // ordered encoding of -inf is > 0, so 0 is a safe identity for max
   unsigned long long fd_bits = 0ull;
-  int file = s_file_first;
-  if (cell < total) {
-    const long long frame = cell / kPitches;
-    const int f = (int)(cell - frame * kPitches);
-    if (s_file_first != s_file_last) file = find_file(frame_off, n_files, frame);
-    const long long base = frame_off[file];
-    const int T = (int)(frame_off[file + 1] - base);
-    const int t = (int)(frame - base);
-    energy[base * kPitches + (long long)f * T + t] = constrained(note, frame, f, lo, hi);
-    mo = float_to_ordered(constrained(onset, frame, f, lo, hi));
-    fd_bits = (unsigned long long)__double_as_longlong(frame_diff(note, base, t, f, lo, hi));
+  for (int idx = tid; idx < nrows * kPitches; idx += 256) {
+    const int r = idx / kPitches, f = idx - r * kPitches;
+    const unsigned int mo_c = float_to_ordered(constrained(onset, g0 + r, f, lo, hi));
+    const double fd = s_row[r].t >= 2 ? frame_diff3(s_n[r + 2][f], s_n[r + 1][f], s_n[r][f]) : 0.0;
+    const unsigned long long fd_c = (unsigned long long)__double_as_longlong(fd);
+    if (one_file) {
+      mo = max(mo, mo_c);
+      fd_bits = max(fd_bits, fd_c);
+    } else {
+      atomicMax(max_onset + s_row[r].file, mo_c);
+      atomicMax(max_fd + s_row[r].file, fd_c);
+    }
   }
-  if (s_file_first == s_file_last) {
+  if (one_file) {
 #pragma unroll
     for (int o = 16; o; o >>= 1) {
       mo = max(mo, __shfl_xor_sync(0xffffffffu, mo, o));
       fd_bits = max(fd_bits, __shfl_xor_sync(0xffffffffu, fd_bits, o));
     }
-    if ((threadIdx.x & 31) == 0) {
-      s_mo[threadIdx.x >> 5] = mo;
-      s_fd[threadIdx.x >> 5] = fd_bits;
+    if (lane == 0) {
+      s_mo[warp] = mo;
+      s_fd[warp] = fd_bits;
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-      for (int i = 1; i < (int)(blockDim.x >> 5); ++i) {
+    if (tid == 0) {
+      for (int i = 1; i < 8; ++i) {
         mo = max(mo, s_mo[i]);
         fd_bits = max(fd_bits, s_fd[i]);
       }
-      if (mo) atomicMax(max_onset + file, mo);
-      atomicMax(max_fd + file, fd_bits);
+      if (mo) atomicMax(max_onset + s_row[0].file, mo);
+      atomicMax(max_fd + s_row[0].file, fd_bits);
     }
-  } else if (cell < total) {
-    atomicMax(max_onset + file, mo);
-    atomicMax(max_fd + file, fd_bits);
+  }
+  // E is column-major per file ([88][T]): lanes = consecutive frames -> contiguous 128-byte runs
+  if (lane < nrows) {
+    const RowInfo ri = s_row[lane];
+    float* e = energy + ri.base * kPitches + ri.t;
+    for (int f = warp; f < kPitches; f += 8) e[(long long)f * ri.T] = s_n[lane + 2][f];
   }
 }
 
-// float64 onset value used for peak picking (NaN when max(frame_diff) == 0, like the reference)
-__device__ __forceinline__ double onset64(const float* __restrict__ note, const float* __restrict__ onset,
-                                          long long base, int t, int f, int lo, int hi, int infer, double maxo,
-                                          double maxfd) {
-  double o = (double)constrained(onset, base + t, f, lo, hi);
-  if (!infer) return o;
-  double fd = frame_diff(note, base, t, f, lo, hi);
-  double v = __ddiv_rn(__dmul_rn(maxo, fd), maxfd);
-  if (v != v) return v;
-  return o > v ? o : v;
-}
-
-__global__ void decode_cand_kernel(const float* __restrict__ note, const float* __restrict__ onset,
-                                   const long long* __restrict__ frame_off, int n_files,
-                                   const unsigned int* __restrict__ max_onset,
-                                   const unsigned long long* __restrict__ max_fd, unsigned int* __restrict__ candbits,
-                                   int lo, int hi, int infer, double onset_thresh) {
-  const long long total = frame_off[n_files] * kPitches;
-  const long long cell = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  bool cand = false;
-  if (cell < total) {
-    const long long frame = cell / kPitches;
-    const int f = (int)(cell - frame * kPitches);
-    const int file = find_file(frame_off, n_files, frame);
-    const long long base = frame_off[file];
-    const int T = (int)(frame_off[file + 1] - base);
-    const int t = (int)(frame - base);
-    const double maxo = (double)ordered_to_float(max_onset[file]);
-    const double maxfd = __longlong_as_double((long long)max_fd[file]);
+__global__ void __launch_bounds__(256) decode_cand_kernel(const float* __restrict__ note, const float* __restrict__ onset,
+                                                          const long long* __restrict__ frame_off, int n_files,
+                                                          const unsigned int* __restrict__ max_onset,
+                                                          const unsigned long long* __restrict__ max_fd,
+                                                          unsigned int* __restrict__ candbits, int lo, int hi, int infer,
+                                                          double onset_thresh) {
+  __shared__ float s_n[kTileFrames + 4][kPitches + 1];  // note rows g0-3 .. g0+32 (inferred onsets only)
+  __shared__ double s_v[kTileFrames + 2][kPitches];     // float64 onset value of rows g0-1 .. g0+32
+  __shared__ RowInfo s_row[kTileFrames + 2];
+  __shared__ double s_maxo[kTileFrames + 2], s_maxfd[kTileFrames + 2];
+  const long long total = frame_off[n_files];
+  const long long g0 = (long long)blockIdx.x * kTileFrames;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid < kTileFrames + 2) {
+    const RowInfo ri = row_info(frame_off, n_files, g0 - 1 + tid, total);
+    s_row[tid] = ri;
+    if (ri.file >= 0) {
+      s_maxo[tid] = (double)ordered_to_float(max_onset[ri.file]);
+      s_maxfd[tid] = __longlong_as_double((long long)max_fd[ri.file]);
+    }
+  }
+  if (infer) {
+    for (int idx = tid; idx < (kTileFrames + 4) * kPitches; idx += 256) {
+      const int rr = idx / kPitches, f = idx - rr * kPitches;
+      const long long g = g0 - 3 + rr;
+      s_n[rr][f] = (g >= 0 && g < total) ? constrained(note, g, f, lo, hi) : 0.f;
+    }
+  }
+  __syncthreads();
+  // float64 onset value used for peak picking (NaN when max(frame_diff) == 0, like the reference): once per cell
+  for (int idx = tid; idx < (kTileFrames + 2) * kPitches; idx += 256) {
+    const int rr = idx / kPitches, f = idx - rr * kPitches;
+    const RowInfo ri = s_row[rr];
+    double v = 0.0;
+    if (ri.file >= 0) {
+      const double o = (double)constrained(onset, g0 - 1 + rr, f, lo, hi);
+      v = o;
+      if (infer) {
+        const double fd = ri.t >= 2 ? frame_diff3(s_n[rr + 2][f], s_n[rr + 1][f], s_n[rr][f]) : 0.0;
+        const double w = __ddiv_rn(__dmul_rn(s_maxo[rr], fd), s_maxfd[rr]);
+        v = (w != w) ? w : (o > w ? o : w);
+      }
+    }
+    s_v[rr][f] = v;
+  }
+  __syncthreads();
+  // strict time peaks >= threshold; a warp ballot is one 32-cell word of the candidate bitmap
+  const long long cell0 = g0 * kPitches;  // multiple of 32
+  const long long total_cells = total * kPitches;
+  for (int word = warp; word < kTileFrames * kPitches / 32; word += 8) {
+    const int cl = word * 32 + lane;
+    const int r = cl / kPitches, f = cl - r * kPitches;
+    const RowInfo ri = s_row[r + 1];
     double val = 0.0;
-    if (t >= 1 && t <= T - 2) {
-      double c = onset64(note, onset, base, t, f, lo, hi, infer, maxo, maxfd);
-      double p = onset64(note, onset, base, t - 1, f, lo, hi, infer, maxo, maxfd);
-      double n = onset64(note, onset, base, t + 1, f, lo, hi, infer, maxo, maxfd);
-      if (c > p && c > n) val = c;
+    if (ri.file >= 0 && ri.t >= 1 && ri.t <= ri.T - 2) {
+      const double c = s_v[r + 1][f];
+      if (c > s_v[r][f] && c > s_v[r + 2][f]) val = c;
     }
-    cand = val >= onset_thresh;
+    const bool cand = ri.file >= 0 && val >= onset_thresh;
+    const unsigned int bits = __ballot_sync(0xffffffffu, cand);
+    if (lane == 0 && cell0 + (long long)word * 32 < total_cells) candbits[(cell0 >> 5) + word] = bits;
   }
-  unsigned int bits = __ballot_sync(0xffffffffu, cand);
-  if ((threadIdx.x & 31) == 0 && cell < total) candbits[cell >> 5] = bits;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -391,7 +440,7 @@ void launch_decode_notes(const float* note, const float* onset, const DecodeBuff
   cudaMemsetAsync(b.max_fd, 0, sizeof(unsigned long long) * n_files, st);
   if (cells > 0) {
     const int threads = 256;
-    const unsigned int blocks = (unsigned int)((cells + threads - 1) / threads);
+    const unsigned int blocks = (unsigned int)((total_frames + kTileFrames - 1) / kTileFrames);
     decode_prep_kernel<<<blocks, threads, 0, st>>>(note, onset, b.frame_off, n_files, b.energy, b.max_onset, b.max_fd,
                                                    p.lo_col, p.hi_col);
     decode_cand_kernel<<<blocks, threads, 0, st>>>(note, onset, b.frame_off, n_files, b.max_onset, b.max_fd,
