@@ -254,7 +254,7 @@ int parse_blob(const void* blob, size_t nbytes, std::vector<float>& params) {
 
 int upload_constants(bp_model* m, cudaStream_t st) {
   const float* hp = m->h_params.data();
-  upload_lowpass(m->d_params + ParamLayout::lowpass, st);
+  upload_lowpass(hp + ParamLayout::lowpass, st);
   tc_upload_epilogue(hp + ParamLayout::contour1_b, hp + ParamLayout::onset1_b, hp + ParamLayout::note1_b,
                      hp + ParamLayout::onset2_w, hp + ParamLayout::note2_w, hp + ParamLayout::contour2_w, st);
   CKL();
@@ -408,7 +408,7 @@ int forward_chunk(bp_model* m, const float* audio, const WinDesc* desc, int nb, 
     }
   }
   CKL();
-  m->launches += 8 + 2 + 1 + (m->path == 1 ? 7 : 6);
+  m->launches += 5 + 2 + 1 + (m->path >= 1 ? 7 : 6);  // decimation (4 + tail), min/max init + CQT, log-normalise, convs
   m->last_path = m->path;
   return BP_OK;
 }

@@ -7,91 +7,159 @@
 //   NormalizedLog.call    reference: basic_pitch/layers/signal.py:171-185
 //   BatchNormalization    reference: basic_pitch/models.py:188-189 (folded scalar affine)
 // Kernels:
-//   decimate_kernel  x_{o+1}[n] = sum_k LP[k] * x_o[2n + k - 127]           (8 launches per chunk)
+//   decimate_kernel  x_{o+1}[n] = sum_k LP[k] * x_o[2n + k - 127]           (4 launches + 1 tail launch per chunk)
 //   cqt_kernel       frames(172) x taps(256) x 72 projection per octave, magnitude*sqrt(len),
 //                    10*log10(p + 1e-10), per-window min/max (atomics)       (1 launch per chunk)
 //   lognorm_kernel   (L - min) / (max - min) * bn_scale + bn_bias            (1 launch per chunk)
 #include "kernels.cuh"
+#include "tc_ptx.cuh"
 
 namespace bp {
 
-__constant__ float c_lowpass[kTaps];
+// Low-pass taps as pairs for the packed FMAs: c_lp2[k] = (h[k - 12], h[k - 14]), zero outside the 256 taps.  A thread that
+// owns outputs 8t .. 8t+7 feeds sample u of its input run into the output pairs (0,1), (2,3), (4,5), (6,7) with
+// c_lp2[u + 12], c_lp2[u + 8], c_lp2[u + 4], c_lp2[u].
+constexpr int kLp2 = kTaps + 14;
+__constant__ float2 c_lp2[kLp2];
 
-void upload_lowpass(const float* d_lp, cudaStream_t st) {
-  cudaMemcpyToSymbolAsync(c_lowpass, d_lp, sizeof(float) * kTaps, 0, cudaMemcpyDeviceToDevice, st);
+void upload_lowpass(const float* h_lp, cudaStream_t st) {
+  float2 tab[kLp2];  // (the copy is synchronised below)
+  for (int k = 0; k < kLp2; ++k) {
+    const int u = k - 12;
+    tab[k].x = (u >= 0 && u < kTaps) ? h_lp[u] : 0.f;
+    tab[k].y = (u - 2 >= 0 && u - 2 < kTaps) ? h_lp[u - 2] : 0.f;
+  }
+  cudaMemcpyToSymbolAsync(c_lp2, tab, sizeof(tab), 0, cudaMemcpyHostToDevice, st);
+  cudaStreamSynchronize(st);
 }
 
 // ------------------------------------------------------------------------------------------------
-// Half-band FIR + decimate by 2.  One CTA = 512 outputs of one window; thread t owns outputs
-// 4t..4t+3.  The 1278 input samples of the tile are stored de-interleaved into 8 phases so that
-// lanes read consecutive words (no bank conflicts) while each loaded sample feeds up to 4 FMAs;
-// the taps come from the constant bank as immediate operands of the (fully unrolled) FMAs.
+// Half-band FIR + decimate by 2:  x_{o+1}[n] = sum_k LP[k] * x_o[2n + k - 127].
+// Input runs live in shared memory de-interleaved into 16 phases (sample li at ph[(li & 15) * S + (li >> 4)], S == 2
+// mod 32: conflict-free scatter and gather); thread t owns outputs 8t .. 8t+7, so every loaded sample feeds up to 8
+// FMAs, issued as 4 packed FMAs (FFMA2) whose tap pairs are uniform-register operands from constant memory.  Each
+// output still accumulates its 256 products in tap order.
+//   decimate_kernel       stages 0-3: one CTA = 1024 outputs of one window
+//   decimate_tail_kernel  stages 4-7 (2740 -> 171 samples): one CTA per window runs the four stages back to back through
+//                         shared memory (as four launches they were latency-bound: 25 % of the chain's time for 6 % of
+//                         its work)
 // ------------------------------------------------------------------------------------------------
-constexpr int kDecTile = 512;
+template <int S>
+__device__ __forceinline__ void fir8(const float* __restrict__ ph, int t, float (&out)[8]) {
+  float2 a01 = make_float2(0.f, 0.f), a23 = a01, a45 = a01, a67 = a01;
+#pragma unroll
+  for (int u = 0; u < kTaps + 14; ++u) {
+    const float v = ph[(u & 15) * S + t + (u >> 4)];
+    if (u < kTaps + 2) ffma2(a01, v, c_lp2[u + 12]);
+    if (u >= 4 && u < kTaps + 6) ffma2(a23, v, c_lp2[u + 8]);
+    if (u >= 8 && u < kTaps + 10) ffma2(a45, v, c_lp2[u + 4]);
+    if (u >= 12) ffma2(a67, v, c_lp2[u]);
+  }
+  out[0] = a01.x, out[1] = a01.y, out[2] = a23.x, out[3] = a23.y;
+  out[4] = a45.x, out[5] = a45.y, out[6] = a67.x, out[7] = a67.y;
+}
+
+constexpr int kDecTile = 1024;
 constexpr int kDecThreads = 128;
-constexpr int kDecPhaseStride = 164;  // == 4 (mod 32): conflict-free scatter and gather
+constexpr int kDecS = 162;  // positions per phase: (2 * 1024 + 270) / 16 = 145 -> next value == 2 (mod 32)
 
 __global__ void __launch_bounds__(kDecThreads) decimate_kernel(const float* __restrict__ audio,
                                                                const WinDesc* __restrict__ desc,  // stage 0 only
                                                                const float* __restrict__ src,     // chain, stage >= 1
                                                                float* __restrict__ dst, int src_off, int dst_off,
                                                                int len_in, int len_out, int from_audio) {
-  __shared__ float ph[8 * kDecPhaseStride];
+  __shared__ float ph[16 * kDecS];
   const int b = blockIdx.y;
   const int n0 = blockIdx.x * kDecTile;
   const int gbase = 2 * n0 - 127;  // input index of local index 0
+  constexpr int kLocal = 2 * kDecTile + 272;  // local inputs staged (multiple of 16)
 
+  const float* s;
+  int lo = 0, hi = len_in;
   if (from_audio) {
-    long long base;
-    int lo, hi;
     if (desc) {
-      WinDesc d = desc[b];
-      base = d.base;
+      const WinDesc d = desc[b];
+      s = audio + d.base;
       lo = d.lo;
       hi = d.hi;
     } else {
-      base = (long long)b * kWinSamples;
-      lo = 0;
+      s = audio + (long long)b * kWinSamples;
       hi = kWinSamples;
     }
-    for (int li = threadIdx.x; li < 8 * 160; li += kDecThreads) {
-      int gi = gbase + li;
-      float v = (gi >= lo && gi < hi) ? __ldg(audio + base + gi) : 0.f;
-      ph[(li & 7) * kDecPhaseStride + (li >> 3)] = v;
-    }
   } else {
-    const float* s = src + (size_t)b * kChainStride + src_off;
-    for (int li = threadIdx.x; li < 8 * 160; li += kDecThreads) {
-      int gi = gbase + li;
-      float v = (gi >= 0 && gi < len_in) ? s[gi] : 0.f;
-      ph[(li & 7) * kDecPhaseStride + (li >> 3)] = v;
-    }
+    s = src + (size_t)b * kChainStride + src_off;
+  }
+  for (int li = threadIdx.x; li < kLocal; li += kDecThreads) {
+    const int gi = gbase + li;
+    ph[(li & 15) * kDecS + (li >> 4)] = (gi >= lo && gi < hi) ? __ldg(s + gi) : 0.f;
   }
   __syncthreads();
 
   const int t = threadIdx.x;
-  float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
-#pragma unroll
-  for (int u = 0; u < kTaps + 6; ++u) {
-    float v = ph[(u & 7) * kDecPhaseStride + t + (u >> 3)];
-    if (u < kTaps) acc0 = fmaf(c_lowpass[u], v, acc0);
-    if (u >= 2 && u - 2 < kTaps) acc1 = fmaf(c_lowpass[u - 2], v, acc1);
-    if (u >= 4 && u - 4 < kTaps) acc2 = fmaf(c_lowpass[u - 4], v, acc2);
-    if (u >= 6 && u - 6 < kTaps) acc3 = fmaf(c_lowpass[u - 6], v, acc3);
-  }
+  const int n = n0 + 8 * t;
+  if (n >= len_out) return;
+  float o[8];
+  fir8<kDecS>(ph, t, o);
   float* d = dst + (size_t)b * kChainStride + dst_off;
-  int n = n0 + 4 * t;
-  if (n + 3 < len_out) {
-    *reinterpret_cast<float4*>(d + n) = make_float4(acc0, acc1, acc2, acc3);
+  if (n + 7 < len_out) {
+    *reinterpret_cast<float4*>(d + n) = make_float4(o[0], o[1], o[2], o[3]);
+    *reinterpret_cast<float4*>(d + n + 4) = make_float4(o[4], o[5], o[6], o[7]);
   } else {
-    if (n < len_out) d[n] = acc0;
-    if (n + 1 < len_out) d[n + 1] = acc1;
-    if (n + 2 < len_out) d[n + 2] = acc2;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (n + i < len_out) d[n + i] = o[i];
+  }
+}
+
+constexpr int kTailFirst = 4;     // the tail kernel runs stages 4 .. 7
+constexpr int kTailThreads = 256;
+constexpr int kTailS = 194;       // (2740 + 127 + 270) / 16 = 197 positions would be needed for reads past the last output's run;
+                                  // active threads (8t < 1370) read positions <= 171 + 16, 194 == 2 (mod 32)
+
+__global__ void __launch_bounds__(kTailThreads) decimate_tail_kernel(float* __restrict__ chain) {
+  __shared__ float buf[2][16 * kTailS];
+  float* c = chain + (size_t)blockIdx.x * kChainStride;
+  const int tid = threadIdx.x;
+  {
+    const float* s = c + chain_off(kTailFirst);
+    const int len = octave_len(kTailFirst);
+    for (int li = tid; li < 16 * kTailS; li += kTailThreads) {
+      const int gi = li - 127;
+      buf[0][(li & 15) * kTailS + (li >> 4)] = (gi >= 0 && gi < len) ? s[gi] : 0.f;
+    }
+  }
+  int cur = 0;
+#pragma unroll 1
+  for (int stage = kTailFirst; stage < 8; ++stage) {
+    const int len_out = octave_len(stage + 1);
+    float* nxt = buf[cur ^ 1];
+    for (int i = tid; i < 16 * kTailS; i += kTailThreads) nxt[i] = 0.f;
+    __syncthreads();  // cur is complete, nxt is zero
+    const int n = 8 * tid;
+    if (n < len_out) {
+      float o[8];
+      fir8<kTailS>(buf[cur], tid, o);
+      float* d = c + chain_off(stage + 1);
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (n + i < len_out) {
+          d[n + i] = o[i];
+          const int li = n + i + 127;  // local index of this sample in the next stage's input run
+          nxt[(li & 15) * kTailS + (li >> 4)] = o[i];
+        }
+    }
+    cur ^= 1;
+    __syncthreads();
   }
 }
 
 void launch_decimate(const float* audio, const WinDesc* desc, float* chain, int stage, int n_windows,
                      cudaStream_t st) {
+  if (stage > kTailFirst) return;  // done by the tail launch
+  if (stage == kTailFirst) {
+    decimate_tail_kernel<<<n_windows, kTailThreads, 0, st>>>(chain);
+    return;
+  }
   // stage s: x_s -> x_{s+1}
   const int len_in = octave_len(stage), len_out = octave_len(stage + 1);
   dim3 grid((len_out + kDecTile - 1) / kDecTile, n_windows);

@@ -10,7 +10,7 @@
 namespace bp {
 
 // ---- hcqt.cu ------------------------------------------------------------------------------------
-void upload_lowpass(const float* d_lp, cudaStream_t st);  // device pointer -> __constant__ taps
+void upload_lowpass(const float* h_lp, cudaStream_t st);  // host taps -> __constant__ tap pairs
 void launch_decimate(const float* audio, const WinDesc* desc, float* chain, int stage, int n_windows, cudaStream_t st);
 void launch_cqt(const float* audio, const WinDesc* desc, const float* chain, const float* wt, const float* scale,
                 float* logmag, unsigned int* minmax, int n_windows, cudaStream_t st);
