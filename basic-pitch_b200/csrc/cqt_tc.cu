@@ -164,39 +164,45 @@ __global__ void __launch_bounds__(cq::kThreads, 1) cqt_tc_kernel(const CqtTcArgs
       }
       const int i0 = t * hop - 128;  // signal index of tap 0 of this frame
       for (int c = 0; c < kTaps / kKc; ++c) {
+        // this thread's 32 taps of the chunk: issued before the wait for a free stage, so the load latency overlaps it
+        const int ib = i0 + c * kKc;
+        const bool interior = live && ib >= lo && ib + kKc <= hi && ib >= 0 && ib + kKc <= len;
+        const bool vec = interior && ((reinterpret_cast<uintptr_t>(src + ib) & 15) == 0);
+        const int j0 = 32 * khalf;
+        float xs[32];
+        if (__all_sync(0xffffffffu, vec)) {  // 16-byte aligned interior rows (hop >= 4): eight 128-bit loads in flight
+          const float4* p4 = reinterpret_cast<const float4*>(src + ib + j0);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 v = __ldg(p4 + i);
+            xs[4 * i] = v.x, xs[4 * i + 1] = v.y, xs[4 * i + 2] = v.z, xs[4 * i + 3] = v.w;
+          }
+        } else if (__all_sync(0xffffffffu, interior)) {  // hop 2 / 1: overlapping rows, mostly L1 hits
+#pragma unroll
+          for (int j = 0; j < 32; ++j) xs[j] = __ldg(src + ib + j0 + j);
+        } else {  // rows that touch the ends of the signal: reflect padding, zeros outside [lo, hi)
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            int idx = ib + j0 + j;
+            float xv = 0.f;
+            if (live) {
+              if (idx < 0) idx = -idx;
+              if (idx >= len) idx = 2 * (len - 1) - idx;
+              if (idx >= lo && idx < hi) xv = __ldg(src + idx);
+            }
+            xs[j] = xv;
+          }
+        }
         mbar_wait(empty + stage, ph ^ 1);
         unsigned char* sa = smem + stage * kStageBytes;
         if (ptid == 0) {
           mbar_expect_tx_only(full + stage, 3 * kWPlane);  // the bulk copy of the W slice completes on the same barrier
           bulk_g2s(sa + 3 * kAPlane, a.wtc + (size_t)c * (3 * kWPlane / 2), 3 * kWPlane, full + stage);
         }
-        const int ib = i0 + c * kKc;
-        const bool interior = live && ib >= lo && ib + kKc <= hi && ib >= 0 && ib + kKc <= len;
-        const bool vec = interior && ((reinterpret_cast<uintptr_t>(src + ib) & 15) == 0);
 #pragma unroll
         for (int q = 0; q < kKc / 16; ++q) {
           const int kc = khalf * (kKc / 16) + q;
-          float x[8];
-          if (vec) {  // 16-byte aligned interior rows: two 128-bit loads
-            const float4 v0 = __ldg(reinterpret_cast<const float4*>(src + ib + 8 * kc));
-            const float4 v1 = __ldg(reinterpret_cast<const float4*>(src + ib + 8 * kc) + 1);
-            x[0] = v0.x; x[1] = v0.y; x[2] = v0.z; x[3] = v0.w;
-            x[4] = v1.x; x[5] = v1.y; x[6] = v1.z; x[7] = v1.w;
-          } else {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              int idx = ib + 8 * kc + j;
-              float xv = 0.f;
-              if (interior) {
-                xv = __ldg(src + idx);
-              } else if (live) {
-                if (idx < 0) idx = -idx;
-                if (idx >= len) idx = 2 * (len - 1) - idx;
-                if (idx >= lo && idx < hi) xv = __ldg(src + idx);
-              }
-              x[j] = xv;
-            }
-          }
+          const float* x = xs + 8 * q;
           __align__(16) __nv_bfloat162 h[4], md[4], l[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
