@@ -41,7 +41,8 @@ constexpr int kStageBytes = 3 * kAPlane + 3 * kWPlane;  // 79872
 constexpr int kStages = 2;
 constexpr int kProducers = 256;  // 8 producer warps: thread = (row, half of the 8 k-chunks)
 constexpr int kThreads = kProducers + 32 + 128;
-constexpr int kSmemBytes = kStages * kStageBytes + 256;
+constexpr int kTilePitch = 37;                    // epilogue staging: [4 warps][32 rows][36 bins + 1]
+constexpr int kSmemBytes = kStages * kStageBytes + 256 + 4 * 32 * kTilePitch * 4;
 }  // namespace cq
 
 static inline uint16_t f2bf_rn(float x) {
@@ -287,25 +288,25 @@ __global__ void __launch_bounds__(cq::kThreads, 1) cqt_tc_kernel(const CqtTcArgs
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * 128u;
       float vmin = INFINITY, vmax = -INFINITY;
-      float* out = a.logmag + (size_t)m * kCqtBins;  // m == b*172 + t
       const int g0 = (8 - o) * kBinsPerOctave - 15;  // global bin of this octave's bin 0 (may be negative for o = 8)
+      // 10*log10(re^2 + im^2 + 1e-10) per bin (MUFU.LG2; the reference's sqrt-then-square differs by < 1e-6 dB), staged
+      // per warp in shared memory so that the stores below write runs of consecutive bins instead of one bin of 32 rows
+      float* tile = reinterpret_cast<float*>(smem + kStages * kStageBytes + 256) + quad * (32 * kTilePitch);
 #pragma unroll 1
       for (int part = 0; part < 5; ++part) {  // 5 x 16 columns = 8 bins each (the last part holds bins 32..35 + padding)
         uint32_t v[16];
         tmem_ld16_nowait(taddr + part * 16, v);
         tmem_ld_wait();
-        if (live) {
 #pragma unroll
-          for (int jb = 0; jb < 8; ++jb) {
-            const int j = part * 8 + jb;
-            const int g = g0 + j;
-            if (j < kBinsPerOctave && g >= 0) {
-              const float s = __ldg(a.scale + g);
-              const float re = __fmul_rn(__uint_as_float(v[2 * jb]), s), im = __fmul_rn(__uint_as_float(v[2 * jb + 1]), s);
-              const float mag = sqrtf(__fadd_rn(__fmul_rn(re, re), __fmul_rn(im, im)));
-              const float p = __fadd_rn(__fmul_rn(mag, mag), 1e-10f);
-              const float L = __fmul_rn(__fmul_rn(logf(p), 0.4342944622039795f), 10.0f);
-              out[g] = L;
+        for (int jb = 0; jb < 8; ++jb) {
+          const int j = part * 8 + jb;
+          const int g = g0 + j;
+          if (j < kBinsPerOctave && g >= 0) {
+            const float s = __ldg(a.scale + g);
+            const float re = __uint_as_float(v[2 * jb]) * s, im = __uint_as_float(v[2 * jb + 1]) * s;
+            const float L = __log2f(fmaf(re, re, im * im) + 1e-10f) * 3.0102999566398120f;
+            tile[lane * kTilePitch + j] = L;
+            if (live) {
               vmin = fminf(vmin, L);
               vmax = fmaxf(vmax, L);
             }
@@ -314,7 +315,18 @@ __global__ void __launch_bounds__(cq::kThreads, 1) cqt_tc_kernel(const CqtTcArgs
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tmem_empty + buf);
+      if (lane == 0) mbar_arrive(tmem_empty + buf);  // the accumulator is free while the tile is written out
+      {
+        const int m0 = mt * kMTile + quad * 32;
+#pragma unroll 4
+        for (int i = 0; i < kBinsPerOctave; ++i) {
+          const int e = i * 32 + lane;
+          const int rr = e / kBinsPerOctave, jj = e - rr * kBinsPerOctave;
+          if (m0 + rr < total_frames && g0 + jj >= 0)
+            a.logmag[(size_t)(m0 + rr) * kCqtBins + g0 + jj] = tile[rr * kTilePitch + jj];
+        }
+      }
+      __syncwarp();  // the staging tile is reused by the next item
       // per-window min / max: one atomic pair per warp when the whole warp sits in one window
       const int b0 = __shfl_sync(0xffffffffu, b, 0);
       const bool uniform = __all_sync(0xffffffffu, b == b0);
