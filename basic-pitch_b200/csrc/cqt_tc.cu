@@ -42,7 +42,8 @@ constexpr int kStages = 2;
 constexpr int kProducers = 256;  // 8 producer warps: thread = (row, half of the 8 k-chunks)
 constexpr int kThreads = kProducers + 32 + 128;
 constexpr int kTilePitch = 37;                    // epilogue staging: [4 warps][32 rows][36 bins + 1]
-constexpr int kSmemBytes = kStages * kStageBytes + 256 + 4 * 32 * kTilePitch * 4;
+constexpr int kStgPitch = 68;                     // producer staging: [128 rows][64 taps + 4] fp32
+constexpr int kSmemBytes = kStages * kStageBytes + 256 + 4 * 32 * kTilePitch * 4 + kMTile * kStgPitch * 4 + kMTile * 24;
 }  // namespace cq
 
 static inline uint16_t f2bf_rn(float x) {
@@ -86,6 +87,11 @@ __device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&v)[1
         "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
       : "r"(taddr));
 }
+
+struct RowP {  // where one frame row of the current item reads its signal (producer scratch in shared memory)
+  const float* src;
+  int i0, lo, hi, live;
+};
 
 struct CqtTcArgs {
   const float* audio;
@@ -136,62 +142,99 @@ __global__ void __launch_bounds__(cq::kThreads, 1) cqt_tc_kernel(const CqtTcArgs
   const int total_frames = a.n_windows * kFrames;
 
   if (warp >= 4 && warp < kMmaWarp) {
-    // ------------------------------ producers: thread = (frame row, half of the k-chunks) ------------------------------
+    // ------------------------------ producers ------------------------------
+    // Phase A (lanes along the taps): warp pw gathers rows 16 pw .. 16 pw + 15 of the chunk, two rows (2 x 64 taps) per
+    // 128-bit load instruction, into the staging tile S[row][64 taps] -- a load instruction touches 4-6 cache lines
+    // instead of 32 (one per row), which is what the LSU pipe was saturated with.  Phase B (lanes along the rows): thread
+    // (row, half) reads its 32 taps back, splits them three ways and writes the K-major operand tile.
     const int ptid = threadIdx.x - 128;  // producer thread 0..255
-    const int r = ptid & 127;
-    const int khalf = ptid >> 7;
+    const int pw = ptid >> 5;
+    const int r = 16 * pw + (lane & 15);  // phase B: the warp converts the 16 rows it gathered, no block-wide barrier
+    const int khalf = lane >> 4;
+    float* stg = reinterpret_cast<float*>(smem + kStages * kStageBytes + 256 + 4 * 32 * kTilePitch * 4);  // [128][kStgPitch]
+    RowP* rowp = reinterpret_cast<RowP*>(smem + kStages * kStageBytes + 256 + 4 * 32 * kTilePitch * 4 +
+                                         kMTile * kStgPitch * 4) + 16 * pw;  // this warp's 16 rows
     uint32_t stage = 0, ph = 0;
     for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
       const int mt = it / kOctaves, o = it % kOctaves;
       const int hop = 256 >> o;
       const int len = octave_len(o);
-      const int m = mt * kMTile + r;
-      const bool live = m < total_frames;
-      const int b = live ? m / kFrames : 0;
-      const int t = live ? m - b * kFrames : 0;
-      const float* src;
-      int lo = 0, hi = len;
-      if (o == 0) {
-        if (a.desc) {
-          const WinDesc d = a.desc[b];
-          src = a.audio + d.base;
-          lo = d.lo;
-          hi = d.hi;
+      __syncwarp();
+      if (lane < 16) {  // per item: where row 16 pw + lane reads its signal
+        const int m = mt * kMTile + 16 * pw + lane;
+        RowP p;
+        p.live = m < total_frames;
+        const int b = p.live ? m / kFrames : 0;
+        const int t = m - b * kFrames;
+        p.lo = 0;
+        p.hi = len;
+        if (o == 0) {
+          if (a.desc) {
+            const WinDesc d = a.desc[b];
+            p.src = a.audio + d.base;
+            p.lo = d.lo;
+            p.hi = d.hi;
+          } else {
+            p.src = a.audio + (long long)b * kWinSamples;
+          }
         } else {
-          src = a.audio + (long long)b * kWinSamples;
+          p.src = a.chain + (size_t)b * kChainStride + chain_off(o);
         }
-      } else {
-        src = a.chain + (size_t)b * kChainStride + chain_off(o);
+        p.i0 = t * hop - 128;  // signal index of tap 0 of this frame
+        rowp[lane] = p;
       }
-      const int i0 = t * hop - 128;  // signal index of tap 0 of this frame
+      __syncwarp();
       for (int c = 0; c < kTaps / kKc; ++c) {
-        // this thread's 32 taps of the chunk: issued before the wait for a free stage, so the load latency overlaps it
-        const int ib = i0 + c * kKc;
-        const bool interior = live && ib >= lo && ib + kKc <= hi && ib >= 0 && ib + kKc <= len;
-        const bool vec = interior && ((reinterpret_cast<uintptr_t>(src + ib) & 15) == 0);
-        const int j0 = 32 * khalf;
         float xs[32];
-        if (__all_sync(0xffffffffu, vec)) {  // 16-byte aligned interior rows (hop >= 4): eight 128-bit loads in flight
-          const float4* p4 = reinterpret_cast<const float4*>(src + ib + j0);
+        unsigned vmask = 0;  // row pairs that took the vector path (warp-uniform)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          // rows 2i, 2i + 1 of the warp's 16; vector path: lane -> (row of the pair, 4 taps)
+          const RowP p = rowp[2 * i + (lane >> 4)];
+          const int ibv = p.i0 + c * kKc;  // signal index of the row's first tap in this chunk
+          const bool okv = p.live && ibv >= p.lo && ibv + kKc <= p.hi && ibv >= 0 && ibv + kKc <= len &&
+                           ((reinterpret_cast<uintptr_t>(p.src + ibv) & 15) == 0);
+          if (__all_sync(0xffffffffu, okv)) {
+            vmask |= 1u << i;
+            const float4 v = __ldg(reinterpret_cast<const float4*>(p.src + ibv) + (lane & 15));
+            xs[4 * i] = v.x, xs[4 * i + 1] = v.y, xs[4 * i + 2] = v.z, xs[4 * i + 3] = v.w;
+          } else {
+            // general path (unaligned low octaves, rows that touch the signal ends): reflect padding, zeros outside
+            // [lo, hi); four loads of (row, 32 consecutive taps)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const RowP pq = rowp[2 * i + (q >> 1)];
+              int idx = pq.i0 + c * kKc + (q & 1) * 32 + lane;
+              float xv = 0.f;
+              if (pq.live) {
+                if (idx < 0) idx = -idx;
+                if (idx >= len) idx = 2 * (len - 1) - idx;
+                if (idx >= pq.lo && idx < pq.hi) xv = __ldg(pq.src + idx);
+              }
+              xs[4 * i + q] = xv;
+            }
+          }
+        }
+        __syncwarp();  // the warp's 16 staging rows are free (phase B of its previous chunk is done)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          if ((vmask >> i) & 1u) {  // lanes hold (row of the pair, 4 taps)
+            *reinterpret_cast<float4*>(stg + (16 * pw + 2 * i + (lane >> 4)) * kStgPitch + 4 * (lane & 15)) =
+                make_float4(xs[4 * i], xs[4 * i + 1], xs[4 * i + 2], xs[4 * i + 3]);
+          } else {  // lanes hold 4 x (row, tap)
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              stg[(16 * pw + 2 * i + (q >> 1)) * kStgPitch + (q & 1) * 32 + lane] = xs[4 * i + q];
+          }
+        }
+        __syncwarp();  // rows complete
+        // phase B: this thread's 32 taps of row r
+        {
+          const float4* sp = reinterpret_cast<const float4*>(stg + r * kStgPitch + 32 * khalf);
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const float4 v = __ldg(p4 + i);
+            const float4 v = sp[i];
             xs[4 * i] = v.x, xs[4 * i + 1] = v.y, xs[4 * i + 2] = v.z, xs[4 * i + 3] = v.w;
-          }
-        } else if (__all_sync(0xffffffffu, interior)) {  // hop 2 / 1: overlapping rows, mostly L1 hits
-#pragma unroll
-          for (int j = 0; j < 32; ++j) xs[j] = __ldg(src + ib + j0 + j);
-        } else {  // rows that touch the ends of the signal: reflect padding, zeros outside [lo, hi)
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            int idx = ib + j0 + j;
-            float xv = 0.f;
-            if (live) {
-              if (idx < 0) idx = -idx;
-              if (idx >= len) idx = 2 * (len - 1) - idx;
-              if (idx >= lo && idx < hi) xv = __ldg(src + idx);
-            }
-            xs[j] = xv;
           }
         }
         mbar_wait(empty + stage, ph ^ 1);
