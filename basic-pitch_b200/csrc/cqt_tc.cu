@@ -39,11 +39,13 @@ constexpr int kAPlane = (kKc / 8) * kMTile * 16;  // 16384 B : [8 k-chunks of 8]
 constexpr int kWPlane = (kKc / 8) * kN * 16;      // 10240 B : [8][80][16 B]
 constexpr int kStageBytes = 3 * kAPlane + 3 * kWPlane;  // 79872
 constexpr int kStages = 2;
-constexpr int kProducers = 256;  // 8 producer warps: thread = (row, half of the 8 k-chunks)
+constexpr int kRowsPerWarp = 8;   // rows of the M-tile a producer warp gathers and converts
+constexpr int kProducers = 32 * kMTile / kRowsPerWarp;  // 16 producer warps (more warps in flight hide the gather latency)
 constexpr int kThreads = kProducers + 32 + 128;
 constexpr int kTilePitch = 37;                    // epilogue staging: [4 warps][32 rows][36 bins + 1]
 constexpr int kStgPitch = 68;                     // producer staging: [128 rows][64 taps + 4] fp32
 constexpr int kSmemBytes = kStages * kStageBytes + 256 + 4 * 32 * kTilePitch * 4 + kMTile * kStgPitch * 4 + kMTile * 24;
+static_assert(kThreads <= 1024 && kRowsPerWarp % 2 == 0 && (kKc * kRowsPerWarp / 32) % 8 == 0, "producer geometry");
 }  // namespace cq
 
 static inline uint16_t f2bf_rn(float x) {
@@ -116,7 +118,7 @@ __global__ void __launch_bounds__(cq::kThreads, 1) cqt_tc_kernel(const CqtTcArgs
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);  // broadcast: warp-uniform role branches and loop state
   const int lane = threadIdx.x & 31;
-  constexpr int kMmaWarp = 12;
+  constexpr int kMmaWarp = 4 + kProducers / 32;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) {
@@ -143,25 +145,28 @@ __global__ void __launch_bounds__(cq::kThreads, 1) cqt_tc_kernel(const CqtTcArgs
 
   if (warp >= 4 && warp < kMmaWarp) {
     // ------------------------------ producers ------------------------------
-    // Phase A (lanes along the taps): warp pw gathers rows 16 pw .. 16 pw + 15 of the chunk, two rows (2 x 64 taps) per
+    // Phase A (lanes along the taps): warp pw gathers rows RW pw .. RW pw + RW - 1 of the chunk, two rows (2 x 64 taps) per
     // 128-bit load instruction, into the staging tile S[row][64 taps] -- a load instruction touches 4-6 cache lines
     // instead of 32 (one per row), which is what the LSU pipe was saturated with.  Phase B (lanes along the rows): thread
     // (row, half) reads its 32 taps back, splits them three ways and writes the K-major operand tile.
-    const int ptid = threadIdx.x - 128;  // producer thread 0..255
+    constexpr int RW = kRowsPerWarp, NI = RW / 2;  // row pairs per warp
+    constexpr int KQ = 32 / RW;                    // phase B: lanes per row
+    constexpr int TPL = kKc / KQ;                  // taps per lane in phase B (a multiple of 8)
+    const int ptid = threadIdx.x - 128;            // producer thread
     const int pw = ptid >> 5;
-    const int r = 16 * pw + (lane & 15);  // phase B: the warp converts the 16 rows it gathered, no block-wide barrier
-    const int khalf = lane >> 4;
+    const int r = RW * pw + (lane % RW);  // phase B: the warp converts the rows it gathered, no block-wide barrier
+    const int kq = lane / RW;
     float* stg = reinterpret_cast<float*>(smem + kStages * kStageBytes + 256 + 4 * 32 * kTilePitch * 4);  // [128][kStgPitch]
     RowP* rowp = reinterpret_cast<RowP*>(smem + kStages * kStageBytes + 256 + 4 * 32 * kTilePitch * 4 +
-                                         kMTile * kStgPitch * 4) + 16 * pw;  // this warp's 16 rows
+                                         kMTile * kStgPitch * 4) + RW * pw;  // this warp's rows
     uint32_t stage = 0, ph = 0;
     for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
       const int mt = it / kOctaves, o = it % kOctaves;
       const int hop = 256 >> o;
       const int len = octave_len(o);
       __syncwarp();
-      if (lane < 16) {  // per item: where row 16 pw + lane reads its signal
-        const int m = mt * kMTile + 16 * pw + lane;
+      if (lane < RW) {  // per item: where row RW pw + lane reads its signal
+        const int m = mt * kMTile + RW * pw + lane;
         RowP p;
         p.live = m < total_frames;
         const int b = p.live ? m / kFrames : 0;
@@ -185,11 +190,11 @@ __global__ void __launch_bounds__(cq::kThreads, 1) cqt_tc_kernel(const CqtTcArgs
       }
       __syncwarp();
       for (int c = 0; c < kTaps / kKc; ++c) {
-        float xs[32];
+        float xs[4 * NI];
         unsigned vmask = 0;  // row pairs that took the vector path (warp-uniform)
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          // rows 2i, 2i + 1 of the warp's 16; vector path: lane -> (row of the pair, 4 taps)
+        for (int i = 0; i < NI; ++i) {
+          // rows 2i, 2i + 1 of the warp's rows; vector path: lane -> (row of the pair, 4 taps)
           const RowP p = rowp[2 * i + (lane >> 4)];
           const int ibv = p.i0 + c * kKc;  // signal index of the row's first tap in this chunk
           const bool okv = p.live && ibv >= p.lo && ibv + kKc <= p.hi && ibv >= 0 && ibv + kKc <= len &&
@@ -215,26 +220,27 @@ __global__ void __launch_bounds__(cq::kThreads, 1) cqt_tc_kernel(const CqtTcArgs
             }
           }
         }
-        __syncwarp();  // the warp's 16 staging rows are free (phase B of its previous chunk is done)
+        __syncwarp();  // the warp's staging rows are free (phase B of its previous chunk is done)
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
+        for (int i = 0; i < NI; ++i) {
           if ((vmask >> i) & 1u) {  // lanes hold (row of the pair, 4 taps)
-            *reinterpret_cast<float4*>(stg + (16 * pw + 2 * i + (lane >> 4)) * kStgPitch + 4 * (lane & 15)) =
+            *reinterpret_cast<float4*>(stg + (RW * pw + 2 * i + (lane >> 4)) * kStgPitch + 4 * (lane & 15)) =
                 make_float4(xs[4 * i], xs[4 * i + 1], xs[4 * i + 2], xs[4 * i + 3]);
           } else {  // lanes hold 4 x (row, tap)
 #pragma unroll
             for (int q = 0; q < 4; ++q)
-              stg[(16 * pw + 2 * i + (q >> 1)) * kStgPitch + (q & 1) * 32 + lane] = xs[4 * i + q];
+              stg[(RW * pw + 2 * i + (q >> 1)) * kStgPitch + (q & 1) * 32 + lane] = xs[4 * i + q];
           }
         }
         __syncwarp();  // rows complete
-        // phase B: this thread's 32 taps of row r
+        // phase B: this lane's TPL taps of row r
+        float xb[TPL];
         {
-          const float4* sp = reinterpret_cast<const float4*>(stg + r * kStgPitch + 32 * khalf);
+          const float4* sp = reinterpret_cast<const float4*>(stg + r * kStgPitch + TPL * kq);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
+          for (int i = 0; i < TPL / 4; ++i) {
             const float4 v = sp[i];
-            xs[4 * i] = v.x, xs[4 * i + 1] = v.y, xs[4 * i + 2] = v.z, xs[4 * i + 3] = v.w;
+            xb[4 * i] = v.x, xb[4 * i + 1] = v.y, xb[4 * i + 2] = v.z, xb[4 * i + 3] = v.w;
           }
         }
         mbar_wait(empty + stage, ph ^ 1);
@@ -244,9 +250,9 @@ __global__ void __launch_bounds__(cq::kThreads, 1) cqt_tc_kernel(const CqtTcArgs
           bulk_g2s(sa + 3 * kAPlane, a.wtc + (size_t)c * (3 * kWPlane / 2), 3 * kWPlane, full + stage);
         }
 #pragma unroll
-        for (int q = 0; q < kKc / 16; ++q) {
-          const int kc = khalf * (kKc / 16) + q;
-          const float* x = xs + 8 * q;
+        for (int q = 0; q < TPL / 8; ++q) {
+          const int kc = kq * (TPL / 8) + q;
+          const float* x = xb + 8 * q;
           __align__(16) __nv_bfloat162 h[4], md[4], l[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
