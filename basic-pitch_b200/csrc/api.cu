@@ -60,12 +60,6 @@ struct DevBuf {
   }
 };
 
-struct UnwrapDesc {
-  long long dst_base;  // first output frame this window contributes to
-  int rows;            // how many of its 142 centre frames are kept (may be <= 0)
-  int pad;
-};
-
 // transposed / interleaved weight layouts derived from the parameter block
 struct DerivedLayout {
   static constexpr int cqt_wt = 0;                           // [256][72] columns: re0,im0,re1,im1,...
@@ -340,8 +334,12 @@ struct ProfScope {
 };
 
 // HCQT + CNN for `nb` windows (nb <= chunk); outputs raw [nb][172][*].
+// note / onset / contour: raw [nb][172][*] outputs.  With `ud` (bp_run_inference_*), the centre frames of every window
+// also go to their unwrapped position in u_note / u_onset / u_contour: fused into the tap-sum kernels on the tensor-core
+// path (then only the raw note rows are still written, the onset conv reads them), separate copies otherwise.
 int forward_chunk(bp_model* m, const float* audio, const WinDesc* desc, int nb, float* note, float* onset,
-                  float* contour, cudaStream_t st) {
+                  float* contour, cudaStream_t st, const UnwrapDesc* ud = nullptr, float* u_note = nullptr,
+                  float* u_onset = nullptr, float* u_contour = nullptr) {
   float* chain = m->chain.p;
   if (m->profile_which >= 0) m->prof_windows += nb;
   if (m->device >= 0 && m->device < 64 && g_const_owner[m->device] != m) {
@@ -372,10 +370,12 @@ int forward_chunk(bp_model* m, const float* audio, const WinDesc* desc, int nb, 
     }
     {
       ProfScope ps(m, 4, st);
-      if (m->path == 1)  // c1 holds the five time-tap planes of the fused conv2
-        launch_contour_tapsum(m->c1.p, m->cw, contour, m->chl.p, cstride, nb, st);
-      else
+      if (m->path == 1) {  // c1 holds the five time-tap planes of the fused conv2
+        launch_contour_tapsum(m->c1.p, m->cw, ud ? u_contour : contour, m->chl.p, cstride, nb, st, ud);
+      } else {
         launch_contour2_tc(m->c1.p, m->cw, contour, m->chl.p, cstride, nb, st);
+        if (ud) unwrap_kernel<<<dim3(16, nb), 256, 0, st>>>(contour, u_contour, ud, kContourBins);
+      }
     }
     {
       ProfScope ps(m, 1, st);
@@ -384,8 +384,8 @@ int forward_chunk(bp_model* m, const float* audio, const WinDesc* desc, int nb, 
     {
       ProfScope ps(m, 4, st);
       launch_conv_tc(m->chl.p, m->tc_note.dev, m->n1.p, nb, cstride, m->n_sms, st);  // -> 21 tap planes
-      launch_note_tapsum(m->n1.p, m->cw, note, nb, st);
-      launch_onset_tapsum(m->o1.p, note, m->cw, onset, nb, st);
+      launch_note_tapsum(m->n1.p, m->cw, note, nb, st, ud, u_note);
+      launch_onset_tapsum(m->o1.p, note, m->cw, ud ? u_onset : onset, nb, st, ud);
     }
   } else {
     {
@@ -407,8 +407,14 @@ int forward_chunk(bp_model* m, const float* audio, const WinDesc* desc, int nb, 
       launch_onset2(note, m->o1.p, m->cw, onset, nb, st);
     }
   }
+  if (ud && m->path == 0) {
+    unwrap_kernel<<<dim3(8, nb), 256, 0, st>>>(note, u_note, ud, kPitches);
+    unwrap_kernel<<<dim3(8, nb), 256, 0, st>>>(onset, u_onset, ud, kPitches);
+    unwrap_kernel<<<dim3(16, nb), 256, 0, st>>>(contour, u_contour, ud, kContourBins);
+  }
   CKL();
   m->launches += 5 + 2 + 1 + (m->path >= 1 ? 7 : 6);  // decimation (4 + tail), min/max init + CQT, log-normalise, convs
+  if (ud) m->launches += m->path == 0 ? 3 : (m->path == 2 ? 1 : 0);  // separate unwrap copies
   m->last_path = m->path;
   return BP_OK;
 }
@@ -646,13 +652,9 @@ int bp_run_inference_device(bp_model_t* m, const float* d_audio, const int64_t* 
   CK(cudaStreamSynchronize(st));  // wd/ud are about to go out of scope (pageable staging)
   for (int64_t c0 = 0; c0 < nwin; c0 += chunk) {
     const int nb = (int)std::min<int64_t>(chunk, nwin - c0);
-    rc = forward_chunk(m, d_audio, m->wdesc.p + c0, nb, m->raw_note.p, m->raw_onset.p, m->raw_contour.p, st);
+    rc = forward_chunk(m, d_audio, m->wdesc.p + c0, nb, m->raw_note.p, m->raw_onset.p, m->raw_contour.p, st,
+                       m->udesc.p + c0, d_note, d_onset, d_contour);
     if (rc) return rc;
-    unwrap_kernel<<<dim3(8, nb), 256, 0, st>>>(m->raw_note.p, d_note, m->udesc.p + c0, kPitches);
-    unwrap_kernel<<<dim3(8, nb), 256, 0, st>>>(m->raw_onset.p, d_onset, m->udesc.p + c0, kPitches);
-    unwrap_kernel<<<dim3(16, nb), 256, 0, st>>>(m->raw_contour.p, d_contour, m->udesc.p + c0, kContourBins);
-    CKL();
-    m->launches += 3;
   }
   m->last_forward_n = std::min<int64_t>(nwin, chunk) == nwin ? nwin : 0;
   return BP_OK;

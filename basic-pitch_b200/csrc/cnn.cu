@@ -324,7 +324,8 @@ __global__ void __launch_bounds__(Cfg::THREADS) conv1_kernel(In in, const float*
 template <int FLT, int HALO, int KH, int PT, int WOUT, bool EXTRA, bool SPLIT>
 __global__ void __launch_bounds__(256) halo_tapsum_kernel(const float* __restrict__ Q, const float* __restrict__ x,
                                                           const float* __restrict__ wx, const float* __restrict__ bias,
-                                                          float* __restrict__ out, SplitOut so) {
+                                                          float* __restrict__ out, SplitOut so,
+                                                          const UnwrapDesc* __restrict__ ud, float* __restrict__ out_raw) {
   __shared__ float tile[32][33];
   constexpr int kTiles = (WOUT + FLT - 1) / FLT, kJ = FLT + 2 * HALO;
   constexpr int kPlane = kJ * kFrames;  // one (tile, dt) plane
@@ -383,7 +384,17 @@ __global__ void __launch_bounds__(256) halo_tapsum_kernel(const float* __restric
   for (int i = 0; i < 4; ++i) {
     const int tl = ty + 8 * i;
     const int t = t0 + tl, f = f0 + tx;
-    if (t < kFrames && f < WOUT) out[((size_t)b * kFrames + t) * WOUT + f] = tile[tx][tl];
+    if (t < kFrames && f < WOUT) {
+      const float v = tile[tx][tl];
+      if (ud) {  // unwrap fused: centre frames go straight to their place in the file's posteriorgram
+        const UnwrapDesc d = ud[b];
+        const int tt = t - kOverlapHalf;
+        if ((unsigned)tt < (unsigned)max(d.rows, 0)) out[(size_t)(d.dst_base + tt) * WOUT + f] = v;
+        if (out_raw) out_raw[((size_t)b * kFrames + t) * WOUT + f] = v;
+      } else {
+        out[((size_t)b * kFrames + t) * WOUT + f] = v;
+      }
+    }
   }
   if (SPLIT && so.planes && threadIdx.x < 128) {  // 32 frames x 4 chunks of 8 bins -> one 16-byte store per plane
     const int tl = threadIdx.x & 31, c = threadIdx.x >> 5;
@@ -460,21 +471,24 @@ void launch_contour2_tc(const float* c1, const CnnWeights& w, float* contour, __
   launch1<Contour2CfgN>(NhwcIn<8, 264>{c1}, w.contour2_wT, w.contour2_b, contour, n, st,
                         SplitOut{chl, rows_total, sp.chunks8, sp.rows_per_window, sp.lead_rows});
 }
-void launch_contour_tapsum(const float* q, const CnnWeights& w, float* contour, __nv_bfloat16* chl, int rows_total, int n,
-                           cudaStream_t st) {
+void launch_contour_tapsum(const float* q, const CnnWeights& w, float* out, __nv_bfloat16* chl, int rows_total, int n,
+                           cudaStream_t st, const UnwrapDesc* ud) {
   const TcConvSpec sp = tc_note_spec();
   halo_tapsum_kernel<16, 2, 5, 2, kContourBins, false, true>
       <<<dim3((kFrames + 31) / 32, (kContourBins + 31) / 32, n), 256, 0, st>>>(
-          q, nullptr, nullptr, w.contour2_b, contour, SplitOut{chl, rows_total, sp.chunks8, sp.rows_per_window, sp.lead_rows});
+          q, nullptr, nullptr, w.contour2_b, out, SplitOut{chl, rows_total, sp.chunks8, sp.rows_per_window, sp.lead_rows}, ud,
+          nullptr);
 }
-void launch_note_tapsum(const float* q, const CnnWeights& w, float* note, int n, cudaStream_t st) {
+void launch_note_tapsum(const float* q, const CnnWeights& w, float* note_raw, int n, cudaStream_t st, const UnwrapDesc* ud,
+                        float* note_unwrapped) {
   halo_tapsum_kernel<4, 1, 7, 3, kPitches, false, false><<<dim3((kFrames + 31) / 32, (kPitches + 31) / 32, n), 256, 0, st>>>(
-      q, nullptr, nullptr, w.note2_b, note, SplitOut{nullptr, 0, 0, 0, 0});
+      q, nullptr, nullptr, w.note2_b, ud ? note_unwrapped : note_raw, SplitOut{nullptr, 0, 0, 0, 0}, ud, ud ? note_raw : nullptr);
 }
-void launch_onset_tapsum(const float* q, const float* note, const CnnWeights& w, float* onset, int n, cudaStream_t st) {
+void launch_onset_tapsum(const float* q, const float* note_raw, const CnnWeights& w, float* out, int n, cudaStream_t st,
+                         const UnwrapDesc* ud) {
   // channel 0 of the onset conv2 weights multiplies the note posteriorgram (models.py:305: concat[note, onset1])
   halo_tapsum_kernel<4, 1, 3, 1, kPitches, true, false><<<dim3((kFrames + 31) / 32, (kPitches + 31) / 32, n), 256, 0, st>>>(
-      q, note, w.onset2_wT, w.onset2_b, onset, SplitOut{nullptr, 0, 0, 0, 0});
+      q, note_raw, w.onset2_wT, w.onset2_b, out, SplitOut{nullptr, 0, 0, 0, 0}, ud, nullptr);
 }
 void launch_note1(const float* contour, const CnnWeights& w, float* n1, int n, cudaStream_t st) {
   launch<Note1Cfg>(PlanarIn<1, 264>{contour}, w.note1_wT, w.note1_b, n1, n, st);

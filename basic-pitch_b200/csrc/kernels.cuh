@@ -78,16 +78,25 @@ void launch_split(const float* src, __nv_bfloat16* dst, const TcConvSpec& spec, 
 // halo_tapsum_kernel) instead of storing the channels-last activations
 void launch_conv_tc(const __nv_bfloat16* data, const TcConvDev& dev, float* out, int n_windows, int rows_stride, int n_sms,
                     cudaStream_t st, bool fuse_next = false);
-void launch_contour_tapsum(const float* q, const CnnWeights& w, float* contour, __nv_bfloat16* chl, int rows_total,
-                           int n_windows, cudaStream_t st);
+// Where window w's centre frames go in the unwrapped (per-file) posteriorgrams (reference: inference.py:247-279).
+struct UnwrapDesc {
+  long long dst_base;  // first output frame this window contributes to
+  int rows;            // how many of its 142 centre frames are kept (may be <= 0)
+  int pad;
+};
+// The tap-sum kernels write [B][172][*] rows, or, with `ud`, only the centre frames of every window straight to their
+// unwrapped position in `out` (note: additionally the raw rows to `note_raw`, which the onset conv reads).
+void launch_contour_tapsum(const float* q, const CnnWeights& w, float* out, __nv_bfloat16* chl, int rows_total,
+                           int n_windows, cudaStream_t st, const UnwrapDesc* ud = nullptr);
 // contour conv2 on the channels-last output of the tensor-core contour conv; also emits the bf16 hi/lo split of the
 // contour posteriorgram in the layout of tc_note_spec()
 void launch_contour2_tc(const float* c1_nhwc, const CnnWeights& w, float* contour, __nv_bfloat16* chl, int rows_total,
                         int n_windows, cudaStream_t st);
 // second convs after the fused channel reduction: shifted sums over the tap planes (+ the note input of the onset conv)
-void launch_note_tapsum(const float* p21, const CnnWeights& w, float* note, int n_windows, cudaStream_t st);
-void launch_onset_tapsum(const float* p9, const float* note, const CnnWeights& w, float* onset, int n_windows,
-                         cudaStream_t st);
+void launch_note_tapsum(const float* q, const CnnWeights& w, float* note_raw, int n_windows, cudaStream_t st,
+                        const UnwrapDesc* ud = nullptr, float* note_unwrapped = nullptr);
+void launch_onset_tapsum(const float* q, const float* note_raw, const CnnWeights& w, float* out, int n_windows,
+                         cudaStream_t st, const UnwrapDesc* ud = nullptr);
 
 // ---- cqt_tc.cu (tcgen05 path of the constant-Q projection, three-way bf16 split) ----------------------------
 void build_cqt_tc_weights(const float* cqt_real, const float* cqt_imag, std::vector<uint16_t>& out);
