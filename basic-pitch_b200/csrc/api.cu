@@ -93,6 +93,15 @@ __global__ void derive_kernel(const float* __restrict__ P, float* __restrict__ D
   tr(ParamLayout::onset2_w, DerivedLayout::onset2_wT, 1, 297);
 }
 
+__global__ void desc_upload_kernel(const int4* __restrict__ a_src, int4* __restrict__ a_dst, const int4* __restrict__ b_src,
+                                   int4* __restrict__ b_dst, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    a_dst[i] = a_src[i];
+    b_dst[i] = b_src[i];
+  }
+}
+
 // centre 142 frames of every window -> unwrapped position (reference: inference.py:247-279)
 __global__ void unwrap_kernel(const float* __restrict__ raw, float* __restrict__ out, const UnwrapDesc* __restrict__ ud,
                               int width) {
@@ -163,6 +172,11 @@ struct bp_model {
   int64_t last_forward_n = 0;
   int last_path = 0;
   // optional per-kernel timing (bench.py roofline): CUDA events around one kernel family
+  WinDesc* h_wd = nullptr;        // pinned staging of the window / unwrap descriptors (bp_run_inference_device)
+  UnwrapDesc* h_ud = nullptr;
+  size_t h_desc_cap = 0;
+  cudaEvent_t desc_ev = nullptr;
+  bool desc_pending = false;
   int profile_which = -1;  // -1 off; 0 contour1, 1 onset1, 2 cqt, 3 decimate chain, 4 small convs, 5 decode, 6 note finish
   std::vector<cudaEvent_t> prof_ev;
   size_t prof_used = 0;
@@ -532,6 +546,9 @@ void bp_model_destroy(bp_model_t* m) {
   if (m->d_derived) cudaFree(m->d_derived);
   if (m->d_gauss) cudaFree(m->d_gauss);
   for (cudaEvent_t e : m->prof_ev) cudaEventDestroy(e);
+  if (m->desc_ev) cudaEventDestroy(m->desc_ev);
+  if (m->h_wd) cudaFreeHost(m->h_wd);
+  if (m->h_ud) cudaFreeHost(m->h_ud);
   for (cudaEvent_t e : m->copy_ev) cudaEventDestroy(e);
   if (m->copy_stream) cudaStreamDestroy(m->copy_stream);
   if (m->stream) cudaStreamDestroy(m->stream);
@@ -647,9 +664,36 @@ int bp_run_inference_device(bp_model_t* m, const float* d_audio, const int64_t* 
   CK(m->raw_contour.reserve((size_t)nbmax * kFrames * kContourBins));
   CK(m->wdesc.reserve(nwin));
   CK(m->udesc.reserve(nwin));
-  CK(cudaMemcpyAsync(m->wdesc.p, wd.data(), sizeof(WinDesc) * nwin, cudaMemcpyHostToDevice, st));
-  CK(cudaMemcpyAsync(m->udesc.p, ud.data(), sizeof(UnwrapDesc) * nwin, cudaMemcpyHostToDevice, st));
-  CK(cudaStreamSynchronize(st));  // wd/ud are about to go out of scope (pageable staging)
+  // descriptors go through pinned staging owned by the model, guarded by an event that completes with the copy (not with
+  // the kernels queued behind it): no stream synchronisation here, so back-to-back calls (the sub-batches of
+  // bp_transcribe_host) keep the GPU queue full
+  if (m->desc_pending) {
+    CK(cudaEventSynchronize(m->desc_ev));
+    m->desc_pending = false;
+  }
+  if ((size_t)nwin > m->h_desc_cap) {
+    if (m->h_wd) cudaFreeHost(m->h_wd);
+    if (m->h_ud) cudaFreeHost(m->h_ud);
+    m->h_wd = nullptr;
+    m->h_ud = nullptr;
+    m->h_desc_cap = 0;
+    const size_t cap = std::max<size_t>((size_t)nwin, 4096);
+    CK(cudaMallocHost(&m->h_wd, sizeof(WinDesc) * cap));
+    CK(cudaMallocHost(&m->h_ud, sizeof(UnwrapDesc) * cap));
+    m->h_desc_cap = cap;
+  }
+  if (!m->desc_ev) CK(cudaEventCreateWithFlags(&m->desc_ev, cudaEventDisableTiming));
+  std::memcpy(m->h_wd, wd.data(), sizeof(WinDesc) * nwin);
+  std::memcpy(m->h_ud, ud.data(), sizeof(UnwrapDesc) * nwin);
+  // a kernel reads the pinned (device-mapped) staging directly: a copy-engine transfer would queue behind the audio
+  // uploads that bp_transcribe_host has in flight on the copy stream
+  static_assert(sizeof(WinDesc) == 16 && sizeof(UnwrapDesc) == 16, "descriptor upload moves 16-byte records");
+  desc_upload_kernel<<<(unsigned)((nwin + 255) / 256), 256, 0, st>>>(
+      reinterpret_cast<const int4*>(m->h_wd), reinterpret_cast<int4*>(m->wdesc.p), reinterpret_cast<const int4*>(m->h_ud),
+      reinterpret_cast<int4*>(m->udesc.p), (int)nwin);
+  CKL();
+  CK(cudaEventRecord(m->desc_ev, st));
+  m->desc_pending = true;
   for (int64_t c0 = 0; c0 < nwin; c0 += chunk) {
     const int nb = (int)std::min<int64_t>(chunk, nwin - c0);
     rc = forward_chunk(m, d_audio, m->wdesc.p + c0, nb, m->raw_note.p, m->raw_onset.p, m->raw_contour.p, st,
@@ -886,16 +930,21 @@ int bp_transcribe_host(bp_model_t* m, const float* h_audio, const int64_t* h_sam
   // stream up front, the compute stream waits for sub-batch k only, so the PCIe transfer of k+1.. overlaps the kernels.
   std::vector<int> cut{0};
   {
+    // Sub-batches end on file boundaries and do not spill a few windows into an extra internal chunk: the first two
+    // hold at most one chunk of windows (their copies are the ones that cannot be hidden), the next two at most two,
+    // the rest at most four.
     int64_t w = 0;
     for (int i = 0; i < n_files; ++i) {
-      // the first sub-batch is small (its copy cannot be hidden), the others span about 4 internal chunks
-      const int64_t limit = (cut.size() == 1 ? 1 : 4) * (int64_t)m->chunk;
-      w += bp_num_windows(rel[i + 1] - rel[i]);
-      if (w >= limit || i + 1 == n_files) {
-        cut.push_back(i + 1);
+      const size_t k = cut.size() - 1;
+      const int64_t limit = (k < 2 ? 1 : (k < 4 ? 2 : 4)) * (int64_t)m->chunk;
+      const int64_t nw = bp_num_windows(rel[i + 1] - rel[i]);
+      if (w > 0 && w + nw > limit) {
+        cut.push_back(i);
         w = 0;
       }
+      w += nw;
     }
+    cut.push_back(n_files);
   }
   const size_t n_sub = cut.size() - 1;
   while (m->copy_ev.size() < n_sub) {

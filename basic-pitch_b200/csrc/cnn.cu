@@ -342,10 +342,21 @@ __global__ void __launch_bounds__(256) halo_tapsum_kernel(const float* __restric
   for (int dt = 0; dt < KH; ++dt)
     if ((unsigned)(t + dt - PT) < (unsigned)kFrames) dmask |= 1u << dt;
   if (t >= kFrames) dmask = 0;
+  // onset: the 3 x 3 taps over the note posteriorgram (frequency-fastest rows) are staged through shared memory so that
+  // the global reads run along f while the lanes of the sum below run along t
+  __shared__ float xs[EXTRA ? 34 : 1][EXTRA ? 35 : 1];
   float wxr[EXTRA ? 9 : 1];
   if (EXTRA) {
 #pragma unroll
     for (int k = 0; k < 9; ++k) wxr[k] = __ldg(wx + k);
+    for (int idx = threadIdx.x; idx < 34 * 34; idx += 256) {
+      const int rr = idx / 34, cc = idx - rr * 34;
+      const int tt = t0 - 1 + rr, ff = f0 - 1 + cc;
+      xs[rr][cc] = ((unsigned)tt < (unsigned)kFrames && (unsigned)ff < (unsigned)WOUT)
+                       ? __ldg(x + ((size_t)b * kFrames + tt) * WOUT + ff)
+                       : 0.f;
+    }
+    __syncthreads();
   }
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -366,15 +377,11 @@ __global__ void __launch_bounds__(256) halo_tapsum_kernel(const float* __restric
         for (int dt = 0; dt < KH; ++dt)
           if ((dmask >> dt) & 1u) acc += __ldg(q2 + dt * kTapStep);
       }
-      if (EXTRA) {
-        const float* xr = x + ((size_t)b * kFrames + (t - PT)) * WOUT + f - 1;
+      if (EXTRA) {  // (KH == 3, PT == 1; frames / bins outside the image are zeros in xs)
 #pragma unroll
-        for (int dt = 0; dt < KH; ++dt)
-          if ((dmask >> dt) & 1u) {
+        for (int dt = 0; dt < 3; ++dt)
 #pragma unroll
-            for (int df = 0; df < 3; ++df)
-              if ((unsigned)(f + df - 1) < (unsigned)WOUT) acc = fmaf(__ldg(xr + dt * WOUT + df), wxr[dt * 3 + df], acc);
-          }
+          for (int df = 0; df < 3; ++df) acc = fmaf(xs[tx + dt][fl + df], wxr[dt * 3 + df], acc);
       }
     }
     tile[fl][tx] = __fdividef(1.f, 1.f + __expf(-acc));
