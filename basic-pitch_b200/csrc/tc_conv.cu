@@ -367,8 +367,13 @@ __device__ __forceinline__ void reduce_store(uint32_t taddr, const float2 (&red)
 #pragma unroll
         for (int p = 0; p < NP; ++p) {
           const float2 w = red[c][df][p];
-          ffma2(accw[2 - df][p], o0, w);  // input bin fl feeds output offset j = fl - df + 2
-          ffma2(accw[3 - df][p], o1, w);
+          if ((KH & 1) && p == NP - 1) {  // odd last time tap: a scalar FMA instead of half an empty pair
+            accw[2 - df][p].x = fmaf(o0, w.x, accw[2 - df][p].x);
+            accw[3 - df][p].x = fmaf(o1, w.x, accw[3 - df][p].x);
+          } else {
+            ffma2(accw[2 - df][p], o0, w);  // input bin fl feeds output offset j = fl - df + 2
+            ffma2(accw[3 - df][p], o1, w);
+          }
         }
     }
     float* d = dst + (size_t)(2 * h) * kFrames;

@@ -301,6 +301,44 @@ def test_transcribe_batch_equals_per_file(model):
     assert sum(len(r["start"]) for r in res) > 20
 
 
+def test_transcribe_host_sub_batches_equal_device_path(model):
+    """bp_transcribe_host splits a large batch into sub-batches on file boundaries (copies overlap the kernels) and runs
+    partial internal chunks; its note events must equal those of one bp_transcribe_device call on the same audio, and the
+    ragged file lengths exercise windows that cross sub-batch / chunk boundaries."""
+    import torch
+
+    from basic_pitch_b200 import engine, synth
+
+    chunk = int(model._lib.bp_model_chunk_windows(model.handle))
+    base = [synth.random_notes_clip(4.0 + 0.7 * (i % 5), seed=100 + i) for i in range(10)]
+    clips = [base[i % len(base)] for i in range(160)]  # ~ 3 windows each -> several sub-batches of 1, 1, 2 chunks
+    n_windows = sum(int(model._lib.bp_num_windows(len(c))) for c in clips)
+    assert n_windows > 2 * chunk
+    packed = engine.PackedAudio(clips, pinned=True)
+    n_frames = sum(int(model._lib.bp_num_frames(len(c))) for c in clips)
+    out_h = engine.NoteBuffers(len(clips), max(4096, 2 * n_frames), max(65536, 24 * n_frames))
+    out_d = engine.NoteBuffers(len(clips), max(4096, 2 * n_frames), max(65536, 24 * n_frames))
+    nh = engine.transcribe_packed_host(model, packed, out_h)
+    d_audio = packed.to_device(model.device)
+    nd = engine.transcribe_packed_device(model, d_audio, packed.offsets, out_d)
+    torch.cuda.synchronize()
+    assert nh == nd > 200
+    for k in ("note_off", "frame_off"):
+        np.testing.assert_array_equal(out_h.a[k][: len(clips) + 1], out_d.a[k][: len(clips) + 1], err_msg=k)
+    for k in ("start", "end", "pitch", "amp"):
+        np.testing.assert_array_equal(out_h.a[k][:nh], out_d.a[k][:nh], err_msg=k)
+    nb = int(out_h.a["bend_off"][nh])
+    np.testing.assert_array_equal(out_h.a["bend_off"][: nh + 1], out_d.a["bend_off"][: nh + 1])
+    np.testing.assert_array_equal(out_h.a["bends"][:nb], out_d.a["bends"][:nb])
+    # identical clips give identical events wherever they sit in the batch
+    no = out_h.a["note_off"]
+    for i in range(len(base), len(clips)):
+        j = i % len(base)
+        assert no[i + 1] - no[i] == no[j + 1] - no[j]
+        np.testing.assert_array_equal(out_h.a["start"][no[i] : no[i + 1]], out_h.a["start"][no[j] : no[j + 1]])
+        np.testing.assert_array_equal(out_h.a["amp"][no[i] : no[i + 1]], out_h.a["amp"][no[j] : no[j + 1]])
+
+
 def test_dense_polyphony_batch_bit_exact(model):
     """BASELINE configs[4]: 88-voice chords, several 10 s clips in one batch; decode (incl. pitch bends) bit-identical to
     the oracle decode on the same GPU posteriorgrams."""
