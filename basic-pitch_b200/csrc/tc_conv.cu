@@ -7,21 +7,24 @@
 // conv + ReLU, reference: basic_pitch/models.py:295-304) of the deployed graph, and the harmonic stacking in
 // front of them (reference: basic_pitch/nn.py:69-88), which is folded into the weight operand and never
 // materialised; node 238/239 (note conv1 + ReLU, models.py:270-279) reads the contour posteriorgram instead.
-// One kernel template, three specs (TcConvSpec).  For the two 32-channel layers the epilogue also applies the
-// channel reduction of the following single-output conv (onset conv2 models.py:305-313, note conv2 :282-290):
-// it emits P[tap][t][f] = sum_c relu(conv1)[c][t][f] * w2[c][tap], so the 32-channel activations never reach
-// HBM and the second conv degenerates to a sum of 3 / 7 time-tap planes (cnn.cu: halo_tapsum_kernel).
+// One kernel template, three specs (TcConvSpec).  The epilogue (EPI 1 / 2 / 3 = onset / note / contour) also reduces
+// the FOLLOWING single-output convolution (onset conv2 models.py:305-313, note conv2 :282-290, contour conv2 :254-262)
+// over its input channels and frequency taps inside the thread that owns the frame and stores time-tap planes with
+// halo columns, so the 8- / 32-channel activations never reach HBM and the second convs degenerate to a sum of 5 / 3 /
+// 7 time-tap planes (cnn.cu: halo_tapsum_kernel).  EPI 0 stores the contour activations channels-last (path 2, tests).
 //
-// Formulation ("Toeplitz along frequency on 16-bin aligned chunks")
+// Formulation ("Toeplitz along frequency on aligned chunks")
 //   rows  m = b*174 + t            time frames of all windows of the chunk, two zero rows between windows
-//   D[m][(fl,co)] (+)= A[m+dt][16q .. 16q+15] x T(ci,dt,off)[16][(fl,co)]
-//     A      the normalised CQT y itself (NOT the 8-channel stack), rows shifted by the time tap dt
+//   D[m][(fl,co)] (+)= A[m+dt][8c .. 8c+15] x T(ci,dt,off)[16][(fl,co)]
+//     A      the normalised CQT y itself (NOT the 8-channel stack), rows shifted by the time tap dt; K = 16 bins that
+//            start on an 8-bin chunk of the k-chunk-major layout
 //     T      16 x 128 "weight tile": T[k][(fl,co)] = W[co][ci][dt][df] with
-//            df = (16q + k) - shift_ci - SF*(ft*FLT + fl) + PL   (zero outside 0 <= df < KW and outside the
-//            stacked image 0 <= g < 264: tiles that touch its edges are boundary variants)
-//            N = FLT output bins x COUT channels = 128 (contour 16 x 8, onset 4 x 32); a tile depends on
-//            (ci, dt, 16q - SF*FLT*ft), so frequency tiles SF*FLT*d = 16*j bins apart share tiles
-//   every (ft, ci, dt, q) with a non-empty tile is one K=16 MMA step of shape 128 x 128 x 16
+//            df = (8c + k) - shift_ci - SF*(ft*FLT + fl) + PL   (zero outside 0 <= df < KW, outside the stacked image
+//            0 <= g < 264 and outside the bins the step is responsible for)
+//            N = FLT output bins x COUT channels = 128 (contour 16 x 8, onset / note 4 x 32); a tile depends on
+//            (ci, dt, 8c - SF*FLT*ft), so frequency tiles SF*FLT*d = 8*j bins apart share tiles (de-duplicated by
+//            content)
+//   every (ft, ci, dt, c) with a non-empty tile is one K=16 MMA step of shape 128 x 128 x 16
 // Precision: both operands are split x = hi + lo (bf16 each) and three products are accumulated
 // (hi*hi + hi*lo + lo*hi) in fp32, which keeps the posteriorgrams within ~1e-5 of the FP32 path
 // (SURVEY.md Appendix C.4); a single bf16 product would miss the 1e-3 bar.
@@ -37,8 +40,8 @@
 //               base + precomputed offset, 3 x tcgen05.mma per step by one elected lane, tcgen05.commit frees the
 //               weight stage / publishes the accumulators
 //   warps 0-3, 4-7  epilogue, one warpgroup-like set of 4 warps (= the 4 TMEM lane quadrants) per accumulator slot:
-//               tcgen05.ld the accumulator columns, + bias, ReLU, then either a channels-last store (contour) or
-//               the fused 32 -> taps reduction with planar float4 stores (onset, note)
+//               tcgen05.ld the accumulator columns, + bias, ReLU, then the fused reduction of the next conv on packed
+//               FP32 FMAs and time-fastest stores of the tap planes
 #include <cuda_bf16.h>
 
 #include <algorithm>
