@@ -37,6 +37,11 @@ MIDI_VELOCITY_SCALE = 127
 PITCH_BEND_SCALE = 4096
 
 
+# training-time sampling weights of the datasets (reference: constants.py:49-55; training is out of scope, kept so that
+# `from basic_pitch.constants import *` users find the name)
+DATASET_SAMPLING_FREQUENCY = {"MAESTRO": 5, "GuitarSet": 2, "MedleyDB-Pitch": 2, "iKala": 2, "slakh": 2}
+
+
 def _freq_bins(bins_per_semitone: int, base_frequency: float, n_semitones: int) -> np.ndarray:
     step = 2.0 ** (1.0 / (SEMITONES_PER_OCTAVE * bins_per_semitone))
     return base_frequency * step ** np.arange(bins_per_semitone * n_semitones)

@@ -165,6 +165,7 @@ struct bp_model {
   // decode workspace
   DevBuf<long long> d_frame_off, d_slot_off, d_note_base;
   DevBuf<float> energy, d_amp;
+  DevBuf<double> d_onset64;
   DevBuf<unsigned int> candbits, max_onset;
   DevBuf<unsigned long long> max_fd;
   DevBuf<int> note_count, slot_start, slot_end, slot_pitch, overflow, d_note_off, d_start, d_end, d_pitch, d_bend_off,
@@ -537,7 +538,7 @@ void bp_model_destroy(bp_model_t* m) {
   m->energy.release(); m->d_amp.release(); m->candbits.release(); m->max_onset.release(); m->max_fd.release();
   m->note_count.release(); m->slot_start.release(); m->slot_end.release(); m->slot_pitch.release();
   m->overflow.release(); m->d_note_off.release(); m->d_start.release(); m->d_end.release(); m->d_pitch.release();
-  m->d_bend_off.release(); m->d_bends.release();
+  m->d_bend_off.release(); m->d_bends.release(); m->d_onset64.release();
   m->yhl.release();
   m->chl.release();
   m->cqt_wtc.release();
@@ -865,6 +866,85 @@ int bp_decode_device(bp_model_t* m, const float* d_note, const float* d_onset, c
   CK(cudaMemcpyAsync(notes->amplitude, m->d_amp.p, sizeof(float) * n_notes, cudaMemcpyDeviceToHost, st));
   if (with_bends && n_bends > 0)
     CK(cudaMemcpyAsync(notes->bends, m->d_bends.p, sizeof(int) * n_bends, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return BP_OK;
+}
+
+int bp_infer_onsets_host(bp_model_t* m, const float* h_onset, const float* h_note, int64_t n_frames, double* h_out) {
+  if (!m || n_frames < 0) return fail(BP_E_INVALID, "bp_infer_onsets_host: bad argument");
+  if (n_frames == 0) return BP_OK;
+  if (!h_onset || !h_note || !h_out) return fail(BP_E_INVALID, "bp_infer_onsets_host: null array");
+  DeviceGuard g(m->device);
+  cudaStream_t st = m->stream;
+  const size_t cells = (size_t)n_frames * kPitches;
+  CK(m->st_note.reserve(cells + 1));
+  CK(m->st_onset.reserve(cells + 1));
+  CK(m->energy.reserve(cells + 1));
+  CK(m->candbits.reserve(cells / 32 + 2));
+  CK(m->max_onset.reserve(1));
+  CK(m->max_fd.reserve(1));
+  CK(m->d_frame_off.reserve(2));
+  CK(m->d_onset64.reserve(cells));
+  const long long foff[2] = {0, (long long)n_frames};
+  CK(cudaMemcpyAsync(m->d_frame_off.p, foff, sizeof(foff), cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(m->st_note.p, h_note, sizeof(float) * cells, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(m->st_onset.p, h_onset, sizeof(float) * cells, cudaMemcpyHostToDevice, st));
+  DecodeBuffers b{};
+  b.frame_off = m->d_frame_off.p;
+  b.energy = m->energy.p;
+  b.candbits = m->candbits.p;
+  b.max_onset = m->max_onset.p;
+  b.max_fd = m->max_fd.p;
+  launch_infer_onsets(m->st_note.p, m->st_onset.p, b, 1, (long long)n_frames, m->d_onset64.p, st);
+  CKL();
+  m->launches += 2;
+  CK(cudaMemcpyAsync(h_out, m->d_onset64.p, sizeof(double) * cells, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return BP_OK;
+}
+
+int bp_pitch_bends_host(bp_model_t* m, const float* h_contour, int64_t n_frames, int32_t n_notes, const int32_t* h_start,
+                        const int32_t* h_end, const int32_t* h_pitch_midi, int32_t* h_bend_off, int32_t* h_bends,
+                        int64_t bend_capacity) {
+  if (!m || n_frames < 0 || n_notes < 0 || !h_bend_off) return fail(BP_E_INVALID, "bp_pitch_bends_host: bad argument");
+  h_bend_off[0] = 0;
+  if (n_notes == 0) return BP_OK;
+  if (!h_contour || !h_start || !h_end || !h_pitch_midi) return fail(BP_E_INVALID, "bp_pitch_bends_host: null array");
+  long long total = 0;
+  for (int j = 0; j < n_notes; ++j) {
+    if (h_start[j] < 0 || h_end[j] <= h_start[j] || h_end[j] > n_frames)
+      return fail(BP_E_INVALID, "bp_pitch_bends_host: note frames must satisfy 0 <= start < end <= n_frames");
+    if (h_pitch_midi[j] < 21 || h_pitch_midi[j] >= 21 + kPitches)
+      return fail(BP_E_INVALID, "bp_pitch_bends_host: pitch outside 21..108");
+    total += h_end[j] - h_start[j];
+    if (total > 0x7fffffffLL) return fail(BP_E_CAPACITY, "bp_pitch_bends_host: more than 2^31 pitch-bend values");
+    h_bend_off[j + 1] = (int32_t)total;
+  }
+  if (total > bend_capacity) return fail(BP_E_CAPACITY, "bp_pitch_bends_host: bend_capacity too small, need " + std::to_string(total));
+  if (!h_bends) return fail(BP_E_INVALID, "bp_pitch_bends_host: bends array missing");
+  DeviceGuard g(m->device);
+  cudaStream_t st = m->stream;
+  CK(m->st_contour.reserve((size_t)n_frames * kContourBins + 1));
+  CK(m->st_note.reserve((size_t)n_frames * kPitches + 1));  // the kernel also averages the note posteriorgram: zeros here
+  CK(m->d_start.reserve(n_notes));
+  CK(m->d_end.reserve(n_notes));
+  CK(m->d_pitch.reserve(n_notes));
+  CK(m->d_amp.reserve(n_notes));
+  CK(m->d_note_base.reserve(n_notes));
+  CK(m->d_bend_off.reserve(n_notes + 1));
+  CK(m->d_bends.reserve((size_t)total + 1));
+  CK(cudaMemsetAsync(m->st_note.p, 0, sizeof(float) * (size_t)n_frames * kPitches, st));
+  CK(cudaMemsetAsync(m->d_note_base.p, 0, sizeof(long long) * n_notes, st));
+  CK(cudaMemcpyAsync(m->st_contour.p, h_contour, sizeof(float) * (size_t)n_frames * kContourBins, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(m->d_start.p, h_start, sizeof(int) * n_notes, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(m->d_end.p, h_end, sizeof(int) * n_notes, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(m->d_pitch.p, h_pitch_midi, sizeof(int) * n_notes, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(m->d_bend_off.p, h_bend_off, sizeof(int) * (n_notes + 1), cudaMemcpyHostToDevice, st));
+  launch_note_finish(m->st_note.p, m->st_contour.p, m->d_note_base.p, m->d_start.p, m->d_end.p, m->d_pitch.p, m->d_amp.p,
+                     m->d_bend_off.p, m->d_bends.p, n_notes, 1, m->d_gauss, st);
+  CKL();
+  m->launches += 1;
+  CK(cudaMemcpyAsync(h_bends, m->d_bends.p, sizeof(int) * (size_t)total, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
   return BP_OK;
 }

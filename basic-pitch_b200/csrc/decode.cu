@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(256) decode_cand_kernel(const float* __restric
                                                           const unsigned int* __restrict__ max_onset,
                                                           const unsigned long long* __restrict__ max_fd,
                                                           unsigned int* __restrict__ candbits, int lo, int hi, int infer,
-                                                          double onset_thresh) {
+                                                          double onset_thresh, double* __restrict__ onset64_out) {
   __shared__ float s_n[kTileFrames + 4][kPitches + 1];  // note rows g0-3 .. g0+32 (inferred onsets only)
   __shared__ double s_v[kTileFrames + 2][kPitches];     // float64 onset value of rows g0-1 .. g0+32
   __shared__ RowInfo s_row[kTileFrames + 2];
@@ -181,6 +181,12 @@ __global__ void __launch_bounds__(256) decode_cand_kernel(const float* __restric
     s_v[rr][f] = v;
   }
   __syncthreads();
+  if (onset64_out) {  // bp_infer_onsets_host: the float64 onset matrix itself (reference: get_infered_onsets)
+    for (int idx = tid; idx < kTileFrames * kPitches; idx += 256) {
+      const int r = idx / kPitches, f = idx - r * kPitches;
+      if (g0 + r < total) onset64_out[(g0 + r) * kPitches + f] = s_v[r + 1][f];
+    }
+  }
   // strict time peaks >= threshold; a warp ballot is one 32-cell word of the candidate bitmap
   const long long cell0 = g0 * kPitches;  // multiple of 32
   const long long total_cells = total * kPitches;
@@ -444,10 +450,23 @@ void launch_decode_notes(const float* note, const float* onset, const DecodeBuff
     decode_prep_kernel<<<blocks, threads, 0, st>>>(note, onset, b.frame_off, n_files, b.energy, b.max_onset, b.max_fd,
                                                    p.lo_col, p.hi_col);
     decode_cand_kernel<<<blocks, threads, 0, st>>>(note, onset, b.frame_off, n_files, b.max_onset, b.max_fd,
-                                                    b.candbits, p.lo_col, p.hi_col, p.infer_onsets, p.onset_thresh);
+                                                    b.candbits, p.lo_col, p.hi_col, p.infer_onsets, p.onset_thresh, nullptr);
   }
   decode_seq_kernel<<<n_files, kSeqThreads, 0, st>>>(b.frame_off, b.energy, b.candbits, b.slot_off, b.note_count,
                                                      b.note_start, b.note_end, b.note_pitch, b.overflow, p);
+}
+
+// float64 inferred onsets of a batch of files (reference: note_creation.py:289-311): the two cell-parallel kernels of the
+// decode, with the candidate kernel also writing the onset matrix it peak-picks on.
+void launch_infer_onsets(const float* note, const float* onset, const DecodeBuffers& b, int n_files, long long total_frames,
+                         double* out64, cudaStream_t st) {
+  cudaMemsetAsync(b.max_onset, 0, sizeof(unsigned int) * n_files, st);
+  cudaMemsetAsync(b.max_fd, 0, sizeof(unsigned long long) * n_files, st);
+  if (total_frames <= 0) return;
+  const unsigned int blocks = (unsigned int)((total_frames + kTileFrames - 1) / kTileFrames);
+  decode_prep_kernel<<<blocks, 256, 0, st>>>(note, onset, b.frame_off, n_files, b.energy, b.max_onset, b.max_fd, 0, kPitches);
+  decode_cand_kernel<<<blocks, 256, 0, st>>>(note, onset, b.frame_off, n_files, b.max_onset, b.max_fd, b.candbits, 0,
+                                             kPitches, 1, 0.0, out64);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -124,6 +124,8 @@ struct DecodeBuffers {
 };
 void launch_decode_notes(const float* note, const float* onset, const DecodeBuffers& buf, int n_files,
                          long long total_frames, const DecodeParamsDev& p, cudaStream_t st);
+void launch_infer_onsets(const float* note, const float* onset, const DecodeBuffers& buf, int n_files, long long total_frames,
+                         double* out64 /* [total_frames][88] */, cudaStream_t st);
 // amplitude (NumPy pairwise mean) + pitch bends for compacted notes
 void launch_note_finish(const float* note, const float* contour, const long long* note_frame_base /*[n_notes]*/,
                         const int* start, const int* end, const int* pitch, float* amp, const int* bend_off,

@@ -240,6 +240,31 @@ class Model:
         )
         return self._split_notes(arrs, n_files)
 
+    def infer_onsets_array(self, onsets: np.ndarray, frames: np.ndarray) -> np.ndarray:
+        """reference: note_creation.py:289-311 `get_infered_onsets` (n_diff = 2) -> float64 (T, 88), on the device."""
+        o = np.ascontiguousarray(onsets, dtype=_F32)
+        f = np.ascontiguousarray(frames, dtype=_F32)
+        if o.ndim != 2 or o.shape[1] != N_FREQ_BINS_NOTES or f.shape != o.shape:
+            raise ValueError("onsets / frames must be (T, 88) and of equal shape")
+        out = np.empty(o.shape, np.float64)
+        self._lib.bp_infer_onsets_host(self._h, _ptr(o), _ptr(f), o.shape[0], _ptr(out))
+        return out
+
+    def pitch_bends_arrays(self, contours: np.ndarray, start: np.ndarray, end: np.ndarray, pitch: np.ndarray):
+        """reference: note_creation.py:182-219 `get_pitch_bends` for given notes -> (bend_off int32[n+1], bends int32[])."""
+        c = np.ascontiguousarray(contours, dtype=_F32)
+        if c.ndim != 2 or c.shape[1] != N_FREQ_BINS_CONTOURS:
+            raise ValueError("contours must be (T, 264)")
+        st = np.ascontiguousarray(start, dtype=np.int32)
+        en = np.ascontiguousarray(end, dtype=np.int32)
+        pi = np.ascontiguousarray(pitch, dtype=np.int32)
+        n = len(st)
+        off = np.zeros(n + 1, np.int32)
+        cap = int(np.maximum(en.astype(np.int64) - st.astype(np.int64), 0).sum())
+        bends = np.empty(max(cap, 1), np.int32)
+        self._lib.bp_pitch_bends_host(self._h, _ptr(c), c.shape[0], n, _ptr(st), _ptr(en), _ptr(pi), _ptr(off), _ptr(bends), cap)
+        return off, bends[: int(off[n])]
+
     # ------------------------------------------------------------------ the whole path
     def transcribe_arrays(self, audios: Sequence[np.ndarray], onset_thresh=0.5, frame_thresh=0.3, min_note_len=11,
                           energy_tol=11, infer_onsets=True, melodia_trick=True, include_pitch_bends=True,

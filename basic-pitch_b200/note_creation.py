@@ -195,8 +195,41 @@ def sonify_midi(midi, save_path, sr: Optional[int] = 44100) -> None:
     wavfile.write(save_path, sr, midi.synthesize(sr))
 
 
+SONIFY_FS = 3000  # reference: note_creation.py:41
+
+
+def sonify_salience(gram, semitone_resolution: float, save_path: Optional[str] = None, thresh: float = 0.2):
+    """reference: note_creation.py:131-165 — needs `mir_eval` / `resampy` (sonification is outside the hot path)."""
+    raise NotImplementedError("sonify_salience needs the `mir_eval` and `resampy` packages (sonification is outside the hot path)")
+
+
+def get_pitch_bends(contours, note_events, n_bins_tolerance: int = 25, model=None):
+    """reference: note_creation.py:182-219 -> [(start_frame, end_frame, pitch_midi, amplitude, [bends])].  Runs the
+    decode's pitch-bend kernel (csrc/decode.cu: note_finish_kernel via `bp_pitch_bends_host`) on the given notes."""
+    if n_bins_tolerance != 25:
+        raise NotImplementedError("the device kernel implements the reference's default n_bins_tolerance = 25")
+    from .inference import default_model
+
+    mdl = model if model is not None else default_model()
+    ev = list(note_events)
+    off, bends = mdl.pitch_bends_arrays(contours, [e[0] for e in ev], [e[1] for e in ev], [e[2] for e in ev])
+    return [(e[0], e[1], e[2], e[3], [int(x) for x in bends[off[i] : off[i + 1]]]) for i, e in enumerate(ev)]
+
+
+def get_infered_onsets(onsets, frames, n_diff: int = 2, model=None):
+    """reference: note_creation.py:289-311 -> float64 (T, 88).  Runs the decode's two cell-parallel kernels
+    (csrc/decode.cu via `bp_infer_onsets_host`)."""
+    if n_diff != 2:
+        raise NotImplementedError("the device kernels implement the reference's default n_diff = 2")
+    from .inference import default_model
+
+    mdl = model if model is not None else default_model()
+    return mdl.infer_onsets_array(onsets, frames)
+
+
 __all__ = [
     "model_output_to_notes", "output_to_notes_polyphonic", "note_events_to_midi", "drop_overlapping_pitch_bends",
-    "model_frames_to_time", "constrain_frequency", "midi_pitch_to_contour_bin", "sonify_midi",
+    "model_frames_to_time", "constrain_frequency", "midi_pitch_to_contour_bin", "sonify_midi", "sonify_salience",
+    "get_pitch_bends", "get_infered_onsets", "SONIFY_FS",
     "MIDI_OFFSET", "MAX_FREQ_IDX", "N_FREQ_BINS_CONTOURS",
 ]  # fmt: skip

@@ -28,6 +28,7 @@ if ROOT not in sys.path:
 
 CLIP_SECONDS = 10.0
 SR = 22050
+WORKLOAD = "BASELINE configs[3] per-GPU shard: 10 s synthetic 22 050 Hz clips, full pipeline (HCQT+CNN+note decode) to note events, sharded by file"
 FLOP_PER_WINDOW = 1_048_159_296
 CONTOUR1_FLOP_PER_WINDOW = 680_030_208  # the dominant kernel (3x39 conv, 8->8 channels) ...
 CONTOUR2_FLOP_PER_WINDOW = 18_163_200  # ... whose epilogue also does the MACs of the 5x5 8->1 conv (2 x 200 x 172 x 264)
@@ -144,7 +145,8 @@ def run_reference(args, rank: int, world: int):
         "impl": "reference", "metric": "audio_seconds_per_second", "value": value, "unit": "audio-s/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "configs[3] sample: 10 s synthetic clips, full pipeline to note events", "clips_per_step": per_step,
+        "config": {"workload": WORKLOAD, "clip_seconds": CLIP_SECONDS, "sample_clips_per_step": per_step,
+                   "sample": f"bounded sample of the workload: {per_step} of its 10 s clips per step",
                    "note": "restated CPU baseline (onnxruntime / TensorFlow are not installable offline; the reference's own decode is pure Python like this port)"},
         "cpu_baseline": {"value": value, "unit": "audio-s/s", "cores": threads, "kind": "port", "sample": desc},
         "e2e": {"value": value, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -267,7 +269,7 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {
-                "workload": "BASELINE configs[3] per-GPU shard: 10 s synthetic 22 050 Hz clips, full pipeline (HCQT+CNN+note decode) to note events, sharded by file",
+                "workload": WORKLOAD,
                 "clips_per_gpu_per_step": args.clips, "clip_seconds": CLIP_SECONDS, "windows_per_gpu_per_step": n_windows,
                 "frames_per_gpu_per_step": n_frames, "notes_per_gpu_per_step": n_notes, "parallelism": f"files x{world}, no data-path collective",
                 "l2": f"inputs {packed.nbytes / 1e6:.0f} MB per step > 126 MB L2 (no flush needed)",

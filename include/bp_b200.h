@@ -147,6 +147,18 @@ int bp_transcribe_host(bp_model_t* m, const float* h_audio, const int64_t* h_sam
 int bp_transcribe_device(bp_model_t* m, const float* d_audio, const int64_t* h_sample_off, int32_t n_files,
                          const bp_decode_params_t* params, int64_t* h_frame_off, bp_notes_t* notes, void* stream);
 
+/* ---- the two sub-steps of the decode the reference also exposes as functions --------------------------------------
+ * bp_infer_onsets_host — reference: basic_pitch/note_creation.py:289-311 get_infered_onsets (n_diff = 2):
+ *   out[t][f] (float64) = max(onsets, max(onsets) * frame_diff / max(frame_diff)) of one file, h_onset / h_note (T,88) f32.
+ *   All-NaN when max(frame_diff) == 0, like the reference.
+ * bp_pitch_bends_host — reference: note_creation.py:182-219 get_pitch_bends (n_bins_tolerance = 25): for every given
+ *   note (start_frame, end_frame, pitch_midi) the per-frame pitch-bend estimates (1/3-semitone units) from the contour
+ *   posteriorgram (T,264); h_bend_off[n_notes+1] receives the offsets into h_bends (BP_E_CAPACITY: "need N"). */
+int bp_infer_onsets_host(bp_model_t* m, const float* h_onset, const float* h_note, int64_t n_frames, double* h_out);
+int bp_pitch_bends_host(bp_model_t* m, const float* h_contour, int64_t n_frames, int32_t n_notes, const int32_t* h_start,
+                        const int32_t* h_end, const int32_t* h_pitch_midi, int32_t* h_bend_off, int32_t* h_bends,
+                        int64_t bend_capacity);
+
 /* ---- introspection used by tests / profiling ----------------------------------------------------
  * Copies an internal activation of the most recent bp_forward_* call for window 0..n-1 to host.
  * which: 0 = CQT log-magnitude after normalisation+BN (n,172,309); 1 = contour conv1 output

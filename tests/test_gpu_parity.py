@@ -339,6 +339,42 @@ def test_transcribe_host_sub_batches_equal_device_path(model):
         np.testing.assert_array_equal(out_h.a["amp"][no[i] : no[i + 1]], out_h.a["amp"][no[j] : no[j + 1]])
 
 
+def test_get_infered_onsets_and_get_pitch_bends_entry_points(model):
+    """The two sub-steps of the decode the reference also exposes as functions (note_creation.py:289-311, 182-219), through
+    their own C-ABI entry points, bit-identical to the oracle restatements."""
+    from basic_pitch_b200 import note_creation as nc
+    from oracle import decode_ref
+
+    rng = np.random.default_rng(5)
+    T = 333  # not a multiple of the 32-frame tiles
+    note = (rng.random((T, 88)) ** 3).astype(np.float32)
+    onset = (rng.random((T, 88)) ** 4).astype(np.float32)
+    got = nc.get_infered_onsets(onset, note, model=model)
+    with np.errstate(all="ignore"):
+        exp = decode_ref.infer_onsets(onset, note)
+    assert got.dtype == np.float64 and got.shape == exp.shape
+    np.testing.assert_array_equal(got, exp)
+    # constant frames -> max(frame_diff) == 0 -> the reference's 0/0: an all-NaN matrix
+    flat = np.full((40, 88), 0.25, np.float32)
+    assert np.isnan(nc.get_infered_onsets(onset[:40], flat, model=model)).all()
+
+    contour = rng.random((T, 264)).astype(np.float32)
+    notes = []
+    for _ in range(60):
+        a = int(rng.integers(0, T - 2))
+        b = int(rng.integers(a + 1, min(T, a + 90) + 1))
+        notes.append((a, b, int(rng.integers(21, 109)), np.float32(rng.random())))
+    notes += [(0, T, 21, np.float32(0.5)), (0, 1, 108, np.float32(0.5)), (T - 1, T, 60, np.float32(0.1))]
+    got_b = nc.get_pitch_bends(contour, notes, model=model)
+    exp_b = decode_ref.pitch_bends(contour, notes)
+    assert len(got_b) == len(exp_b)
+    for g, e in zip(got_b, exp_b):
+        assert g[:3] == tuple(e[:3]) and g[3] == e[3]
+        assert g[4] == [int(x) for x in e[4]]
+    with pytest.raises(Exception):
+        nc.get_pitch_bends(contour, [(5, 5, 60, 0.1)], model=model)  # empty note
+
+
 def test_dense_polyphony_batch_bit_exact(model):
     """BASELINE configs[4]: 88-voice chords, several 10 s clips in one batch; decode (incl. pitch bends) bit-identical to
     the oracle decode on the same GPU posteriorgrams."""

@@ -170,3 +170,17 @@ def test_numpy_pairwise_sum_model():
     for n in (1, 2, 7, 8, 9, 15, 16, 17, 100, 127, 128, 129, 130, 255, 256, 257, 1000, 1023, 2999):
         col = m[5 : 5 + n, 17]
         assert np.float32(pw(col) / np.float32(n)) == np.mean(col), n
+
+
+def test_decode_substep_functions_reject_unsupported_arguments():
+    """get_pitch_bends / get_infered_onsets exist with the reference's signatures (note_creation.py:182, 289); the device
+    kernels implement the reference defaults only, other values are refused before any GPU work."""
+    from basic_pitch_b200 import note_creation as nc
+
+    with pytest.raises(NotImplementedError):
+        nc.get_pitch_bends(np.zeros((4, 264), np.float32), [(0, 2, 60, 0.5)], n_bins_tolerance=10)
+    with pytest.raises(NotImplementedError):
+        nc.get_infered_onsets(np.zeros((4, 88), np.float32), np.zeros((4, 88), np.float32), n_diff=3)
+    with pytest.raises(NotImplementedError):
+        nc.sonify_salience(np.zeros((264, 4)), 3)
+    assert nc.SONIFY_FS == 3000
