@@ -184,3 +184,32 @@ def test_decode_substep_functions_reject_unsupported_arguments():
     with pytest.raises(NotImplementedError):
         nc.sonify_salience(np.zeros((264, 4)), 3)
     assert nc.SONIFY_FS == 3000
+
+
+def test_file_output_helpers_match_reference_behaviour(tmp_path):
+    """save_note_events / build_output_path / verify_* (reference: inference.py:349-428).  Expected strings were produced by
+    the unmodified reference functions (oracle/ref_shims) on the same inputs."""
+    import pathlib
+
+    from basic_pitch_b200 import inference as inf
+
+    ev = [(np.float64(0.5), np.float64(1.25), np.int64(60), np.float32(0.73), [np.int64(1), np.int64(-2), np.int64(0)]),
+          (np.float64(0.011609977324263039), np.float64(0.13), np.int64(21), np.float32(0.004), None),
+          (np.float64(2.0), np.float64(2.5), np.int64(108), np.float32(1.0), [])]
+    p = tmp_path / "x.csv"
+    inf.save_note_events(ev, p)
+    assert p.read_text() == ("start_time_s,end_time_s,pitch_midi,velocity,pitch_bend\n0.5,1.25,60,93,1,-2,0\n"
+                             "0.011609977324263039,0.13,21,1\n2.0,2.5,108,127\n")
+    assert [(e.name, e.value) for e in inf.OutputExtensions] == [
+        ("MIDI", "mid"), ("MODEL_OUTPUT_NPZ", "npz"), ("MIDI_SONIFICATION", "wav"), ("NOTE_EVENTS", "csv")]
+    assert inf.build_output_path("/a/b/song.flac", str(tmp_path), inf.OutputExtensions.MIDI) == tmp_path / "song_basic_pitch.mid"
+    assert inf.build_output_path("song.name.wav", tmp_path, inf.OutputExtensions.NOTE_EVENTS) == tmp_path / "song.name_basic_pitch.csv"
+    (tmp_path / "song_basic_pitch.mid").write_text("x")
+    with pytest.raises(IOError):
+        inf.build_output_path("/x/song.wav", tmp_path, inf.OutputExtensions.MIDI)
+    for fn, arg in ((inf.verify_input_path, tmp_path / "nope.wav"), (inf.verify_input_path, tmp_path),
+                    (inf.verify_output_dir, tmp_path / "nodir"), (inf.verify_output_dir, p)):
+        with pytest.raises(ValueError):
+            fn(arg)
+    inf.verify_input_path(p)
+    inf.verify_output_dir(pathlib.Path(tmp_path))
