@@ -263,11 +263,17 @@ def test_run_inference_equals_windowed_predict(model):
 
     clips = [synth.random_notes_clip(10.0, seed=31), synth.tones_clip(2.0, seed=1), np.zeros(1, np.float32),
              synth.random_notes_clip(3.3, seed=33)[:36165]]
-    outs = model.run_inference_arrays(clips)
-    for clip, out in zip(clips, outs):
-        raw = model.predict(host_ref.window_audio(clip))
-        for k in raw:
-            np.testing.assert_array_equal(out[k], host_ref.unwrap(raw[k], len(clip)), err_msg=k)
+    # path 1 writes the unwrapped rows from the tap-sum kernels, paths 0 / 2 (partly) through separate copies
+    for path in (1, 0, 2):
+        try:
+            model.set_path(path)
+            outs = model.run_inference_arrays(clips)
+            for clip, out in zip(clips, outs):
+                raw = model.predict(host_ref.window_audio(clip))
+                for k in raw:
+                    np.testing.assert_array_equal(out[k], host_ref.unwrap(raw[k], len(clip)), err_msg=f"{k} (path {path})")
+        finally:
+            model.set_path(1)
 
 
 def test_time_shift_equivariance_across_windows(model):
