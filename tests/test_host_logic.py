@@ -213,3 +213,35 @@ def test_file_output_helpers_match_reference_behaviour(tmp_path):
             fn(arg)
     inf.verify_input_path(p)
     inf.verify_output_dir(pathlib.Path(tmp_path))
+
+
+def test_window_audio_file_and_get_audio_input_like_the_reference_tests(golden_dir, tmp_path):
+    """Mirrors reference tests/test_inference.py:164-194 (`test_window_audio_file`, `test_get_audio_input`) on the same
+    recording (its 22 050 Hz rendition from the golden fixture; a float32 WAV round-trips exactly)."""
+    from scipy.io import wavfile
+
+    from basic_pitch_b200 import inference as inf
+    from basic_pitch_b200.constants import AUDIO_N_SAMPLES, AUDIO_SAMPLE_RATE, FFT_HOP
+
+    audio = np.load(golden_dir / "vocadito10.npz")["audio22k"]
+    windows, times = zip(*inf.window_audio_file(audio, AUDIO_N_SAMPLES - 30 * FFT_HOP))
+    assert len(windows) == 6 and len(times) == 6
+    assert all(t["start"] <= t["end"] for t in times)
+    np.testing.assert_equal(audio[:AUDIO_N_SAMPLES], np.squeeze(windows[0]))
+
+    wav = tmp_path / "vocadito_10_22k.wav"
+    wavfile.write(wav, AUDIO_SAMPLE_RATE, audio)  # float32 WAV
+    overlap_len = 30 * FFT_HOP
+    padded = np.concatenate([np.zeros((overlap_len // 2,), dtype=np.float32), audio])
+    got, got_times, orig = [], [], None
+    for w, t, original_length in inf.get_audio_input(wav, overlap_len, AUDIO_N_SAMPLES - overlap_len):
+        got.append(w)
+        got_times.append(t)
+        orig = original_length
+    got = np.array(got)
+    assert len(got) == 6 and len(got_times) == 6
+    assert all(t["start"] <= t["end"] for t in got_times)
+    np.testing.assert_equal(padded[:AUDIO_N_SAMPLES], np.squeeze(got[0]))
+    assert orig == 200607
+    with pytest.raises(AssertionError):
+        next(inf.get_audio_input(wav, 3, AUDIO_N_SAMPLES - 3))  # odd overlap, like the reference (inference.py:237)
