@@ -1,16 +1,19 @@
-// Convolution stack, FP32 FFMA path (accuracy reference on device and the path for layers that
-// have no tensor-core kernel yet).
+// Convolution stack: the FP32 FFMA kernels (path 0: accuracy reference on device; path 2 uses the channels-last
+// contour conv2 below) and the tap-sum kernel that finishes the three single-output convolutions after the fused
+// epilogues of the tensor-core kernels (path 1, tc_conv.cu).
 //
 // Replaces nodes 213-247 of the deployed graph:
 //   HarmonicStacking.call   reference: basic_pitch/nn.py:69-88   (never materialised: the 8 "channels"
 //                           are shifted, zero-gated views of the normalised CQT, see StackIn)
 //   conv stack              reference: basic_pitch/models.py:241-318 (BatchNorm folded, as exported)
 //
-// One generic direct-convolution kernel.  A CTA produces a tile of TT frames x FT=FL*P bins for all
+// conv_kernel: one generic direct-convolution kernel.  A CTA produces a tile of TT frames x FT=FL*P bins for all
 // COUT channels of one window; the input patch and the (transposed) weights are staged in shared
 // memory.  Thread (cg, tl, fl) owns COB output channels x P bins {fl + FL*p}: lanes walk consecutive
 // bins (conflict-free for stride 1 and 3), every loaded input feeds COB FMAs, weights are warp-uniform
 // float4 broadcasts.
+// conv1_kernel: the C_out = 1 convolutions with a 4 x 4 register tile per thread (planar or channels-last input).
+// halo_tapsum_kernel: time-tap / halo sums + sigmoid (+ unwrap, + bf16 split of the contour) behind the fused epilogues.
 #include "kernels.cuh"
 
 namespace bp {
