@@ -2,7 +2,7 @@
 
 There is no fallback of any kind: if the shared library is missing or no B200 is visible, loading or
 model creation raises.  Build the library with `python -c "import __graft_entry__ as g; g.build()"`
-or `make -C basic-pitch_b200/csrc`.
+or `make -C basic_pitch_b200/csrc`.
 """
 from __future__ import annotations
 
@@ -73,7 +73,7 @@ def load() -> C.CDLL:
     if not LIB_PATH.is_file():
         raise ImportError(
             f"{LIB_PATH} not found: the CUDA extension has not been built "
-            "(run `make -C basic-pitch_b200/csrc`). There is no CPU fallback."
+            "(run `make -C basic_pitch_b200/csrc`). There is no CPU fallback."
         )
     lib = C.CDLL(str(LIB_PATH))
     vp, i32, i64, sz = C.c_void_p, C.c_int32, C.c_int64, C.c_size_t

@@ -91,7 +91,7 @@ int64_t bp_num_frames(int64_t n_samples);
 /* ---- model lifetime ----------------------------------------------------------------------
  * reference: Model.__init__ (basic_pitch/inference.py:78-154) loading
  * the files under basic_pitch/saved_models/icassp_2022.  `blob` is the BPW1 tensor blob
- * (basic-pitch_b200/weights.py); it is copied, the caller keeps ownership. */
+ * (basic_pitch_b200/weights.py); it is copied, the caller keeps ownership. */
 int bp_model_create(const void* blob, size_t nbytes, int device, bp_model_t** out);
 void bp_model_destroy(bp_model_t* m);
 int bp_model_device(const bp_model_t* m);

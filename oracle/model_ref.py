@@ -1,7 +1,7 @@
 """ORACLE (test infrastructure, not product code): CPU restatement of the deployed basic-pitch graph.
 
 Only `tests/`, `__graft_entry__.smoke()` and `bench.py`'s cpu_baseline / `--impl reference` legs may
-import this module.  The product path (`basic-pitch_b200/`) never does.
+import this module.  The product path (`basic_pitch_b200/`) never does.
 
 What it restates: the graph the reference hands to its ML runtime at
 reference: basic_pitch/inference.py:156-182 (`Model.predict`), i.e. the contents of

@@ -1,9 +1,9 @@
 #!/usr/bin/env python
-"""Regenerate basic-pitch_b200/saved_models/icassp_2022/nmp.bpw from an ONNX export of the network.
+"""Regenerate basic_pitch_b200/saved_models/icassp_2022/nmp.bpw from an ONNX export of the network.
 
 Usage: python tools/extract_weights.py [/path/to/nmp.onnx]
 Default source: /root/reference/basic_pitch/saved_models/icassp_2022/nmp.onnx (only present in the
-build container).  The blob holds tensors only (≈143 KB); see basic-pitch_b200/weights.py for the layout.
+build container).  The blob holds tensors only (≈143 KB); see basic_pitch_b200/weights.py for the layout.
 """
 import hashlib
 import pathlib
