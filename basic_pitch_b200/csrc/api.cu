@@ -5,6 +5,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -188,7 +189,12 @@ namespace {
 
 // Weight-dependent data in __constant__ memory (FIR taps, conv1 biases, fused conv2 weights) is shared by all models
 // of a process on one device; remember whose values are resident.
+// The bank is guarded per device: a launch sequence that depends on it (forward_chunk) holds the device's mutex while
+// it enqueues, and a change of owner first drains the device so that kernels of the previous owner that are still in
+// flight never see the new values.  Models with different weights may therefore be used from several host threads;
+// they serialise at chunk granularity.
 const bp_model* g_const_owner[64] = {};
+std::mutex g_const_mu[64];
 
 struct DeviceGuard {
   int prev = -1;
@@ -263,6 +269,8 @@ int parse_blob(const void* blob, size_t nbytes, std::vector<float>& params) {
 
 int upload_constants(bp_model* m, cudaStream_t st) {
   const float* hp = m->h_params.data();
+  if (m->device >= 0 && m->device < 64 && g_const_owner[m->device] && g_const_owner[m->device] != m)
+    CK(cudaDeviceSynchronize());  // kernels of the previous owner may still be reading the bank
   upload_lowpass(hp + ParamLayout::lowpass, st);
   tc_upload_epilogue(hp + ParamLayout::contour1_b, hp + ParamLayout::onset1_b, hp + ParamLayout::note1_b,
                      hp + ParamLayout::onset2_w, hp + ParamLayout::note2_w, hp + ParamLayout::contour2_w, st);
@@ -302,8 +310,9 @@ int derive(bp_model* m, cudaStream_t st) {
     CK(cudaMemcpyAsync(m->cqt_wtc.p, wtc.data(), wtc.size() * 2, cudaMemcpyHostToDevice, st));
     CK(cudaStreamSynchronize(st));
   }
+  std::unique_lock<std::mutex> const_lock;
+  if (m->device >= 0 && m->device < 64) const_lock = std::unique_lock<std::mutex>(g_const_mu[m->device]);
   return upload_constants(m, st);
-  return BP_OK;
 }
 
 int ensure_forward_ws(bp_model* m, int nb) {
@@ -357,6 +366,8 @@ int forward_chunk(bp_model* m, const float* audio, const WinDesc* desc, int nb, 
                   float* u_onset = nullptr, float* u_contour = nullptr) {
   float* chain = m->chain.p;
   if (m->profile_which >= 0) m->prof_windows += nb;
+  std::unique_lock<std::mutex> const_lock;
+  if (m->device >= 0 && m->device < 64) const_lock = std::unique_lock<std::mutex>(g_const_mu[m->device]);
   if (m->device >= 0 && m->device < 64 && g_const_owner[m->device] != m) {
     int rc = upload_constants(m, st);
     if (rc) return rc;
@@ -475,8 +486,11 @@ int64_t bp_num_frames(int64_t n_samples) {
   return (int64_t)((double)n_samples / (double)kHopSamples * (double)kHopFrames);
 }
 
+static int model_init(bp_model* m, const std::vector<float>& params, const cudaDeviceProp& prop);
+
 int bp_model_create(const void* blob, size_t nbytes, int device, bp_model_t** out) {
   if (!blob || !out) return fail(BP_E_INVALID, "bp_model_create: null argument");
+  *out = nullptr;
   std::vector<float> params;
   int rc = parse_blob(blob, nbytes, params);
   if (rc) return rc;
@@ -494,24 +508,40 @@ int bp_model_create(const void* blob, size_t nbytes, int device, bp_model_t** ou
                                std::to_string(prop.minor) + "; this library is built for sm_100a only");
   bp_model* m = new bp_model();
   m->device = device;
+  rc = model_init(m, params, prop);
+  if (rc) {  // every failure path releases the streams and device buffers created so far
+    const std::string msg = g_err;
+    bp_model_destroy(m);
+    g_err = msg;
+    return rc;
+  }
+  *out = m;
+  return BP_OK;
+}
+
+static int model_init(bp_model* m, const std::vector<float>& params, const cudaDeviceProp& prop) {
+  int rc;
   CK(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
   CK(cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking));
   CK(cudaMalloc(&m->d_params, sizeof(float) * ParamLayout::total));
   CK(cudaMalloc(&m->d_derived, sizeof(float) * DerivedLayout::total));
   CK(cudaMalloc(&m->d_gauss, sizeof(double) * 51));
-  CK(cudaMemcpy(m->d_params, params.data(), sizeof(float) * ParamLayout::total, cudaMemcpyHostToDevice));
+  // stream-ordered with derive_kernel below (m->stream is non-blocking: it does not wait for the legacy stream)
+  CK(cudaMemcpyAsync(m->d_params, params.data(), sizeof(float) * ParamLayout::total, cudaMemcpyHostToDevice, m->stream));
   double gauss[51];
   for (int i = 0; i < 51; ++i) {  // scipy.signal.windows.gaussian(51, std=5): exp(-n^2 / (2*std^2))
     double n = (double)i - 25.0;
     gauss[i] = std::exp(-(n * n) / 50.0);
   }
-  CK(cudaMemcpy(m->d_gauss, gauss, sizeof(gauss), cudaMemcpyHostToDevice));
+  CK(cudaMemcpyAsync(m->d_gauss, gauss, sizeof(gauss), cudaMemcpyHostToDevice, m->stream));
+  CK(cudaStreamSynchronize(m->stream));  // `gauss` is a stack array
   const float* P = m->d_params;
   const float* D = m->d_derived;
   m->cw = CnnWeights{D + DerivedLayout::contour1_wT, P + ParamLayout::contour1_b, D + DerivedLayout::contour2_wT,
                      P + ParamLayout::contour2_b,    D + DerivedLayout::note1_wT, P + ParamLayout::note1_b,
                      D + DerivedLayout::note2_wT,    P + ParamLayout::note2_b,    D + DerivedLayout::onset1_wT,
                      P + ParamLayout::onset1_b,      D + DerivedLayout::onset2_wT, P + ParamLayout::onset2_b};
+  hcqt_setup();
   cnn_setup();
   tc_setup();
   cqt_tc_setup();
@@ -522,7 +552,6 @@ int bp_model_create(const void* blob, size_t nbytes, int device, bp_model_t** ou
   rc = derive(m, m->stream);
   if (rc) return rc;
   CK(cudaStreamSynchronize(m->stream));
-  *out = m;
   return BP_OK;
 }
 
@@ -530,7 +559,10 @@ void bp_model_destroy(bp_model_t* m) {
   if (!m) return;
   DeviceGuard g(m->device);
   cudaDeviceSynchronize();
-  if (m->device >= 0 && m->device < 64 && g_const_owner[m->device] == m) g_const_owner[m->device] = nullptr;
+  if (m->device >= 0 && m->device < 64) {
+    std::lock_guard<std::mutex> lk(g_const_mu[m->device]);
+    if (g_const_owner[m->device] == m) g_const_owner[m->device] = nullptr;
+  }
   m->chain.release(); m->y.release(); m->c1.release(); m->n1.release(); m->o1.release();
   m->raw_note.release(); m->raw_onset.release(); m->raw_contour.release(); m->minmax.release();
   m->wdesc.release(); m->udesc.release(); m->st_audio.release(); m->st_note.release(); m->st_onset.release();

@@ -526,7 +526,7 @@ __global__ void note_finish_kernel(const float* __restrict__ note, const float* 
   int* out = bends + bend_off[n];
   for (int t = t0; t < t1; ++t) {
     const float* row = contour + (base + t) * kContourBins + lo;
-    double bv = -1.0;
+    double bv = -INFINITY;  // np.argmax semantics for any input (callers may pass contours < 0)
     int bi = 0x7fffffff;
     for (int j = lane; j < width; j += 32) {
       double v = __dmul_rn((double)row[j], gauss[g0 + j]);

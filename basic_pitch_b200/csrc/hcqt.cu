@@ -301,14 +301,15 @@ __global__ void minmax_init_kernel(unsigned int* mm, int n) {
   }
 }
 
+// per-device opt-in to > 48 KB of dynamic shared memory (called from bp_model_create under the device guard)
+void hcqt_setup() {
+  cudaFuncSetAttribute(cqt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                       (int)((kFrames * kCqtApad + kCqtKc * kCqtCols) * sizeof(float)));
+}
+
 void launch_cqt(const float* audio, const WinDesc* desc, const float* chain, const float* wt, const float* scale,
                 float* logmag, unsigned int* minmax, int n_windows, cudaStream_t st) {
-  static bool attr_set = false;
   const int smem = (kFrames * kCqtApad + kCqtKc * kCqtCols) * sizeof(float);
-  if (!attr_set) {
-    cudaFuncSetAttribute(cqt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    attr_set = true;
-  }
   minmax_init_kernel<<<(n_windows + 255) / 256, 256, 0, st>>>(minmax, n_windows);
   cqt_kernel<<<dim3(kOctaves, n_windows), kCqtThreads, smem, st>>>(audio, desc, chain, wt, scale, logmag, minmax);
 }

@@ -10,6 +10,7 @@
 namespace bp {
 
 // ---- hcqt.cu ------------------------------------------------------------------------------------
+void hcqt_setup();  // per device: shared-memory opt-in of the FP32 CQT kernel
 void upload_lowpass(const float* h_lp, cudaStream_t st);  // host taps -> __constant__ tap pairs
 void launch_decimate(const float* audio, const WinDesc* desc, float* chain, int stage, int n_windows, cudaStream_t st);
 void launch_cqt(const float* audio, const WinDesc* desc, const float* chain, const float* wt, const float* scale,

@@ -15,16 +15,19 @@
 //
 // Formulation ("Toeplitz along frequency on aligned chunks")
 //   rows  m = b*174 + t            time frames of all windows of the chunk, two zero rows between windows
-//   D[m][(fl,co)] (+)= A[m+dt][8c .. 8c+15] x T(ci,dt,off)[16][(fl,co)]
+//   D[m][(fl,co)] (+)= A[m+dt][8c .. 8c+15] x T(dt,off)[16][(fl,co)]
 //     A      the normalised CQT y itself (NOT the 8-channel stack), rows shifted by the time tap dt; K = 16 bins that
 //            start on an 8-bin chunk of the k-chunk-major layout
-//     T      16 x 128 "weight tile": T[k][(fl,co)] = W[co][ci][dt][df] with
-//            df = (8c + k) - shift_ci - SF*(ft*FLT + fl) + PL   (zero outside 0 <= df < KW, outside the stacked image
-//            0 <= g < 264 and outside the bins the step is responsible for)
+//     T      16 x 128 "weight tile": T[k][(fl,co)] = sum_ci W[co][ci][dt][df_ci] with
+//            df_ci = (8c + k) - shift_ci - SF*(ft*FLT + fl) + PL   (terms outside 0 <= df < KW or outside the stacked
+//            image 0 <= g < 264 dropped).  The harmonic channels are shifted views of one image, so they are MERGED
+//            in the weight operand: the stack conv is a single-channel conv of y whose taps are the union of the
+//            shifted per-channel taps (contour: 8 x 39 = 312 taps on 176 distinct offsets -> 12 instead of 32
+//            K-steps per time tap and frequency tile).
 //            N = FLT output bins x COUT channels = 128 (contour 16 x 8, onset / note 4 x 32); a tile depends on
-//            (ci, dt, 8c - SF*FLT*ft), so frequency tiles SF*FLT*d = 8*j bins apart share tiles (de-duplicated by
+//            (dt, 8c - SF*FLT*ft), so frequency tiles SF*FLT*d = 8*j bins apart share tiles (de-duplicated by
 //            content)
-//   every (ft, ci, dt, c) with a non-empty tile is one K=16 MMA step of shape 128 x 128 x 16
+//   every (ft, dt, c) with a non-empty tile is one K=16 MMA step of shape 128 x 128 x 16
 // Precision: both operands are split x = hi + lo (bf16 each) and three products are accumulated
 // (hi*hi + hi*lo + lo*hi) in fp32, which keeps the posteriorgrams within ~1e-5 of the FP32 path
 // (SURVEY.md Appendix C.4); a single bf16 product would miss the 1e-3 bar.
@@ -114,18 +117,32 @@ void TcConvPlan::build(const TcConvSpec& sp, const float* W /* [COUT][n_ci][KH][
   std::unordered_map<uint64_t, std::vector<int>> by_hash;
   int n_keys = 0;
   std::vector<uint16_t> scratch(kTileBytes / 2);
-  // tile for input channel ci, time tap dt, relative offset off = (first bin of the step) - SF*FLT*ft; rows kk outside
-  // [clip_lo, clip_hi) are zero (bins outside the stacked image or owned by the neighbouring step)
-  auto find_or_add = [&](int ci, int dt, int off, int clip_lo, int clip_hi) -> int {
-    const int s = sp.shifts[ci];
+  // The n_ci input channels are shifted views of ONE image (harmonic stacking, nn.py:69-88), so the stack conv is a
+  // single-channel conv of y with the merged kernel  Wm[co][dt][u] = sum_ci W[co][ci][dt][u - shift_ci + PL]  wherever
+  // the stacked pixel exists (0 <= g = u_abs - shift_ci < 264): the contour taps of the 8 harmonics (8 x 39 = 312)
+  // cover only 176 distinct bin offsets, the onset clusters of the upper harmonics overlap too.  A tile therefore
+  // holds the SUM over the channels: tile for time tap dt, K rows [clip_lo, 16) of the 16 bins that start at bin
+  // 8*c, frequency tile ft (rows below clip_lo belong to the previous step when the last chunk pair is clamped).
+  auto find_or_add = [&](int dt, int c, int ft, int clip_lo) -> int {
     bool any = false;
     std::fill(scratch.begin(), scratch.end(), (uint16_t)0);
-    for (int kk = clip_lo; kk < clip_hi; ++kk) {
+    for (int kk = clip_lo; kk < 16; ++kk) {
+      const int u = 8 * c + kk;  // bin of y
+      if (u >= sp.data_bins) continue;
       for (int n = 0; n < 128; ++n) {
         const int fl = n / sp.COUT, co = n % sp.COUT;
-        const int df = off + kk - s - sp.SF * fl + sp.PL;
-        if (df < 0 || df >= sp.KW) continue;
-        const float w = W[((co * sp.n_ci + ci) * sp.KH + dt) * sp.KW + df];
+        const int f = ft * sp.FLT + fl;  // (columns f >= WOUT are computed like the others and dropped by the epilogue)
+        double acc = 0.0;
+        bool hit = false;
+        for (int ci = 0; ci < sp.n_ci; ++ci) {
+          const int gg = u - sp.shifts[ci];  // bin of the stacked image
+          const int df = gg - sp.SF * f + sp.PL;
+          if (df < 0 || df >= sp.KW || gg < 0 || gg >= kContourBins) continue;
+          acc += (double)W[((co * sp.n_ci + ci) * sp.KH + dt) * sp.KW + df];
+          hit = true;
+        }
+        if (!hit) continue;
+        const float w = (float)acc;
         const uint16_t hi = f2bf(w);
         const uint16_t lo = f2bf(w - bf2f(hi));
         const size_t o = (size_t)(kk >> 3) * 128 * 8 + (size_t)n * 8 + (kk & 7);
@@ -163,39 +180,40 @@ void TcConvPlan::build(const TcConvSpec& sp, const float* W /* [COUT][n_ci][KH][
       int tile, slot, c8, dt, off;
     };
     std::vector<Use> uses;
-    for (int ci = 0; ci < sp.n_ci; ++ci) {
-      const int s = sp.shifts[ci];
-      for (int dt = 0; dt < sp.KH; ++dt) {
-        std::vector<Use> cand;
-        for (int slot = 0; slot < 2; ++slot) {
-          const int ft = fts[slot];
-          if (ft < 0) continue;
-          // data bins u = g + s this frequency tile reads through channel ci (g inside the stacked image)
-          int lo = 1 << 30, hi = -1;
+    for (int dt = 0; dt < sp.KH; ++dt) {
+      std::vector<Use> cand;
+      for (int slot = 0; slot < 2; ++slot) {
+        const int ft = fts[slot];
+        if (ft < 0) continue;
+        // 8-bin blocks of y this frequency tile reads through any channel
+        std::vector<bool> need(sp.chunks8, false);
+        for (int ci = 0; ci < sp.n_ci; ++ci)
           for (int fl = 0; fl < sp.FLT; ++fl) {
             const int f = ft * sp.FLT + fl;
             if (f >= sp.WOUT) continue;
             for (int df = 0; df < sp.KW; ++df) {
-              const int gg = sp.SF * f - sp.PL + df, u = gg + s;
+              const int gg = sp.SF * f - sp.PL + df, u = gg + sp.shifts[ci];
               if (gg < 0 || gg >= kContourBins || u < 0 || u >= sp.data_bins) continue;
-              lo = std::min(lo, u);
-              hi = std::max(hi, u + 1);
+              need[u / 8] = true;
             }
           }
-          for (int c8 = lo >= hi ? sp.chunks8 : lo / 8; 8 * c8 < hi; c8 += 2) {
-            const int c = std::min(c8, sp.chunks8 - 2);  // both k-chunks of the step must exist in the data tile
-            const int v_lo = std::max(8 * c8, s);  // bins below 8*c8 belong to the previous step
-            const int v_hi = std::min(8 * c + 16, s + kContourBins);
-            const int off = 8 * c - sp.SF * sp.FLT * ft;
-            const int tile = find_or_add(ci, dt, off, std::max(0, v_lo - 8 * c), std::min(16, v_hi - 8 * c));
-            if (tile >= 0) cand.push_back(Use{tile, slot, c, dt, off});
+        // cover the needed blocks with K = 16 steps (two adjacent blocks), left to right
+        for (int c8 = 0; c8 < sp.chunks8;) {
+          if (!need[c8]) {
+            ++c8;
+            continue;
           }
+          const int c = std::min(c8, sp.chunks8 - 2);  // both k-chunks of the step must exist in the data tile
+          const int off = 8 * c - sp.SF * sp.FLT * ft;
+          const int tile = find_or_add(dt, c, ft, 8 * (c8 - c));
+          if (tile >= 0) cand.push_back(Use{tile, slot, c, dt, off});
+          c8 += 2;
         }
-        std::stable_sort(cand.begin(), cand.end(), [](const Use& a, const Use& b) {
-          return a.off != b.off ? a.off < b.off : (a.tile != b.tile ? a.tile < b.tile : a.slot < b.slot);
-        });
-        uses.insert(uses.end(), cand.begin(), cand.end());
       }
+      std::stable_sort(cand.begin(), cand.end(), [](const Use& a, const Use& b) {
+        return a.off != b.off ? a.off < b.off : (a.tile != b.tile ? a.tile < b.tile : a.slot < b.slot);
+      });
+      uses.insert(uses.end(), cand.begin(), cand.end());
     }
     bool seen[2] = {false, false};
     size_t i = 0;
