@@ -142,7 +142,7 @@ struct bp_model {
   float* d_derived = nullptr;
   double* d_gauss = nullptr;
   CnnWeights cw{};
-  int chunk = 216;  // windows per launch sequence: the M-tiles of every tensor-core layer fill whole waves (bp_model_create)
+  int chunk = 206;  // windows per launch sequence: the M-tiles of every tensor-core layer fill whole waves (bp_model_create)
   int path = 1;  // 0 = FP32 FFMA everywhere, 1 = tcgen05 with fused epilogues, 2 = tcgen05 keeping the contour activations
   int n_sms = 148;
   struct TcLayer {
@@ -159,6 +159,7 @@ struct bp_model {
   // forward workspace (chunk windows)
   DevBuf<float> chain, y, c1, n1, o1, raw_note, raw_onset, raw_contour;
   DevBuf<unsigned int> minmax;
+  DevBuf<float> edge;  // partial sums where two frequency-tile ranges of a fused conv meet (tc_conv.cu)
   DevBuf<WinDesc> wdesc;
   DevBuf<UnwrapDesc> udesc;
   // staging for the host entry points
@@ -273,7 +274,8 @@ int upload_constants(bp_model* m, cudaStream_t st) {
     CK(cudaDeviceSynchronize());  // kernels of the previous owner may still be reading the bank
   upload_lowpass(hp + ParamLayout::lowpass, st);
   tc_upload_epilogue(hp + ParamLayout::contour1_b, hp + ParamLayout::onset1_b, hp + ParamLayout::note1_b,
-                     hp + ParamLayout::onset2_w, hp + ParamLayout::note2_w, hp + ParamLayout::contour2_w, st);
+                     hp + ParamLayout::onset2_w, hp + ParamLayout::note2_w, hp + ParamLayout::contour2_w,
+                     hp + ParamLayout::contour2_b, hp + ParamLayout::onset2_b, hp + ParamLayout::note2_b, st);
   CKL();
   if (m->device >= 0 && m->device < 64) g_const_owner[m->device] = m;
   return BP_OK;
@@ -318,10 +320,15 @@ int derive(bp_model* m, cudaStream_t st) {
 int ensure_forward_ws(bp_model* m, int nb) {
   CK(m->chain.reserve((size_t)nb * kChainStride));
   CK(m->y.reserve((size_t)nb * kFrames * kCqtBins));
-  CK(m->c1.reserve((size_t)nb * 8 * kFrames * kContourBins));
-  CK(m->n1.reserve((size_t)nb * 32 * kFrames * kPitches));
-  CK(m->o1.reserve((size_t)nb * 32 * kFrames * kPitches));
+  // the default path never materialises the 8- / 32-channel activations
+  if (m->path != 1) CK(m->c1.reserve((size_t)nb * 8 * kFrames * kContourBins));
+  if (m->path == 0) {
+    CK(m->n1.reserve((size_t)nb * 32 * kFrames * kPitches));
+    CK(m->o1.reserve((size_t)nb * 32 * kFrames * kPitches));
+  }
   CK(m->minmax.reserve((size_t)nb * 2));
+  CK(m->edge.reserve(std::max({tc_edge_floats(tc_contour_spec(), nb), tc_edge_floats(tc_onset_spec(), nb),
+                               tc_edge_floats(tc_note_spec(), nb)})));
   // split layouts use the row stride of a full chunk whatever the batch size (see launch_conv_tc)
   CK(m->yhl.reserve((size_t)2 * 40 * 8 * tc_rows_total(m->chunk, tc_contour_spec().rows_per_window)));
   {
@@ -376,42 +383,53 @@ int forward_chunk(bp_model* m, const float* audio, const WinDesc* desc, int nb, 
     ProfScope ps(m, 3, st);
     for (int s = 0; s < 8; ++s) launch_decimate(audio, desc, chain, s, nb, st);
   }
+  const TcConvSpec cs = tc_contour_spec(), ns = tc_note_spec();
+  const int ystride = tc_rows_total(m->chunk, cs.rows_per_window), cstride = tc_rows_total(m->chunk, ns.rows_per_window);
   {
     ProfScope ps(m, 2, st);
-    if (m->path >= 1)
+    if (m->path >= 1) {
       launch_cqt_tc(audio, desc, chain, m->cqt_wtc.p, m->d_params + ParamLayout::cqt_scale, m->y.p, m->minmax.p, nb,
                     m->n_sms, st);
-    else
+      // NormalizedLog + BatchNorm and the bf16 hi/lo split the convs read, one pass
+      launch_lognorm_split(m->y.p, m->minmax.p, m->d_params + ParamLayout::bn, m->yhl.p, cs, nb, ystride, st);
+    } else {
       launch_cqt(audio, desc, chain, m->d_derived + DerivedLayout::cqt_wt, m->d_params + ParamLayout::cqt_scale, m->y.p,
                  m->minmax.p, nb, st);
-    launch_lognorm(m->y.p, m->minmax.p, m->d_params + ParamLayout::bn, nb, st);
+      launch_lognorm(m->y.p, m->minmax.p, m->d_params + ParamLayout::bn, nb, st);
+    }
   }
   if (m->path >= 1) {
-    const TcConvSpec cs = tc_contour_spec(), ns = tc_note_spec();
-    const int ystride = tc_rows_total(m->chunk, cs.rows_per_window), cstride = tc_rows_total(m->chunk, ns.rows_per_window);
-    launch_split(m->y.p, m->yhl.p, cs, nb, ystride, st);
     {
       ProfScope ps(m, 0, st);
-      launch_conv_tc(m->yhl.p, m->tc_contour.dev, m->c1.p, nb, ystride, m->n_sms, st, /*fuse_next=*/m->path == 1);
+      TcOut o;
+      o.raw = m->path == 1 ? contour : m->c1.p;  // path 1: the finished raw contour rows; path 2: channels-last activations
+      o.edge = m->edge.p;
+      launch_conv_tc(m->yhl.p, m->tc_contour.dev, o, nb, ystride, m->n_sms, st, /*fuse_next=*/m->path == 1);
     }
     {
       ProfScope ps(m, 4, st);
-      if (m->path == 1) {  // c1 holds the five time-tap planes of the fused conv2
-        launch_contour_tapsum(m->c1.p, m->cw, ud ? u_contour : contour, m->chl.p, cstride, nb, st, ud);
+      if (m->path == 1) {
+        launch_contour_split(contour, m->chl.p, nb, cstride, st, ud, u_contour);
       } else {
         launch_contour2_tc(m->c1.p, m->cw, contour, m->chl.p, cstride, nb, st);
         if (ud) unwrap_kernel<<<dim3(16, nb), 256, 0, st>>>(contour, u_contour, ud, kContourBins);
       }
+      TcOut o;
+      o.raw = note;  // the onset conv2 reads the raw note rows of the whole window
+      o.unwrapped = u_note;
+      o.ud = ud;
+      o.edge = m->edge.p;
+      launch_conv_tc(m->chl.p, m->tc_note.dev, o, nb, cstride, m->n_sms, st);
     }
     {
       ProfScope ps(m, 1, st);
-      launch_conv_tc(m->yhl.p, m->tc_onset.dev, m->o1.p, nb, ystride, m->n_sms, st);  // -> 9 tap planes
-    }
-    {
-      ProfScope ps(m, 4, st);
-      launch_conv_tc(m->chl.p, m->tc_note.dev, m->n1.p, nb, cstride, m->n_sms, st);  // -> 21 tap planes
-      launch_note_tapsum(m->n1.p, m->cw, note, nb, st, ud, u_note);
-      launch_onset_tapsum(m->o1.p, note, m->cw, ud ? u_onset : onset, nb, st, ud);
+      TcOut o;
+      o.raw = ud ? nullptr : onset;
+      o.unwrapped = u_onset;
+      o.ud = ud;
+      o.note_raw = note;
+      o.edge = m->edge.p;
+      launch_conv_tc(m->yhl.p, m->tc_onset.dev, o, nb, ystride, m->n_sms, st);
     }
   } else {
     {
@@ -439,7 +457,9 @@ int forward_chunk(bp_model* m, const float* audio, const WinDesc* desc, int nb, 
     unwrap_kernel<<<dim3(16, nb), 256, 0, st>>>(contour, u_contour, ud, kContourBins);
   }
   CKL();
-  m->launches += 5 + 2 + 1 + (m->path >= 1 ? 7 : 6);  // decimation (4 + tail), min/max init + CQT, log-normalise, convs
+  // decimation (4 + tail), min/max init + CQT, log-normalise (+ split); tensor-core convs: 3 x (conv + edge fix) +
+  // contour split (path 2: + contour conv2 instead of one edge fix); FP32 path: 6 convs
+  m->launches += 5 + 2 + 1 + (m->path >= 1 ? 7 : 6);
   if (ud) m->launches += m->path == 0 ? 3 : (m->path == 2 ? 1 : 0);  // separate unwrap copies
   m->last_path = m->path;
   return BP_OK;
@@ -546,9 +566,13 @@ static int model_init(bp_model* m, const std::vector<float>& params, const cudaD
   tc_setup();
   cqt_tc_setup();
   m->n_sms = prop.multiProcessorCount;
-  // largest chunk whose 128-row M-tiles (175 rows per window in the note layer, 174 in the others) make at most two
-  // per SM: 216 windows on 148 SMs (217 would leave one M-tile for a third, almost empty wave of the note layer)
-  m->chunk = std::max(1, 2 * m->n_sms * 128 / tc_note_spec().rows_per_window);
+  // largest chunk whose M-tiles make at most two per SM in every layer.  M-tiles advance by 128 - (KH2 - 1) rows (they
+  // overlap by the time taps of the fused conv2): 122 rows of 175 per window in the note layer, 124 / 126 of 174 in the
+  // contour / onset layers -> 206 windows on 148 SMs
+  {
+    const TcConvSpec ns = tc_note_spec();
+    m->chunk = std::max(1, 2 * m->n_sms * (128 - (ns.KH2 - 1)) / ns.rows_per_window);
+  }
   rc = derive(m, m->stream);
   if (rc) return rc;
   CK(cudaStreamSynchronize(m->stream));
@@ -564,7 +588,7 @@ void bp_model_destroy(bp_model_t* m) {
     if (g_const_owner[m->device] == m) g_const_owner[m->device] = nullptr;
   }
   m->chain.release(); m->y.release(); m->c1.release(); m->n1.release(); m->o1.release();
-  m->raw_note.release(); m->raw_onset.release(); m->raw_contour.release(); m->minmax.release();
+  m->raw_note.release(); m->raw_onset.release(); m->raw_contour.release(); m->minmax.release(); m->edge.release();
   m->wdesc.release(); m->udesc.release(); m->st_audio.release(); m->st_note.release(); m->st_onset.release();
   m->st_contour.release(); m->d_frame_off.release(); m->d_slot_off.release(); m->d_note_base.release();
   m->energy.release(); m->d_amp.release(); m->candbits.release(); m->max_onset.release(); m->max_fd.release();

@@ -1,6 +1,6 @@
 // Convolution stack: the FP32 FFMA kernels (path 0: accuracy reference on device; path 2 uses the channels-last
-// contour conv2 below) and the tap-sum kernel that finishes the three single-output convolutions after the fused
-// epilogues of the tensor-core kernels (path 1, tc_conv.cu).
+// contour conv2 below).  On the default path the second convolutions are fused into the epilogues of the tensor-core
+// kernels (tc_conv.cu).
 //
 // Replaces nodes 213-247 of the deployed graph:
 //   HarmonicStacking.call   reference: basic_pitch/nn.py:69-88   (never materialised: the 8 "channels"
@@ -13,7 +13,6 @@
 // bins (conflict-free for stride 1 and 3), every loaded input feeds COB FMAs, weights are warp-uniform
 // float4 broadcasts.
 // conv1_kernel: the C_out = 1 convolutions with a 4 x 4 register tile per thread (planar or channels-last input).
-// halo_tapsum_kernel: time-tap / halo sums + sigmoid (+ unwrap, + bf16 split of the contour) behind the fused epilogues.
 #include "kernels.cuh"
 
 namespace bp {
@@ -312,120 +311,6 @@ __global__ void __launch_bounds__(Cfg::THREADS) conv1_kernel(In in, const float*
   }
 }
 
-// ------------------------------------------------------------------------------------------------
-// The single-output second convolutions (contour conv2 models.py:254-262, note conv2 :282-290, onset conv2 :305-313)
-// after the fused epilogues of the tensor-core kernels (tc_conv.cu).  Those reduce channels and frequency taps inside
-// the thread that owns a frame and emit, per frequency tile of FLT bins, KH time-tap planes of J = FLT + 2*HALO output
-// offsets (J - FLT halo columns belong to the neighbouring tiles), time-fastest:  Q[B][tiles][KH][J][172].  Left here:
-//   out[t][f] = sigmoid(bias + sum_dt ( Q[ft][dt][r + HALO][t + dt - PT] + Q[neighbour][dt][r + HALO -/+ FLT][..] )
-//                       (+ sum_{dt,df} x[t + dt - PT][f + df - 1] * wx[dt*3 + df]   -- onset: the note input channel) )
-// with ft = f / FLT, r = f % FLT, the neighbour term only for the HALO outer bins on either side of a tile.
-// A CTA computes a 32 (t) x 32 (f) tile with t on the lanes (coalesced 128-byte reads), transposes through shared
-// memory for the frequency-fastest posteriorgram, and (contour) also stores the bf16 hi/lo split in the row layout of
-// the note conv's tensor-core kernel.
-// ------------------------------------------------------------------------------------------------
-template <int FLT, int HALO, int KH, int PT, int WOUT, bool EXTRA, bool SPLIT>
-__global__ void __launch_bounds__(256) halo_tapsum_kernel(const float* __restrict__ Q, const float* __restrict__ x,
-                                                          const float* __restrict__ wx, const float* __restrict__ bias,
-                                                          float* __restrict__ out, SplitOut so,
-                                                          const UnwrapDesc* __restrict__ ud, float* __restrict__ out_raw) {
-  __shared__ float tile[32][33];
-  constexpr int kTiles = (WOUT + FLT - 1) / FLT, kJ = FLT + 2 * HALO;
-  constexpr int kPlane = kJ * kFrames;  // one (tile, dt) plane
-  constexpr int kTapStep = kPlane + 1;  // next time tap: next plane, next input frame (t + dt - PT)
-  static_assert((FLT & (FLT - 1)) == 0, "FLT is a power of two");
-  const int b = blockIdx.z;
-  const int t0 = blockIdx.x * 32, f0 = blockIdx.y * 32;
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const float* Qb = Q + (size_t)b * kTiles * KH * kPlane;
-  const float bv = __ldg(bias);
-  const int t = t0 + tx;
-  unsigned dmask = 0;  // time taps whose input frame t + dt - PT exists
-#pragma unroll
-  for (int dt = 0; dt < KH; ++dt)
-    if ((unsigned)(t + dt - PT) < (unsigned)kFrames) dmask |= 1u << dt;
-  if (t >= kFrames) dmask = 0;
-  // onset: the 3 x 3 taps over the note posteriorgram (frequency-fastest rows) are staged through shared memory so that
-  // the global reads run along f while the lanes of the sum below run along t
-  __shared__ float xs[EXTRA ? 34 : 1][EXTRA ? 35 : 1];
-  float wxr[EXTRA ? 9 : 1];
-  if (EXTRA) {
-#pragma unroll
-    for (int k = 0; k < 9; ++k) wxr[k] = __ldg(wx + k);
-    for (int idx = threadIdx.x; idx < 34 * 34; idx += 256) {
-      const int rr = idx / 34, cc = idx - rr * 34;
-      const int tt = t0 - 1 + rr, ff = f0 - 1 + cc;
-      xs[rr][cc] = ((unsigned)tt < (unsigned)kFrames && (unsigned)ff < (unsigned)WOUT)
-                       ? __ldg(x + ((size_t)b * kFrames + tt) * WOUT + ff)
-                       : 0.f;
-    }
-    __syncthreads();
-  }
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int fl = ty + 8 * i;
-    const int f = f0 + fl;
-    float acc = bv;
-    if (f < WOUT && dmask) {
-      const int ft = f / FLT, r = f % FLT;
-      const float* q = Qb + (ft * KH * kJ + r + HALO) * kFrames + (t - PT);
-#pragma unroll
-      for (int dt = 0; dt < KH; ++dt)
-        if ((dmask >> dt) & 1u) acc += __ldg(q + dt * kTapStep);
-      const int ft2 = (r < HALO) ? ft - 1 : ((r >= FLT - HALO) ? ft + 1 : -1);  // neighbour whose halo covers this bin
-      if (ft2 >= 0 && ft2 < kTiles) {
-        const int j2 = (r < HALO) ? r + HALO + FLT : r + HALO - FLT;
-        const float* q2 = Qb + (ft2 * KH * kJ + j2) * kFrames + (t - PT);
-#pragma unroll
-        for (int dt = 0; dt < KH; ++dt)
-          if ((dmask >> dt) & 1u) acc += __ldg(q2 + dt * kTapStep);
-      }
-      if (EXTRA) {  // (KH == 3, PT == 1; frames / bins outside the image are zeros in xs)
-#pragma unroll
-        for (int dt = 0; dt < 3; ++dt)
-#pragma unroll
-          for (int df = 0; df < 3; ++df) acc = fmaf(xs[tx + dt][fl + df], wxr[dt * 3 + df], acc);
-      }
-    }
-    tile[fl][tx] = __fdividef(1.f, 1.f + __expf(-acc));
-  }
-  __syncthreads();
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int tl = ty + 8 * i;
-    const int t = t0 + tl, f = f0 + tx;
-    if (t < kFrames && f < WOUT) {
-      const float v = tile[tx][tl];
-      if (ud) {  // unwrap fused: centre frames go straight to their place in the file's posteriorgram
-        const UnwrapDesc d = ud[b];
-        const int tt = t - kOverlapHalf;
-        if ((unsigned)tt < (unsigned)max(d.rows, 0)) out[(size_t)(d.dst_base + tt) * WOUT + f] = v;
-        if (out_raw) out_raw[((size_t)b * kFrames + t) * WOUT + f] = v;
-      } else {
-        out[((size_t)b * kFrames + t) * WOUT + f] = v;
-      }
-    }
-  }
-  if (SPLIT && so.planes && threadIdx.x < 128) {  // 32 frames x 4 chunks of 8 bins -> one 16-byte store per plane
-    const int tl = threadIdx.x & 31, c = threadIdx.x >> 5;
-    const int t = t0 + tl, f = f0 + 8 * c;
-    if (t < kFrames && f < WOUT) {
-      __align__(16) __nv_bfloat16 hi[8], lo[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float o = tile[8 * c + j][tl];
-        hi[j] = __float2bfloat16_rn(o);
-        lo[j] = __float2bfloat16_rn(o - __bfloat162float(hi[j]));
-      }
-      const size_t d = (size_t)so.lead + (size_t)b * so.rows_per_window + t;
-      const size_t off = ((size_t)(f >> 3) * so.rows_total + d) * 8;
-      const size_t plane = (size_t)so.chunks8 * so.rows_total * 8;
-      *reinterpret_cast<uint4*>(so.planes + off) = *reinterpret_cast<const uint4*>(hi);
-      *reinterpret_cast<uint4*>(so.planes + plane + off) = *reinterpret_cast<const uint4*>(lo);
-    }
-  }
-}
-
 //                           CIN CIC KH KW PT PL WOUT TR
 using Contour2Cfg1 = Conv1Cfg<8, 4, 5, 5, 2, 2, 264, 11>;
 using Contour2CfgN = Conv1Cfg<8, 4, 5, 5, 2, 2, 264, 11>;  // channels-last input, two passes of 4 channels
@@ -480,25 +365,6 @@ void launch_contour2_tc(const float* c1, const CnnWeights& w, float* contour, __
   const TcConvSpec sp = tc_note_spec();
   launch1<Contour2CfgN>(NhwcIn<8, 264>{c1}, w.contour2_wT, w.contour2_b, contour, n, st,
                         SplitOut{chl, rows_total, sp.chunks8, sp.rows_per_window, sp.lead_rows});
-}
-void launch_contour_tapsum(const float* q, const CnnWeights& w, float* out, __nv_bfloat16* chl, int rows_total, int n,
-                           cudaStream_t st, const UnwrapDesc* ud) {
-  const TcConvSpec sp = tc_note_spec();
-  halo_tapsum_kernel<16, 2, 5, 2, kContourBins, false, true>
-      <<<dim3((kFrames + 31) / 32, (kContourBins + 31) / 32, n), 256, 0, st>>>(
-          q, nullptr, nullptr, w.contour2_b, out, SplitOut{chl, rows_total, sp.chunks8, sp.rows_per_window, sp.lead_rows}, ud,
-          nullptr);
-}
-void launch_note_tapsum(const float* q, const CnnWeights& w, float* note_raw, int n, cudaStream_t st, const UnwrapDesc* ud,
-                        float* note_unwrapped) {
-  halo_tapsum_kernel<4, 1, 7, 3, kPitches, false, false><<<dim3((kFrames + 31) / 32, (kPitches + 31) / 32, n), 256, 0, st>>>(
-      q, nullptr, nullptr, w.note2_b, ud ? note_unwrapped : note_raw, SplitOut{nullptr, 0, 0, 0, 0}, ud, ud ? note_raw : nullptr);
-}
-void launch_onset_tapsum(const float* q, const float* note_raw, const CnnWeights& w, float* out, int n, cudaStream_t st,
-                         const UnwrapDesc* ud) {
-  // channel 0 of the onset conv2 weights multiplies the note posteriorgram (models.py:305: concat[note, onset1])
-  halo_tapsum_kernel<4, 1, 3, 1, kPitches, true, false><<<dim3((kFrames + 31) / 32, (kPitches + 31) / 32, n), 256, 0, st>>>(
-      q, note_raw, w.onset2_wT, w.onset2_b, out, SplitOut{nullptr, 0, 0, 0, 0}, ud, nullptr);
 }
 void launch_note1(const float* contour, const CnnWeights& w, float* n1, int n, cudaStream_t st) {
   launch<Note1Cfg>(PlanarIn<1, 264>{contour}, w.note1_wT, w.note1_b, n1, n, st);

@@ -38,14 +38,15 @@ void launch_onset2(const float* note, const float* o1, const CnnWeights& w, floa
                    cudaStream_t st);
 
 
-// ---- tc_conv.cu (tcgen05 path of the three wide convolutions) ------------------------------------
+// ---- tc_conv.cu (tcgen05 path of the three wide convolutions, each with its following conv fused) ------------
 struct TcConvSpec {
   int KH, KW, SF, PT, PL, COUT, FLT, WOUT;  // taps, frequency stride, pads, channels, bins per 128-column tile, output bins
   int n_ci;                                 // input channels (harmonics of y, or 1 for the contour posteriorgram)
   int shifts[8];                            // frequency shift of every input channel (harmonic stacking)
   int data_bins, chunks8;                   // bins of the input rows and 8-bin chunks of the split layout (even)
-  int rows_per_window, lead_rows;           // row layout of the split input: 172 frames + >= PT zero rows per window
-  int epi, taps;                            // epilogue: 0 = bias+ReLU channels-last; 1/2 = fused reduction to `taps` planes
+  int rows_per_window, lead_rows;           // row layout of the split input: 172 frames + zero rows per window
+  int epi;                                  // 0 contour, 1 onset, 2 note
+  int KH2, HALO, G0;                        // fused next conv: time taps, frequency halo; tiles of a group are G0 apart
 };
 TcConvSpec tc_contour_spec();
 TcConvSpec tc_onset_spec();
@@ -68,36 +69,44 @@ struct TcConvDev {
 };
 int tc_upload_program(int layer, const TcConvPlan& plan, cudaStream_t st);  // 0 on success
 void tc_upload_epilogue(const float* contour1_b, const float* onset1_b, const float* note1_b, const float* onset2_w,
-                        const float* note2_w, const float* contour2_w, cudaStream_t st);
+                        const float* note2_w, const float* contour2_w, const float* contour2_b, const float* onset2_b,
+                        const float* note2_b, cudaStream_t st);
 int tc_rows_total(int n_windows, int rows_per_window);
+size_t tc_edge_floats(const TcConvSpec& spec, int n_windows);  // size of the edge buffer of a fused layer
 void tc_setup();
-void launch_split(const float* src, __nv_bfloat16* dst, const TcConvSpec& spec, int n_windows, int rows_stride,
-                  cudaStream_t st);
-// rows_stride: row stride of the split layout (>= tc_rows_total(n_windows, ...)); fixed per model so that rows the
-// kernels never write (separators, pads) keep their zeros across batches of different size
-// fuse_next (contour layer only): reduce the output against the following conv in the epilogue (tap planes Q, see
-// halo_tapsum_kernel) instead of storing the channels-last activations
-void launch_conv_tc(const __nv_bfloat16* data, const TcConvDev& dev, float* out, int n_windows, int rows_stride, int n_sms,
-                    cudaStream_t st, bool fuse_next = false);
 // Where window w's centre frames go in the unwrapped (per-file) posteriorgrams (reference: inference.py:247-279).
 struct UnwrapDesc {
   long long dst_base;  // first output frame this window contributes to
   int rows;            // how many of its 142 centre frames are kept (may be <= 0)
   int pad;
 };
-// The tap-sum kernels write [B][172][*] rows, or, with `ud`, only the centre frames of every window straight to their
-// unwrapped position in `out` (note: additionally the raw rows to `note_raw`, which the onset conv reads).
-void launch_contour_tapsum(const float* q, const CnnWeights& w, float* out, __nv_bfloat16* chl, int rows_total,
-                           int n_windows, cudaStream_t st, const UnwrapDesc* ud = nullptr);
+// NormalizedLog + folded BatchNorm of the CQT log-magnitudes (in place, fp32) and their bf16 hi/lo split in the
+// k-chunk-major row layout of tc_contour_spec() / tc_onset_spec() in one pass.
+// rows_stride: row stride of the split layout (>= tc_rows_total(n_windows, ...)); fixed per model so that rows the
+// kernels never write (separators, pads) keep their zeros across batches of different size
+void launch_lognorm_split(float* y, const unsigned int* minmax, const float* bn, __nv_bfloat16* dst, const TcConvSpec& spec,
+                          int n_windows, int rows_stride, cudaStream_t st);
+// raw contour posteriorgram [B][172][264] -> split operand of the note conv (+ centre frames to their unwrapped place)
+void launch_contour_split(const float* raw_contour, __nv_bfloat16* chl, int n_windows, int rows_stride, cudaStream_t st,
+                          const UnwrapDesc* ud = nullptr, float* unwrapped = nullptr);
+// Outputs of a fused layer: the finished posteriorgram rows go to `raw` ([B][172][WOUT], may be null) and / or, with `ud`,
+// the centre frames of every window straight to their unwrapped position in `unwrapped`.  EPI 0 (path 2): `raw` is the
+// channels-last activation buffer.
+struct TcOut {
+  float* raw = nullptr;
+  float* unwrapped = nullptr;
+  const UnwrapDesc* ud = nullptr;
+  const float* note_raw = nullptr;  // onset layer: the raw note posteriorgram (input channel 0 of its conv2)
+  float* edge = nullptr;            // >= tc_edge_floats(spec, n_windows) floats of scratch
+};
+// fuse_next (contour layer only; the other two always fuse): also compute the following conv in the epilogue instead
+// of storing the channels-last activations
+void launch_conv_tc(const __nv_bfloat16* data, const TcConvDev& dev, const TcOut& out, int n_windows, int rows_stride,
+                    int n_sms, cudaStream_t st, bool fuse_next = false);
 // contour conv2 on the channels-last output of the tensor-core contour conv; also emits the bf16 hi/lo split of the
 // contour posteriorgram in the layout of tc_note_spec()
 void launch_contour2_tc(const float* c1_nhwc, const CnnWeights& w, float* contour, __nv_bfloat16* chl, int rows_total,
                         int n_windows, cudaStream_t st);
-// second convs after the fused channel reduction: shifted sums over the tap planes (+ the note input of the onset conv)
-void launch_note_tapsum(const float* q, const CnnWeights& w, float* note_raw, int n_windows, cudaStream_t st,
-                        const UnwrapDesc* ud = nullptr, float* note_unwrapped = nullptr);
-void launch_onset_tapsum(const float* q, const float* note_raw, const CnnWeights& w, float* out, int n_windows,
-                         cudaStream_t st, const UnwrapDesc* ud = nullptr);
 
 // ---- cqt_tc.cu (tcgen05 path of the constant-Q projection, three-way bf16 split) ----------------------------
 void build_cqt_tc_weights(const float* cqt_real, const float* cqt_imag, std::vector<uint16_t>& out);

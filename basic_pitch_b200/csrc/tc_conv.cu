@@ -7,11 +7,18 @@
 // conv + ReLU, reference: basic_pitch/models.py:295-304) of the deployed graph, and the harmonic stacking in
 // front of them (reference: basic_pitch/nn.py:69-88), which is folded into the weight operand and never
 // materialised; node 238/239 (note conv1 + ReLU, models.py:270-279) reads the contour posteriorgram instead.
-// One kernel template, three specs (TcConvSpec).  The epilogue (EPI 1 / 2 / 3 = onset / note / contour) also reduces
+// One kernel template, three specs (TcConvSpec).  The epilogue (EPI 1 / 2 / 3 = onset / note / contour) also computes
 // the FOLLOWING single-output convolution (onset conv2 models.py:305-313, note conv2 :282-290, contour conv2 :254-262)
-// over its input channels and frequency taps inside the thread that owns the frame and stores time-tap planes with
-// halo columns, so the 8- / 32-channel activations never reach HBM and the second convs degenerate to a sum of 5 / 3 /
-// 7 time-tap planes (cnn.cu: halo_tapsum_kernel).  EPI 0 stores the contour activations channels-last (path 2, tests).
+// completely, so neither the 8- / 32-channel activations nor any partial sums of them reach HBM:
+//   * channels and frequency taps are reduced inside the thread that owns the frame (packed FP32 FMAs),
+//   * the time taps are summed across the lanes of the warp (the 32 lanes hold 32 consecutive frames: shuffles) and
+//     across the four epilogue warps of an accumulator slot through a 480-byte shared-memory exchange; M-tiles overlap
+//     by KH2 - 1 rows, so every frame is complete in exactly one tile,
+//   * the frequency halo between neighbouring tiles is a register carry: a slot walks its frequency tiles in ascending
+//     order; only where two tile RANGES meet (slot 0 | slot 1, or the group splits of a small batch) the two partial
+//     sums go to a small edge buffer and edge_fix_kernel finishes those 4 (contour) / 2 bins,
+//   * bias, sigmoid (+ the note input channel of the onset conv2, + unwrap inference.py:247-279) and the store.
+// EPI 0 stores the contour activations channels-last (path 2, activation-level tests).
 //
 // Formulation ("Toeplitz along frequency on aligned chunks")
 //   rows  m = b*174 + t            time frames of all windows of the chunk, two zero rows between windows
@@ -32,8 +39,8 @@
 // (hi*hi + hi*lo + lo*hi) in fp32, which keeps the posteriorgrams within ~1e-5 of the FP32 path
 // (SURVEY.md Appendix C.4); a single bf16 product would miss the 1e-3 bar.
 //
-// Work decomposition: item = (M-tile of 128 rows, split s of S over the frequency groups); group = up to 2
-// frequency tiles that share weight tiles (2 x 128 TMEM columns; the 512 columns hold two groups, so the
+// Work decomposition: item = (M-tile of 128 rows, split s of S over the frequency groups); group g = the two
+// frequency tiles {g, g + G0} (they share weight tiles; 2 x 128 TMEM columns; the 512 columns hold two groups, so the
 // epilogue of one group overlaps the MMAs of the next).  A CTA (1 per SM, persistent) walks items
 // i = blockIdx.x, +gridDim.x, ...:
 //   warp 8      producer: bulk-copies the (128+KH-1) x 320 bf16 hi/lo data tile (k-chunk-major) once per item and
@@ -43,8 +50,7 @@
 //               base + precomputed offset, 3 x tcgen05.mma per step by one elected lane, tcgen05.commit frees the
 //               weight stage / publishes the accumulators
 //   warps 0-3, 4-7  epilogue, one warpgroup-like set of 4 warps (= the 4 TMEM lane quadrants) per accumulator slot:
-//               tcgen05.ld the accumulator columns, + bias, ReLU, then the fused reduction of the next conv on packed
-//               FP32 FMAs and time-fastest stores of the tap planes
+//               tcgen05.ld the accumulator columns, + bias, ReLU, then the whole next conv as described above
 #include <cuda_bf16.h>
 
 #include <algorithm>
@@ -68,7 +74,11 @@ constexpr int kThreads = 352;  // 11 warps: 2 x 4 epilogue warps, producer, 2 MM
 // The issue arbiter of an SM sub-partition prefers the highest warp id, so the latency-critical single-thread roles
 // (producer, MMA issuers) get the highest ids and are never starved by the FFMA streams of the epilogue warps.
 constexpr int kProducerWarp = 8, kMmaWarp0 = 9, kMmaWarp1 = 10;
-constexpr int kSmemBytes = kMaxDataBytes + kStages * kTileBytes + 512;
+// time-halo exchange between the four epilogue warps of a slot: [slot 2][buffer 2][warp 4][kXchgFloats]
+constexpr int kXchgFloats = 120;  // contour: 6 published lanes x 20 output offsets (note 12 x 6, onset 2 x 6)
+constexpr int kXchgBytes = 2 * 2 * 4 * kXchgFloats * 4;
+constexpr int kSmemBytes = kMaxDataBytes + kStages * kTileBytes + kXchgBytes + 512;
+constexpr int kMaxEdges = 32;  // frequency tiles at which a tile range may start (edge buffer slots)
 // step word of a slot: [0,14) A start-address offset >> 4, [15] first MMA into that accumulator; kNoUse = the
 // slot's frequency tile does not use this step's weight tile
 constexpr uint32_t kUseFirstAcc = 1u << 15, kNoUse = 0xffffffffu;
@@ -91,10 +101,10 @@ static inline float bf2f(uint16_t h) {
   return f;
 }
 
-//                                      KH KW SF PT PL COUT FLT WOUT n_ci  shifts                              bins ch8 rows/win lead epi taps
-TcConvSpec tc_contour_spec() { return {3, 39, 1, 1, 19, 8, 16, 264, 8, {-36, 0, 36, 57, 72, 84, 93, 101}, 309, 40, 174, 2, 0, 0}; }
-TcConvSpec tc_onset_spec() { return {5, 5, 3, 2, 1, 32, 4, 88, 8, {-36, 0, 36, 57, 72, 84, 93, 101}, 309, 40, 174, 2, 1, 9}; }
-TcConvSpec tc_note_spec() { return {7, 7, 3, 3, 2, 32, 4, 88, 1, {0, 0, 0, 0, 0, 0, 0, 0}, 264, 34, 175, 3, 2, 21}; }
+//                                      KH KW SF PT PL COUT FLT WOUT n_ci  shifts                              bins ch8 rows/win lead epi KH2 HALO G0
+TcConvSpec tc_contour_spec() { return {3, 39, 1, 1, 19, 8, 16, 264, 8, {-36, 0, 36, 57, 72, 84, 93, 101}, 309, 40, 174, 3, 0, 5, 2, 9}; }
+TcConvSpec tc_onset_spec() { return {5, 5, 3, 2, 1, 32, 4, 88, 8, {-36, 0, 36, 57, 72, 84, 93, 101}, 309, 40, 174, 3, 1, 3, 1, 12}; }
+TcConvSpec tc_note_spec() { return {7, 7, 3, 3, 2, 32, 4, 88, 1, {0, 0, 0, 0, 0, 0, 0, 0}, 264, 34, 175, 6, 2, 7, 1, 12}; }
 
 void TcConvPlan::build(const TcConvSpec& sp, const float* W /* [COUT][n_ci][KH][KW] */) {
   using namespace tc;
@@ -109,9 +119,10 @@ void TcConvPlan::build(const TcConvSpec& sp, const float* W /* [COUT][n_ci][KH][
   const int data_rows = kMTile + sp.KH - 1;
   const int lbo16 = data_rows;  // (rows * 16 B) >> 4
   // K = 16 steps start on 8-bin chunk boundaries (the k-chunk-major layout makes any chunk index a legal
-  // descriptor start), so frequency tiles d apart share weight tiles when SF*FLT*d is a multiple of 8 bins
-  int stride = 1;
-  while ((sp.SF * sp.FLT * stride) % 8 != 0) ++stride;
+  // descriptor start), so frequency tiles d apart share weight tiles when SF*FLT*d is a multiple of 8 bins; the two
+  // tiles of a group are G0 apart: slot 0 walks tiles 0 .. G0-1, slot 1 tiles G0 .. n_ft-1, both in ascending order
+  // (the fused epilogue carries the frequency halo of the next conv from tile to tile in registers)
+  const int stride = sp.G0;
 
   // weight tiles are de-duplicated by content (boundary clipping makes otherwise equal keys differ and vice versa)
   std::unordered_map<uint64_t, std::vector<int>> by_hash;
@@ -161,18 +172,11 @@ void TcConvPlan::build(const TcConvSpec& sp, const float* W /* [COUT][n_ci][KH][
     return n_keys++;
   };
 
-  // groups: pairs {ft, ft + stride} (or singles)
-  std::vector<bool> taken(n_ft, false);
+  // groups: pairs {g, g + G0} (or singles)
   group_step_off.push_back(0);
   n_uses = 0;
-  for (int ft_a = 0; ft_a < n_ft; ++ft_a) {
-    if (taken[ft_a]) continue;
-    taken[ft_a] = true;
-    int ft_b = ft_a + stride;
-    if (ft_b < n_ft && !taken[ft_b])
-      taken[ft_b] = true;
-    else
-      ft_b = -1;
+  for (int ft_a = 0; ft_a < stride; ++ft_a) {
+    const int ft_b = ft_a + stride < n_ft ? ft_a + stride : -1;
     const int fts[2] = {ft_a, ft_b};
     group_ft.push_back(ft_a);
     group_ft.push_back(ft_b);
@@ -246,22 +250,27 @@ __constant__ uint32_t c_prog[3][2][tc::kMaxSteps];  // [layer][slot][step]
 __constant__ int c_tile_seq[3][tc::kMaxSteps];       // [layer][step] -> weight tile id
 __constant__ int c_group_step_off[3][tc::kMaxGroups + 1];
 __constant__ int c_group_ft[3][2 * tc::kMaxGroups];
-// epilogue constants: conv1 bias and the weights of the fused channel reduction (conv2), [channel][tap]
+// epilogue constants: conv1 bias, conv2 bias, and the weights of the fused conv2, [channel][tap]
 __constant__ float c_bias1[3][32];
+__constant__ float c_bias2[3];
 // onset / note conv2 weights as pairs of time taps for the packed FMAs: [channel][df][pair p] = (w2[c][2p][df], w2[c][2p+1][df])
 // (onset 3 time taps -> 2 pairs, note 7 -> 4 pairs, the odd last one padded with 0)
 __constant__ float2 c_red_onset[32][3][2];
 __constant__ float2 c_red_note[32][3][4];
+// channel 0 of the onset conv2 multiplies the note posteriorgram (models.py:305: concat[note, onset1]): [dt][df]
+__constant__ float c_onset_note_w[9];
 // contour conv2 [dt][channel][6 pairs]: an input bin at even offset bl feeds the output pairs (bl,bl+1), (bl+2,bl+3),
 // (bl+4,bl+5) with weights (w4,w3), (w2,w1), (w0,0); at odd bl the pairs (bl-1,bl), (bl+1,bl+2), (bl+3,bl+4) with
 // (0,w4), (w3,w2), (w1,w0)   [output offset j = bl + 4 - df]
 __constant__ float2 c_red_contour[5][8][6];
 
 void tc_upload_epilogue(const float* contour1_b, const float* onset1_b, const float* note1_b, const float* onset2_w,
-                        const float* note2_w, const float* contour2_w, cudaStream_t st) {
+                        const float* note2_w, const float* contour2_w, const float* contour2_b, const float* onset2_b,
+                        const float* note2_b, cudaStream_t st) {
   float b[3][32] = {};
   for (int i = 0; i < 8; ++i) b[0][i] = contour1_b[i];
   for (int i = 0; i < 32; ++i) b[1][i] = onset1_b[i], b[2][i] = note1_b[i];
+  const float b2[3] = {contour2_b[0], onset2_b[0], note2_b[0]};
   float2 ro[32][3][2], rn[32][3][4];
   for (int c = 0; c < 32; ++c)
     for (int df = 0; df < 3; ++df) {
@@ -282,8 +291,10 @@ void tc_upload_epilogue(const float* contour1_b, const float* onset1_b, const fl
     }
   cudaMemcpyToSymbolAsync(c_red_contour, rc, sizeof(rc), 0, cudaMemcpyHostToDevice, st);
   cudaMemcpyToSymbolAsync(c_bias1, b, sizeof(b), 0, cudaMemcpyHostToDevice, st);
+  cudaMemcpyToSymbolAsync(c_bias2, b2, sizeof(b2), 0, cudaMemcpyHostToDevice, st);
   cudaMemcpyToSymbolAsync(c_red_onset, ro, sizeof(ro), 0, cudaMemcpyHostToDevice, st);
   cudaMemcpyToSymbolAsync(c_red_note, rn, sizeof(rn), 0, cudaMemcpyHostToDevice, st);
+  cudaMemcpyToSymbolAsync(c_onset_note_w, onset2_w, 9 * sizeof(float), 0, cudaMemcpyHostToDevice, st);
   cudaStreamSynchronize(st);
 }
 
@@ -302,12 +313,28 @@ int tc_upload_program(int layer, const TcConvPlan& pl, cudaStream_t st) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// src (fp32, [B][172][bins]) -> bf16 hi/lo planes in the k-chunk-major row layout the MMA reads:
+// fp32 rows -> bf16 hi/lo planes in the k-chunk-major row layout the MMA reads:
 //   dst[plane][q8 (chunks8)][row d (rows_total)][8],  d = lead + b*rows_per_window + t, every other row zero.
-// Used for y (309 bins -> 40 chunks) and for the contour posteriorgram (264 bins -> 34 chunks).
+// lognorm_split_kernel: the log-magnitude of the CQT kernel -> NormalizedLog (reference: layers/signal.py:177-183:
+//   (L - min) / (max - min), 0 when max == min) + folded BatchNorm (models.py:188-189), written back in place as fp32
+//   (FP32 path, activation tests) AND as the split operand of the contour / onset convs (309 bins -> 40 chunks).
+// contour_split_kernel: the contour posteriorgram (264 bins -> 34 chunks) as the operand of the note conv, and its
+//   centre frames to their unwrapped position (reference: inference.py:247-279).
 // ------------------------------------------------------------------------------------------------
-__global__ void split_kernel(const float* __restrict__ src, int bins, __nv_bfloat16* __restrict__ dst, int n_windows,
-                             int rows_used, int rows_total /* stride */, int chunks8, int rows_per_window, int lead) {
+__device__ __forceinline__ void store_split8(const float (&v)[8], __nv_bfloat16* dst, size_t off, size_t plane) {
+  __align__(16) __nv_bfloat16 hi[8], lo[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    hi[j] = __float2bfloat16_rn(v[j]);
+    lo[j] = __float2bfloat16_rn(v[j] - __bfloat162float(hi[j]));
+  }
+  *reinterpret_cast<uint4*>(dst + off) = *reinterpret_cast<const uint4*>(hi);
+  *reinterpret_cast<uint4*>(dst + plane + off) = *reinterpret_cast<const uint4*>(lo);
+}
+
+__global__ void lognorm_split_kernel(float* __restrict__ y, const unsigned int* __restrict__ minmax,
+                                     const float* __restrict__ bn, __nv_bfloat16* __restrict__ dst, int n_windows,
+                                     int rows_used, int rows_total /* stride */, int chunks8, int rows_per_window, int lead) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // one (row, q8) per thread
   const long long total = (long long)rows_used * chunks8;
   if (idx >= total) return;
@@ -320,22 +347,45 @@ __global__ void split_kernel(const float* __restrict__ src, int bins, __nv_bfloa
   if (m >= 0) {
     const int b = m / rows_per_window, t = m - b * rows_per_window;
     if (b < n_windows && t < kFrames) {
-      const float* p = src + ((size_t)b * kFrames + t) * bins + q8 * 8;
+      const float bn_scale = __ldg(bn), bn_bias = __ldg(bn + 1);
+      const float mn = ordered_to_float(minmax[2 * b]);
+      const float mx = __fsub_rn(ordered_to_float(minmax[2 * b + 1]), mn);
+      float* p = y + ((size_t)b * kFrames + t) * kCqtBins + q8 * 8;
 #pragma unroll
       for (int j = 0; j < 8; ++j)
-        if (q8 * 8 + j < bins) v[j] = __ldg(p + j);
+        if (q8 * 8 + j < kCqtBins) {
+          const float q = (mx == 0.f) ? 0.f : __fdiv_rn(__fsub_rn(p[j], mn), mx);
+          v[j] = __fadd_rn(__fmul_rn(q, bn_scale), bn_bias);
+          p[j] = v[j];
+        }
     }
   }
-  __align__(16) __nv_bfloat16 hi[8], lo[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    hi[j] = __float2bfloat16_rn(v[j]);
-    lo[j] = __float2bfloat16_rn(v[j] - __bfloat162float(hi[j]));
+  store_split8(v, dst, ((size_t)q8 * rows_total + d) * 8, (size_t)chunks8 * rows_total * 8);
+}
+
+__global__ void contour_split_kernel(const float* __restrict__ raw /* [B][172][264] */, __nv_bfloat16* __restrict__ dst,
+                                     int n_windows, int rows_total, int chunks8, int rows_per_window, int lead,
+                                     const UnwrapDesc* __restrict__ ud, float* __restrict__ unwrapped) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // one (frame, q8) per thread, frames fastest
+  const long long total = (long long)n_windows * kFrames * (kContourBins / 8);
+  if (idx >= total) return;
+  const int fr = (int)(idx % ((long long)n_windows * kFrames));
+  const int q8 = (int)(idx / ((long long)n_windows * kFrames));
+  const int b = fr / kFrames, t = fr - b * kFrames;
+  const float4* p = reinterpret_cast<const float4*>(raw + (size_t)fr * kContourBins + q8 * 8);
+  const float4 x0 = __ldg(p), x1 = __ldg(p + 1);
+  const float v[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+  const size_t d = (size_t)lead + (size_t)b * rows_per_window + t;
+  store_split8(v, dst, ((size_t)q8 * rows_total + d) * 8, (size_t)chunks8 * rows_total * 8);
+  if (ud) {
+    const UnwrapDesc u = ud[b];
+    const int tt = t - kOverlapHalf;
+    if ((unsigned)tt < (unsigned)max(u.rows, 0)) {
+      float4* o = reinterpret_cast<float4*>(unwrapped + (size_t)(u.dst_base + tt) * kContourBins + q8 * 8);
+      o[0] = x0;
+      o[1] = x1;
+    }
   }
-  const size_t plane = (size_t)chunks8 * rows_total * 8;
-  const size_t off = ((size_t)q8 * rows_total + d) * 8;
-  *reinterpret_cast<uint4*>(dst + off) = *reinterpret_cast<const uint4*>(hi);
-  *reinterpret_cast<uint4*>(dst + plane + off) = *reinterpret_cast<const uint4*>(lo);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -344,66 +394,157 @@ __global__ void split_kernel(const float* __restrict__ src, int bins, __nv_bfloa
 struct TcArgs {
   const __nv_bfloat16* data;    // [2][chunks8][rows_total][8]
   const uint16_t* tiles;        // [n_tiles][8192 B]
-  float* out;                   // EPI 0: [B][172][WOUT][COUT] channels-last ; EPI 1/2: [B][taps][WOUT][172] time-fastest
+  float* out;                   // EPI 0: [B][172][WOUT][COUT] channels-last ; EPI 1/2/3: raw [B][172][WOUT] (may be null)
+  float* out_unw;               // EPI 1/2: unwrapped [frames][WOUT] (with ud)
+  const UnwrapDesc* ud;
+  const float* note_raw;        // EPI 1: the note posteriorgram [B][172][88] (input channel 0 of the onset conv2)
+  float* edge;                  // [edge slot][side 2][KE][edge_rows]: partial sums where two tile ranges meet
+  int edge_rows;
   int layer;                    // which constant-memory program (0 contour, 1 onset, 2 note)
   int rows_total, n_mtiles, n_windows;
   int n_groups, n_split;        // an item covers groups [s*n_groups/n_split, (s+1)*n_groups/n_split)
-  int data_rows, row0;          // tile rows (128 + KH - 1); first data row of M-tile 0 (= lead - PT)
+  int data_rows, row0;          // tile rows (128 + KH - 1); first data row of M-tile 0
+  int ms, h2;                   // M-tile stride (128 - 2*h2) and time halo of the fused conv2
   int chunks8, rows_per_window;
-  int cout, flt, wout;
+  int cout, flt, wout, n_ft, g0;
 };
 
-// Fused second conv of the onset / note branch (32 -> 1 channels, KH x 3 taps, models.py:305-313 / 282-290) in the
-// epilogue.  The tile is 4 bins x 32 channels of relu(conv1) for one frame per thread; channels and frequency taps are
-// reduced in the thread:
-//   Q[dt][j][t] = sum_{c, df} relu(conv1)[c][t][4 ft + j + df - 2] * w2[c][dt][df]     j = 0 .. 5  (bins 4 ft - 1 + j)
-// and the time taps (and the two halo columns of the neighbouring tiles) are summed by halo_tapsum_kernel (cnn.cu).
-// Q is time-fastest ([B][22 tiles][KH][6][172]): the 32 lanes of a warp hold 32 consecutive frames, so every store
-// writes one contiguous 128-byte run; it is half the size of one plane per (dt, df) tap.  Packed FMAs over pairs of
-// time taps; the weight pairs are uniform-register operands loaded from constant memory at static offsets (LDCU.128),
-// two bins per loaded pair, so no weight lives in a vector register.
+__device__ __forceinline__ float sigmoidf_fast(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+
+__device__ __forceinline__ void slot_barrier(int slot) {  // the four epilogue warps of one accumulator slot
+  asm volatile("bar.sync %0, 128;" ::"r"(1 + slot) : "memory");
+}
+
+// Time taps of the fused conv2 across frames.  P are the per-frame partial sums of time tap dt2 (delta = dt2 - H):
+// output frame r needs P of frame r + delta, i.e. lane + delta; lanes whose source lies in the neighbouring warp get it
+// from that warp's published values after the slot barrier (time_edges).  Published entries of a warp:
+//   delta = +a (a = 1..H): its lanes 0 .. a-1          -> entries a(a-1)/2 + lane
+//   delta = -a           : its lanes 32-a .. 31        -> entries H(H+1)/2 + a(a-1)/2 + lane - (32 - a)
+template <int H, int NJ>
+__device__ __forceinline__ void time_tap(float (&S)[NJ], const float (&P)[NJ], int delta, int lane, float* pub) {
+  if (delta == 0) {
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) S[j] += P[j];
+    return;
+  }
+  const int src = lane + delta;
+  const bool ok = (unsigned)src < 32u;
+  const int a = delta > 0 ? delta : -delta;
+  const int idx = delta > 0 ? lane : lane - (32 - a);
+  const bool publish = (unsigned)idx < (unsigned)a;
+  float* e = pub + ((delta > 0 ? 0 : H * (H + 1) / 2) + a * (a - 1) / 2 + idx) * NJ;
+#pragma unroll
+  for (int j = 0; j < NJ; ++j) {
+    const float v = __shfl_sync(0xffffffffu, P[j], src & 31);
+    if (ok) S[j] += v;
+    if (publish) e[j] = P[j];
+  }
+}
+template <int H, int NJ>
+__device__ __forceinline__ void time_edges(float (&S)[NJ], int quad, int lane, const float* xb /* [4][kXchgFloats] */) {
+#pragma unroll
+  for (int a = 1; a <= H; ++a) {
+    if (quad < 3 && lane >= 32 - a) {  // delta = +a from the next warp
+      const float* e = xb + (quad + 1) * tc::kXchgFloats + (a * (a - 1) / 2 + lane + a - 32) * NJ;
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) S[j] += e[j];
+    }
+    if (quad > 0 && lane < a) {  // delta = -a from the previous warp
+      const float* e = xb + (quad - 1) * tc::kXchgFloats + (H * (H + 1) / 2 + a * (a - 1) / 2 + lane) * NJ;
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) S[j] += e[j];
+    }
+  }
+}
+
+// Edge-buffer slot of the tile range that slot `s` of split `q` walks (it starts at tile g0(q) + s * G0): s * n_split + q.
+// The range that ENDS below it is slot s of split q - 1, or, for (s, q) = (1, 0), slot 0 of the last split.
+
+// what the epilogue thread of one frame knows about where its results go
+struct RowOut {
+  float* raw;    // raw [B][172][WOUT] row of this frame (nullptr: not stored)
+  float* unw;    // unwrapped row (nullptr: not stored)
+  float* edge;   // edge buffer column of this frame: edge + R (nullptr: row not complete / not live)
+  const float* note_rows[3];  // EPI 1: rows t-1, t, t+1 of the raw note posteriorgram (nullptr outside the window)
+  bool ok;       // live frame whose time taps are complete in this M-tile
+  int e_lo, e_hi;  // edge slots of this range's start and of the range above its end (-1: none)
+};
+
+// Time taps of one output column (onset / note layers): acc holds the KH2 per-frame partial sums of the column as pairs
+// of time taps; returns the sum over the taps available inside the warp and publishes the edge lanes (see time_tap).
+template <int KH2>
+__device__ __forceinline__ float time_taps_col(const float2 (&acc)[(KH2 + 1) / 2], int lane, float* pub_col /* pub + j */) {
+  constexpr int H = KH2 / 2;
+  float s = 0.f;
+#pragma unroll
+  for (int dt = 0; dt < KH2; ++dt) {
+    const float p = (dt & 1) ? acc[dt >> 1].y : acc[dt >> 1].x;
+    const int delta = dt - H;
+    if (delta == 0) {
+      s += p;
+    } else {
+      const int src = lane + delta;
+      const float v = __shfl_sync(0xffffffffu, p, src & 31);
+      if ((unsigned)src < 32u) s += v;
+      const int a = delta > 0 ? delta : -delta;
+      const int idx = delta > 0 ? lane : lane - (32 - a);
+      if ((unsigned)idx < (unsigned)a) pub_col[((delta > 0 ? 0 : H * (H + 1) / 2) + a * (a - 1) / 2 + idx) * 6] = p;
+    }
+  }
+  return s;
+}
+
+// Fused second conv of the onset / note branch (32 -> 1 channels, KH x 3 taps, models.py:305-313 / 282-290).  The tile
+// is 4 bins x 32 channels of relu(conv1) for one frame per thread; channels and frequency taps are reduced in the thread:
+//   P[dt][j] = sum_{c, df} relu(conv1)[c][t][4 ft + j + df - 2] * w2[c][dt][df]     j = 0 .. 5  (bins 4 ft - 1 + j)
+// and the time taps follow per finished column (time_taps_col): S[j] = sum_dt P[dt][j][frame + dt - H].
+// Packed FMAs over pairs of time taps; the weight pairs are uniform-register operands loaded from constant memory at
+// static offsets (LDCU.128).  Rolling window over the output offsets: half h (input bins 2h, 2h+1) touches j = 2h .. 2h+3 =
+// accw[0..3]; after it j = 2h and 2h+1 are complete.  The half loop is NOT unrolled (unrolled, the compiler keeps the
+// weights in vector registers and spills); finished columns are pushed through S like a shift register.
 template <int LAYER, int KH>
-__device__ __forceinline__ void reduce_store(uint32_t taddr, const float2 (&red)[32][3][(KH + 1) / 2],
-                                             float* dst /* (b, ft, dt 0, j 0, t) */, bool live) {
+__device__ __forceinline__ void pitch_tile_sums(uint32_t taddr, const float2 (&red)[32][3][(KH + 1) / 2], bool live, int lane,
+                                                float* pub, float (&S)[6]) {
   constexpr int NP = (KH + 1) / 2;
-  // rolling window over the output offsets: half h (input bins 2h, 2h+1) touches j = 2h .. 2h+3 = accw[0..3]; after it
-  // j = 2h and 2h+1 are complete.  The half loop is not unrolled (the weights stay LDCU operands instead of registers).
   float2 accw[4][NP];
 #pragma unroll
   for (int k = 0; k < 4; ++k)
 #pragma unroll
     for (int p = 0; p < NP; ++p) accw[k][p] = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int j = 0; j < 6; ++j) S[j] = 0.f;
 #pragma unroll 1
-  for (int h = 0; h < 2; ++h) {
-    uint32_t v0[32], v1[32];
-    tmem_ld32_nowait(taddr + h * 64, v0);
-    tmem_ld32_nowait(taddr + h * 64 + 32, v1);
-    tmem_ld_wait();
+  for (int h = 0; h < 3; ++h) {
+    if (h < 2) {
 #pragma unroll
-    for (int c = 0; c < 32; ++c) {
-      const float o0 = fmaxf(__uint_as_float(v0[c]) + c_bias1[LAYER][c], 0.f);
-      const float o1 = fmaxf(__uint_as_float(v1[c]) + c_bias1[LAYER][c], 0.f);
+      for (int q = 0; q < 2; ++q) {  // input bin fl = 2h + q feeds output offsets j = fl - df + 2 = 2h + (q + 2 - df)
+        uint32_t v[32];
+        tmem_ld32_nowait(taddr + (2 * h + q) * 32, v);
+        tmem_ld_wait();
 #pragma unroll
-      for (int df = 0; df < 3; ++df)
+        for (int c = 0; c < 32; ++c) {
+          const float o = live ? fmaxf(__uint_as_float(v[c]) + c_bias1[LAYER][c], 0.f) : 0.f;
 #pragma unroll
-        for (int p = 0; p < NP; ++p) {
-          const float2 w = red[c][df][p];
-          if ((KH & 1) && p == NP - 1) {  // odd last time tap: a scalar FMA instead of half an empty pair
-            accw[2 - df][p].x = fmaf(o0, w.x, accw[2 - df][p].x);
-            accw[3 - df][p].x = fmaf(o1, w.x, accw[3 - df][p].x);
-          } else {
-            ffma2(accw[2 - df][p], o0, w);  // input bin fl feeds output offset j = fl - df + 2
-            ffma2(accw[3 - df][p], o1, w);
-          }
+          for (int df = 0; df < 3; ++df)
+#pragma unroll
+            for (int p = 0; p < NP; ++p) {
+              const float2 w = red[c][df][p];
+              if ((KH & 1) && p == NP - 1) {  // odd last time tap: a scalar FMA instead of half an empty pair
+                accw[q + 2 - df][p].x = fmaf(o, w.x, accw[q + 2 - df][p].x);
+              } else {
+                ffma2(accw[q + 2 - df][p], o, w);
+              }
+            }
         }
+      }
     }
-    float* d = dst + (size_t)(2 * h) * kFrames;
-    if (live) {
+    // columns j = 2h, 2h + 1 are complete (h == 2: the halo columns of the next tile)
+    const float s0 = time_taps_col<KH>(accw[0], lane, pub + 2 * h);
+    const float s1 = time_taps_col<KH>(accw[1], lane, pub + 2 * h + 1);
 #pragma unroll
-      for (int dt = 0; dt < KH; ++dt)
-#pragma unroll
-        for (int k = 0; k < 2; ++k) d[(size_t)(dt * 6 + k) * kFrames] = (dt & 1) ? accw[k][dt >> 1].y : accw[k][dt >> 1].x;
-    }
+    for (int j = 0; j < 4; ++j) S[j] = S[j + 2];
+    S[4] = s0;
+    S[5] = s1;
 #pragma unroll
     for (int p = 0; p < NP; ++p) {
       accw[0][p] = accw[2][p];
@@ -411,31 +552,79 @@ __device__ __forceinline__ void reduce_store(uint32_t taddr, const float2 (&red)
       accw[2][p] = accw[3][p] = make_float2(0.f, 0.f);
     }
   }
-  if (live) {  // j = 4, 5: the halo columns of the next tile
+}
+
+// Frequency halo + finish for the onset / note layers (FLT = 4, halo 1): S[j] is the time-complete sum for bin 4 ft - 1 + j.
+template <int EPI>
+__device__ __forceinline__ void finish_pitch_tile(const TcArgs& a, const RowOut& ro, float (&S)[6], float (&carry)[2], int ft,
+                                                  bool first, bool last) {
+  constexpr int L = EPI == 1 ? 1 : 2;
+  const bool lower = ft > 0;
+  if (first) {
+    if (lower && ro.edge) {
+      float* e = ro.edge + (size_t)(ro.e_lo * 2 + 0) * 2 * a.edge_rows;
+      e[0] = S[0];
+      e[a.edge_rows] = S[1];
+    }
+  } else {
+    S[0] += carry[0];
+    S[1] += carry[1];
+  }
+  const int jlo = first ? (lower ? 2 : 1) : 0;
+  const int jhi = (ft == a.n_ft - 1) ? 5 : 4;  // the last tile also finishes its top bin (no tile above)
+  if (ro.ok) {
+    float nv[3][6];
+    if constexpr (EPI == 1) {  // note rows t-1 .. t+1, columns 4 ft - 2 .. 4 ft + 3 (zero outside the image)
 #pragma unroll
-    for (int dt = 0; dt < KH; ++dt)
+      for (int r = 0; r < 3; ++r)
 #pragma unroll
-      for (int k = 0; k < 2; ++k)
-        dst[(size_t)(dt * 6 + 4 + k) * kFrames] = (dt & 1) ? accw[k][dt >> 1].y : accw[k][dt >> 1].x;
+        for (int q = 0; q < 3; ++q) {
+          const int c0 = 4 * ft - 2 + 2 * q;
+          float2 x = make_float2(0.f, 0.f);
+          if (ro.note_rows[r] && c0 >= 0 && c0 < kPitches) x = __ldg(reinterpret_cast<const float2*>(ro.note_rows[r] + c0));
+          nv[r][2 * q] = x.x;
+          nv[r][2 * q + 1] = x.y;
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+      if (j < jlo || j >= jhi) continue;
+      const int f = 4 * ft - 1 + j;
+      float x = S[j] + c_bias2[L];
+      if constexpr (EPI == 1) {
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+          for (int df = 0; df < 3; ++df)
+            if (j + df < 6) x = fmaf(nv[r][j + df], c_onset_note_w[r * 3 + df], x);  // column f + df - 1 = 4 ft - 2 + (j + df)
+      }
+      const float v = sigmoidf_fast(x);
+      if (ro.raw) ro.raw[f] = v;
+      if (ro.unw) ro.unw[f] = v;
+    }
+  }
+  carry[0] = S[4];
+  carry[1] = S[5];
+  if (last && ft < a.n_ft - 1 && ro.edge && ro.e_hi >= 0) {
+    float* e = ro.edge + (size_t)(ro.e_hi * 2 + 1) * 2 * a.edge_rows;
+    e[0] = S[4];
+    e[a.edge_rows] = S[5];
   }
 }
 
 // Fused contour conv2 (8 -> 1 channels, 5 x 5 taps, models.py:252-259) in the contour epilogue.  A tile holds 16 bins
 // x 8 channels of relu(conv1) for one frame per thread; the channel and frequency taps are reduced in the thread,
-//   Q[dt][j][t] = sum_{c, df} relu(conv1)[c][t][16 ft + j - df] * w2[c][dt][df]      j = 0 .. 19  (bins 16 ft - 2 + j),
-// and the five time taps are summed by halo_tapsum_kernel (cnn.cu), which also adds the four halo columns of the
-// neighbouring tiles.  Q is time-fastest ([B][17 tiles][5][20][172]), so every store is a contiguous 128-byte run,
-// and 19 % smaller than the channels-last activations it replaces; the 8-channel image never reaches HBM.
-// Pass 0 applies bias + ReLU (and zeroes the bins >= 264 of the last tile) in place in TMEM; the dt loop is not
-// unrolled, so only the 40 weights of one time tap are live.
-__device__ __forceinline__ void contour_quad(const uint32_t (&v)[32], int dt, float2 (&acc)[10], int c4) {
+//   P[dt][j] = sum_{c, df} relu(conv1)[c][t][16 ft + j - df] * w2[c][dt][df]      j = 0 .. 19  (bins 16 ft - 2 + j).
+// Pass 0 applies bias + ReLU (and zeroes the bins >= 264 of the last tile and frames that are not live) in place in TMEM;
+// the dt loop is not unrolled, so only the 40 weights of one time tap are live.
+__device__ __forceinline__ void contour_pair(const uint32_t (&v)[16], int dt, float2 (&acc)[10], int c2) {
 #pragma unroll
-  for (int bl = 0; bl < 4; ++bl)
+  for (int bl = 0; bl < 2; ++bl)
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
       const float o = __uint_as_float(v[bl * 8 + c]);
-      const int j2 = (4 * c4 + bl) >> 1;  // pair index of output offsets (2 j2, 2 j2 + 1)
-      if ((bl & 1) == 0) {
+      const int j2 = c2;  // pair index of output offsets (2 j2, 2 j2 + 1) of input bin 2 c2 + bl
+      if (bl == 0) {
         ffma2(acc[j2], o, c_red_contour[dt][c][0]);
         ffma2(acc[j2 + 1], o, c_red_contour[dt][c][1]);
         ffma2(acc[j2 + 2], o, c_red_contour[dt][c][2]);
@@ -447,8 +636,9 @@ __device__ __forceinline__ void contour_quad(const uint32_t (&v)[32], int dt, fl
     }
 }
 
-__device__ __forceinline__ void contour_reduce_store(uint32_t taddr, int n_valid /* live columns of the tile */,
-                                                     float* dst /* (b, ft, dt 0, j 0, t) */, bool live) {
+__device__ __forceinline__ void contour_tile(const TcArgs& a, const RowOut& ro, uint32_t taddr, int n_valid, bool live,
+                                             int ft, bool first, bool last, int quad, int lane, int slot, float* xb,
+                                             float (&carry)[4]) {
 #pragma unroll 1
   for (int c4 = 0; c4 < 4; ++c4) {
     uint32_t v[32];
@@ -457,33 +647,70 @@ __device__ __forceinline__ void contour_reduce_store(uint32_t taddr, int n_valid
 #pragma unroll
     for (int i = 0; i < 32; ++i) {
       const float o = fmaxf(__uint_as_float(v[i]) + c_bias1[0][i & 7], 0.f);
-      v[i] = (c4 * 32 + i < n_valid) ? __float_as_uint(o) : 0u;
+      v[i] = (live && c4 * 32 + i < n_valid) ? __float_as_uint(o) : 0u;
     }
     tmem_st32(taddr + c4 * 32, v);
   }
   tmem_st_wait();
+  float S[20];
+#pragma unroll
+  for (int j = 0; j < 20; ++j) S[j] = 0.f;
+  float* pub = xb + quad * tc::kXchgFloats;
 #pragma unroll 1
   for (int dt = 0; dt < 5; ++dt) {
     float2 acc[10];  // output offsets j = 0 .. 19 as pairs
 #pragma unroll
     for (int j = 0; j < 10; ++j) acc[j] = make_float2(0.f, 0.f);
-    uint32_t v0[32], v1[32];
-    tmem_ld32_nowait(taddr, v0);
-    tmem_ld_wait();
-    tmem_ld32_nowait(taddr + 32, v1);
-    contour_quad(v0, dt, acc, 0);
-    tmem_ld_wait();
-    tmem_ld32_nowait(taddr + 64, v0);
-    contour_quad(v1, dt, acc, 1);
-    tmem_ld_wait();
-    tmem_ld32_nowait(taddr + 96, v1);
-    contour_quad(v0, dt, acc, 2);
-    tmem_ld_wait();
-    contour_quad(v1, dt, acc, 3);
-    if (live) {
+    // 16 accumulator columns (2 bins x 8 channels) per load, the next load in flight while this one is consumed
+    uint32_t v0[16], v1[16];
+    tmem_ld16_nowait(taddr, v0);
 #pragma unroll
-      for (int j = 0; j < 20; ++j) dst[(size_t)(dt * 20 + j) * kFrames] = (j & 1) ? acc[j >> 1].y : acc[j >> 1].x;
+    for (int c2 = 0; c2 < 8; c2 += 2) {
+      tmem_ld_wait();
+      tmem_ld16_nowait(taddr + (c2 + 1) * 16, v1);
+      contour_pair(v0, dt, acc, c2);
+      tmem_ld_wait();
+      if (c2 + 2 < 8) tmem_ld16_nowait(taddr + (c2 + 2) * 16, v0);
+      contour_pair(v1, dt, acc, c2 + 1);
     }
+    float P[20];
+#pragma unroll
+    for (int j = 0; j < 10; ++j) P[2 * j] = acc[j].x, P[2 * j + 1] = acc[j].y;
+    time_tap<2, 20>(S, P, dt - 2, lane, pub);
+  }
+  __syncwarp();
+  slot_barrier(slot);
+  time_edges<2, 20>(S, quad, lane, xb);
+  // frequency halo: S[j] <-> bin 16 ft - 2 + j; bins 16 ft - 2 .. 16 ft + 1 also get the top four sums of the tile below
+  const bool lower = ft > 0;
+  if (first) {
+    if (lower && ro.edge) {
+      float* e = ro.edge + (size_t)(ro.e_lo * 2 + 0) * 4 * a.edge_rows;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) e[(size_t)k * a.edge_rows] = S[k];
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) S[k] += carry[k];
+  }
+  if (ro.ok) {
+    const int jlo = first ? (lower ? 4 : 2) : 0;
+    float* dst = ro.raw + 16 * ft - 2;
+#pragma unroll
+    for (int j = 0; j < 16; j += 2) {
+      if (j < jlo || 16 * ft - 2 + j >= kContourBins) continue;
+      float2 o;
+      o.x = sigmoidf_fast(S[j] + c_bias2[0]);
+      o.y = sigmoidf_fast(S[j + 1] + c_bias2[0]);
+      *reinterpret_cast<float2*>(dst + j) = o;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) carry[k] = S[16 + k];
+  if (last && ft < a.n_ft - 1 && ro.edge && ro.e_hi >= 0) {
+    float* e = ro.edge + (size_t)(ro.e_hi * 2 + 1) * 4 * a.edge_rows;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) e[(size_t)k * a.edge_rows] = S[16 + k];
   }
 }
 
@@ -493,7 +720,8 @@ __global__ void __launch_bounds__(tc::kThreads, 1) conv_tc_kernel(const TcArgs a
   extern __shared__ __align__(128) unsigned char smem[];
   unsigned char* s_data = smem;                    // [2 planes][40 chunks][data_rows][16 B]
   unsigned char* s_w = smem + kMaxDataBytes;       // [kStages][8192]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kMaxDataBytes + kStages * kTileBytes);
+  float* s_x = reinterpret_cast<float*>(smem + kMaxDataBytes + kStages * kTileBytes);  // [slot][buf][warp][kXchgFloats]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kMaxDataBytes + kStages * kTileBytes + kXchgBytes);
   uint64_t* full_w = bars;             // [kStages]
   uint64_t* empty_w = bars + kStages;  // [kStages]
   uint64_t* data_full = bars + 2 * kStages;
@@ -547,7 +775,7 @@ __global__ void __launch_bounds__(tc::kThreads, 1) conv_tc_kernel(const TcArgs a
         const int g0 = sp * a.n_groups / a.n_split, g1 = (sp + 1) * a.n_groups / a.n_split;
         mbar_wait(data_empty, ph_d ^ 1);
         mbar_expect_tx(data_full, 2 * plane_bytes);
-        const size_t row = (size_t)mt * kMTile + a.row0;
+        const size_t row = (size_t)mt * a.ms + a.row0;
         for (int p = 0; p < 2; ++p)
           for (int c = 0; c < a.chunks8; ++c)
             bulk_g2s(s_data + p * plane_bytes + c * lbo, a.data + p * plane_elems + ((size_t)c * a.rows_total + row) * 8,
@@ -624,12 +852,36 @@ __global__ void __launch_bounds__(tc::kThreads, 1) conv_tc_kernel(const TcArgs a
     const int row = quad * 32 + lane;
     uint32_t ph_t[2] = {0, 0};
     uint32_t gcount = 0;
+    uint32_t xbuf = 0;  // exchange buffer of this slot, toggled per tile
     for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
       const int mt = it / a.n_split, sp = it % a.n_split;
       const int g0 = sp * a.n_groups / a.n_split, g1 = (sp + 1) * a.n_groups / a.n_split;
-      const int m = mt * kMTile + row;
-      const int b = m / a.rows_per_window, t = m - b * a.rows_per_window;
-      const bool live = (b < a.n_windows) && (t < kFrames);
+      const int m = mt * a.ms - a.h2 + row;  // row of the (window, frame) space: m = b * rows_per_window + t
+      const int b = m >= 0 ? m / a.rows_per_window : 0, t = m - b * a.rows_per_window;
+      const bool live = m >= 0 && (b < a.n_windows) && (t < kFrames);
+      RowOut ro{};
+      float carry[4] = {0.f, 0.f, 0.f, 0.f};
+      if constexpr (EPI != 0) {
+        ro.e_lo = slot * a.n_split + sp;
+        ro.e_hi = (sp + 1 < a.n_split) ? slot * a.n_split + sp + 1 : (slot == 0 ? a.n_split : -1);
+        ro.ok = live && row >= a.h2 && row < kMTile - a.h2;
+        if (ro.ok) {
+          ro.edge = a.edge + (size_t)mt * a.ms + (row - a.h2);
+          if (a.out) ro.raw = a.out + ((size_t)b * kFrames + t) * a.wout;
+          if (a.ud) {
+            const UnwrapDesc u = a.ud[b];
+            const int tt = t - kOverlapHalf;
+            if ((unsigned)tt < (unsigned)max(u.rows, 0)) ro.unw = a.out_unw + (size_t)(u.dst_base + tt) * a.wout;
+          }
+          if constexpr (EPI == 1) {
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+              ro.note_rows[r] = ((unsigned)(t + r - 1) < (unsigned)kFrames)
+                                    ? a.note_raw + ((size_t)b * kFrames + t + r - 1) * kPitches
+                                    : nullptr;
+          }
+        }
+      }
       for (int g = g0; g < g1; ++g) {
         const uint32_t buf = gcount & 1u;
         mbar_wait(tmem_full + buf, ph_t[buf]);
@@ -638,6 +890,9 @@ __global__ void __launch_bounds__(tc::kThreads, 1) conv_tc_kernel(const TcArgs a
         const int ft = c_group_ft[a.layer][2 * g + slot];
         if (ft >= 0) {
           const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * 256u + (uint32_t)slot * 128u;
+          // first / last tile of this slot's ascending range inside the item
+          const bool first = (g == g0);
+          const bool last = (g == g1 - 1) || (ft == a.n_ft - 1);
           if constexpr (EPI == 0) {
             // contour: 16 bins x 8 channels, bias + ReLU, channels-last rows of 128 contiguous floats
             const int n_valid = min(a.flt, a.wout - ft * a.flt) * a.cout;
@@ -661,17 +916,27 @@ __global__ void __launch_bounds__(tc::kThreads, 1) conv_tc_kernel(const TcArgs a
             }
           } else if constexpr (EPI == 3) {
             const int n_valid = min(a.flt, a.wout - ft * a.flt) * a.cout;
-            float* dst = a.out + ((size_t)b * 17 + ft) * (5 * 20 * kFrames) + t;
-            contour_reduce_store(taddr, n_valid, dst, live);
+            float* xb = s_x + (slot * 2 + xbuf) * 4 * kXchgFloats;
+            contour_tile(a, ro, taddr, n_valid, live, ft, first, last, quad, lane, slot, xb, carry);
+            xbuf ^= 1u;
           } else {
-            // onset / note: the tile is 4 bins x 32 channels; reduce channels and frequency taps of the next conv
-            constexpr int KH2 = (EPI == 1) ? 3 : 7;
-            float* dst = a.out + ((size_t)b * 22 + ft) * (KH2 * 6 * kFrames) + t;
+            // onset / note: the tile is 4 bins x 32 channels; the whole next conv (32 -> 1, KH2 x 3) follows
+            constexpr int KH2 = (EPI == 1) ? 3 : 7, H = KH2 / 2;
+            float* xb = s_x + (slot * 2 + xbuf) * 4 * kXchgFloats;
+            float S[6];
             if constexpr (EPI == 1) {
-              reduce_store<1, 3>(taddr, c_red_onset, dst, live);
+              pitch_tile_sums<1, 3>(taddr, c_red_onset, live, lane, xb + quad * kXchgFloats, S);
             } else {
-              reduce_store<2, 7>(taddr, c_red_note, dst, live);
+              pitch_tile_sums<2, 7>(taddr, c_red_note, live, lane, xb + quad * kXchgFloats, S);
             }
+            __syncwarp();
+            slot_barrier(slot);
+            time_edges<H, 6>(S, quad, lane, xb);
+            xbuf ^= 1u;
+            float c2[2] = {carry[0], carry[1]};
+            finish_pitch_tile<EPI>(a, ro, S, c2, ft, first, last);
+            carry[0] = c2[0];
+            carry[1] = c2[1];
           }
         }
         tc_fence_before();
@@ -690,10 +955,61 @@ __global__ void __launch_bounds__(tc::kThreads, 1) conv_tc_kernel(const TcArgs a
 }
 
 // ------------------------------------------------------------------------------------------------
+// Where two tile ranges meet (frequency tile ft_b = first tile of a range, ft_b > 0) the KE = 2 * HALO bins
+// SF2... FLT * ft_b - HALO + k (k < KE) got one partial sum from each side: finish them here.
+// ------------------------------------------------------------------------------------------------
+struct EdgeFixArgs {
+  const float* edge;
+  int edge_rows, n_rows;        // rows of the (window, frame) space covered by the M-tiles
+  int n_edges;                  // 2 * n_split slots: slot e = s * n_split + q starts at tile q * n_groups / n_split + s * G0
+  int n_split, n_groups, g0, n_ft;
+  int layer, flt, halo, wout, rows_per_window, n_windows;
+  float* raw;
+  float* unw;
+  const UnwrapDesc* ud;
+  const float* note_raw;
+};
+
+__global__ void edge_fix_kernel(const EdgeFixArgs a) {
+  const int ke = 2 * a.halo;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)a.n_rows * a.n_edges * ke;
+  if (idx >= total) return;
+  const int R = (int)(idx % a.n_rows);  // rows fastest: coalesced reads of the edge buffer
+  const int ek = (int)(idx / a.n_rows);
+  const int e = ek / ke, k = ek - e * ke;
+  const int b = R / a.rows_per_window, t = R - b * a.rows_per_window;
+  if (b >= a.n_windows || t >= kFrames) return;
+  const int es = e / a.n_split, eq = e - es * a.n_split;
+  const int ft_b = eq * a.n_groups / a.n_split + es * a.g0;
+  if (ft_b <= 0 || ft_b >= a.n_ft) return;  // not a boundary between two ranges
+  const int f = a.flt * ft_b - a.halo + k;
+  if (f < 0 || f >= a.wout) return;
+  float x = c_bias2[a.layer] + a.edge[((size_t)(e * 2 + 0) * ke + k) * a.edge_rows + R] +
+            a.edge[((size_t)(e * 2 + 1) * ke + k) * a.edge_rows + R];
+  if (a.note_raw) {
+#pragma unroll
+    for (int dt = 0; dt < 3; ++dt)
+#pragma unroll
+      for (int df = 0; df < 3; ++df) {
+        const int tt = t + dt - 1, ff = f + df - 1;
+        if ((unsigned)tt < (unsigned)kFrames && (unsigned)ff < (unsigned)kPitches)
+          x = fmaf(__ldg(a.note_raw + ((size_t)b * kFrames + tt) * kPitches + ff), c_onset_note_w[dt * 3 + df], x);
+      }
+  }
+  const float v = sigmoidf_fast(x);
+  if (a.raw) a.raw[((size_t)b * kFrames + t) * a.wout + f] = v;
+  if (a.ud) {
+    const UnwrapDesc u = a.ud[b];
+    const int tt = t - kOverlapHalf;
+    if ((unsigned)tt < (unsigned)max(u.rows, 0)) a.unw[(size_t)(u.dst_base + tt) * a.wout + f] = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 int tc_rows_total(int n_windows, int rows_per_window) {
-  const int rows = n_windows * rows_per_window;
-  const int n_mtiles = (rows + tc::kMTile - 1) / tc::kMTile;
-  return n_mtiles * tc::kMTile + 8;
+  // lead rows + the rows of the windows + what the last (overlapping) M-tile and its time taps may touch
+  return n_windows * rows_per_window + tc::kMTile + 16;
 }
 
 void tc_setup() {
@@ -703,24 +1019,46 @@ void tc_setup() {
   cudaFuncSetAttribute(conv_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes);
 }
 
-void launch_split(const float* src, __nv_bfloat16* dst, const TcConvSpec& sp, int n_windows, int rows_stride,
-                  cudaStream_t st) {
+void launch_lognorm_split(float* y, const unsigned int* minmax, const float* bn, __nv_bfloat16* dst, const TcConvSpec& sp,
+                          int n_windows, int rows_stride, cudaStream_t st) {
   const int rows_used = tc_rows_total(n_windows, sp.rows_per_window);  // <= rows_stride
   const long long cells = (long long)rows_used * sp.chunks8;
-  split_kernel<<<(unsigned)((cells + 255) / 256), 256, 0, st>>>(src, sp.data_bins, dst, n_windows, rows_used, rows_stride,
-                                                               sp.chunks8, sp.rows_per_window, sp.lead_rows);
+  lognorm_split_kernel<<<(unsigned)((cells + 255) / 256), 256, 0, st>>>(y, minmax, bn, dst, n_windows, rows_used, rows_stride,
+                                                                       sp.chunks8, sp.rows_per_window, sp.lead_rows);
 }
 
-void launch_conv_tc(const __nv_bfloat16* data, const TcConvDev& dev, float* out, int n_windows, int rows_stride,
+void launch_contour_split(const float* raw_contour, __nv_bfloat16* chl, int n_windows, int rows_stride, cudaStream_t st,
+                          const UnwrapDesc* ud, float* unwrapped) {
+  const TcConvSpec sp = tc_note_spec();
+  const long long cells = (long long)n_windows * kFrames * (kContourBins / 8);
+  contour_split_kernel<<<(unsigned)((cells + 255) / 256), 256, 0, st>>>(raw_contour, chl, n_windows, rows_stride, sp.chunks8,
+                                                                       sp.rows_per_window, sp.lead_rows, ud, unwrapped);
+}
+
+size_t tc_edge_floats(const TcConvSpec& sp, int n_windows) {
+  const int ms = tc::kMTile - (sp.KH2 - 1);
+  const int n_mtiles = (n_windows * sp.rows_per_window + ms - 1) / ms;
+  return (size_t)2 * sp.G0 * 2 * (2 * sp.HALO) * ((size_t)n_mtiles * ms);  // at most 2 * G0 range starts
+}
+
+void launch_conv_tc(const __nv_bfloat16* data, const TcConvDev& dev, const TcOut& o, int n_windows, int rows_stride,
                     int n_sms, cudaStream_t st, bool fuse_next) {
   const TcConvSpec& sp = dev.spec;
-  TcArgs a;
+  const bool fused = sp.epi != 0 || fuse_next;
+  TcArgs a{};
   a.data = data;
   a.tiles = dev.tiles;
-  a.out = out;
+  a.out = o.raw;
+  a.out_unw = o.unwrapped;
+  a.ud = o.ud;
+  a.note_raw = o.note_raw;
+  a.edge = o.edge;
   a.layer = dev.layer;
   a.rows_total = rows_stride;  // row stride of the split layout (fixed per model, independent of the batch)
-  a.n_mtiles = (tc_rows_total(n_windows, sp.rows_per_window) - 8) / tc::kMTile;
+  a.h2 = fused ? (sp.KH2 - 1) / 2 : 0;
+  a.ms = tc::kMTile - 2 * a.h2;
+  a.n_mtiles = (n_windows * sp.rows_per_window + a.ms - 1) / a.ms;
+  a.edge_rows = a.n_mtiles * a.ms;
   a.n_windows = n_windows;
   a.n_groups = dev.n_groups;
   // An item is (M-tile, one of `split` runs of frequency groups).  Pick the split that minimises the number of waves
@@ -735,12 +1073,20 @@ void launch_conv_tc(const __nv_bfloat16* data, const TcConvDev& dev, float* out,
   }
   a.n_split = split;
   a.data_rows = tc::kMTile + sp.KH - 1;
-  a.row0 = sp.lead_rows - sp.PT;
+  a.row0 = sp.lead_rows - sp.PT - a.h2;
   a.chunks8 = sp.chunks8;
   a.rows_per_window = sp.rows_per_window;
   a.cout = sp.COUT;
   a.flt = sp.FLT;
   a.wout = sp.WOUT;
+  a.n_ft = (sp.WOUT + sp.FLT - 1) / sp.FLT;
+  a.g0 = sp.G0;
+  EdgeFixArgs ef{};
+  ef.n_edges = fused ? 2 * split : 0;  // slot s of split q covers tiles [g0(q) + s*G0, g1(q) + s*G0): edge slot s*split + q
+  ef.n_split = split;
+  ef.n_groups = dev.n_groups;
+  ef.g0 = sp.G0;
+  ef.n_ft = a.n_ft;
   const int n_items = a.n_mtiles * a.n_split;
   const int grid = n_items < n_sms ? n_items : n_sms;
   if (sp.epi == 0 && fuse_next)
@@ -751,6 +1097,23 @@ void launch_conv_tc(const __nv_bfloat16* data, const TcConvDev& dev, float* out,
     conv_tc_kernel<1><<<grid, tc::kThreads, tc::kSmemBytes, st>>>(a);
   else
     conv_tc_kernel<2><<<grid, tc::kThreads, tc::kSmemBytes, st>>>(a);
+  if (fused && ef.n_edges > 0) {
+    ef.edge = o.edge;
+    ef.edge_rows = a.edge_rows;
+    ef.n_rows = n_windows * sp.rows_per_window;
+    ef.layer = sp.epi == 0 ? 0 : sp.epi;  // c_bias2 index: 0 contour, 1 onset, 2 note
+    ef.flt = sp.FLT;
+    ef.halo = sp.HALO;
+    ef.wout = sp.WOUT;
+    ef.rows_per_window = sp.rows_per_window;
+    ef.n_windows = n_windows;
+    ef.raw = o.raw;
+    ef.unw = o.unwrapped;
+    ef.ud = o.ud;
+    ef.note_raw = o.note_raw;
+    const long long total = (long long)ef.n_rows * ef.n_edges * 2 * sp.HALO;
+    edge_fix_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(ef);
+  }
 }
 
 }  // namespace bp

@@ -1,88 +1,186 @@
-"""CPU: the decomposition behind the fused epilogues of the tensor-core kernels (csrc/tc_conv.cu: contour_reduce_store,
-reduce_store) and the tap-sum kernel (csrc/cnn.cu: halo_tapsum_kernel), restated in NumPy with the same index
-arithmetic and compared with the direct convolution of the oracle.
+"""CPU: the index arithmetic of the fused second convolutions in the epilogues of the tensor-core kernels
+(csrc/tc_conv.cu: contour_tile, pitch_tile_sums, time_tap / time_taps_col / time_edges, finish_pitch_tile, edge_fix_kernel),
+restated in NumPy with the SAME structure and compared with the direct convolution of the oracle:
 
-Per frequency tile of FLT bins the epilogue reduces relu(conv1) over channels and frequency taps into KH time-tap planes
-of J = FLT + 2*HALO output offsets,   Q[ft][dt][j][t] = sum_{c,df} x[c][t][FLT*ft + j + df - 2*HALO] * w2[c][dt][df]
-(output bin f = FLT*ft + j - HALO; the HALO outer columns on either side belong to the neighbouring tiles), and the
-tap-sum kernel computes   out[t][f] = sigmoid(b + sum_dt (Q[ft][dt][r + HALO][t + dt - PT] + neighbour halo term)).
-This pins the halo bookkeeping, the time-tap stride and the zero padding; the GPU tests then only have to prove the
-kernels."""
+  * per frequency tile of FLT bins the thread of a frame reduces relu(conv1) over channels and frequency taps into
+    P[dt][j], j = 0 .. FLT + 2*HALO - 1 (output bin FLT*ft - HALO + j),
+  * time taps: output row r takes P[dt] of row r + dt - H — from lane + delta inside the warp (32 consecutive rows), from
+    the published edge lanes of the neighbouring warp otherwise; M-tiles advance by 128 - 2H rows, rows H .. 127-H of a
+    tile are complete,
+  * frequency halo: a slot walks its tile range in ascending order carrying the top 2*HALO sums; where two ranges meet
+    (slot 0 | slot 1, group splits) both sides go to the edge buffer and the fix-up adds them.
+
+This pins the halo bookkeeping, lane / entry formulas, tile ranges and zero padding; the GPU tests then only have to
+prove the kernels."""
 import numpy as np
 import pytest
 import torch
 import torch.nn.functional as F
 
-CASES = {  # name: (weights key, C_in, KH, KW, FLT, HALO, W)
-    "contour2": ("contour2_w", 8, 5, 5, 16, 2, 264),
-    "note2": ("note2_w", 32, 7, 3, 4, 1, 88),
-    "onset2": ("onset2_w", 32, 3, 3, 4, 1, 88),  # channels 1..32 of the 33-channel conv; channel 0 is the note input
+CASES = {  # name: (weights key, C_in, KH2, KW, FLT, HALO, W, rows_per_window, G0)
+    "contour2": ("contour2_w", 8, 5, 5, 16, 2, 264, 174, 9),
+    "note2": ("note2_w", 32, 7, 3, 4, 1, 88, 175, 12),
+    "onset2": ("onset2_w", 32, 3, 3, 4, 1, 88, 174, 12),  # channels 1..32 of the 33-channel conv; channel 0 is the note input
 }
+T = 172
 
 
-def _epilogue_planes(x, w2, KH, KW, FLT, HALO, W):
-    """x: relu(conv1) [C][T][W]; w2 [C][KH][KW] -> Q [tiles][KH][J][T] exactly as the epilogue accumulates it."""
-    C, T, _ = x.shape
-    n_tiles = (W + FLT - 1) // FLT
+def _thread_partials(x, w2, KH2, KW, FLT, HALO, W):
+    """x: relu(conv1) [C][rows][W] (zero for rows that are not live) -> P[ft][dt][j][row] as the epilogue thread of a row
+    accumulates it: input bin fl of the tile feeds output offset j = fl - df + 2*HALO."""
+    C, R, _ = x.shape
+    n_ft = (W + FLT - 1) // FLT
     J = FLT + 2 * HALO
-    Q = np.zeros((n_tiles, KH, J, T))
-    for ft in range(n_tiles):
+    P = np.zeros((n_ft, KH2, J, R))
+    for ft in range(n_ft):
         for fl in range(FLT):
             g = FLT * ft + fl
-            if g >= W:  # bins past the image contribute zero (masked in the epilogue's first pass)
+            if g >= W:  # bins past the image are zeroed in the epilogue's first pass
                 continue
             for df in range(KW):
-                j = fl - df + 2 * HALO  # input bin fl feeds output offset j (KW = 2*HALO + 1)
-                for dt in range(KH):
-                    Q[ft, dt, j, :] += np.einsum("ct,c->t", x[:, :, g], w2[:, dt, df])
-    return Q
+                j = fl - df + 2 * HALO
+                for dt in range(KH2):
+                    P[ft, dt, j, :] += np.einsum("cr,c->r", x[:, :, g], w2[:, dt, df])
+    return P
 
 
-def _tapsum(Q, bias, KH, PT, FLT, HALO, W, extra=None):
-    n_tiles, _, J, T = Q.shape
-    out = np.full((T, W), float(bias))
-    for f in range(W):
-        ft, r = divmod(f, FLT)
-        terms = [(ft, r + HALO)]
-        if r < HALO and ft - 1 >= 0:
-            terms.append((ft - 1, r + HALO + FLT))
-        if r >= FLT - HALO and ft + 1 < n_tiles:
-            terms.append((ft + 1, r + HALO - FLT))
-        for t in range(T):
-            for dt in range(KH):
-                tt = t + dt - PT
-                if 0 <= tt < T:
-                    out[t, f] += sum(Q[a, dt, j, tt] for a, j in terms)
-    if extra is not None:
-        out += extra
-    return 1.0 / (1.0 + np.exp(-out))
+def _time_sum_tile(Ptile, H):
+    """Ptile [KH2][J][128] (rows of one M-tile) -> S [J][128] exactly like time_tap + time_edges: 4 warps of 32 lanes."""
+    KH2, J, _ = Ptile.shape
+    S = np.zeros((J, 128))
+    HH = H * (H + 1) // 2
+    pub = np.full((4, 2 * HH, J), np.nan)  # published entries per warp
+    for quad in range(4):
+        for lane in range(32):
+            row = quad * 32 + lane
+            for dt in range(KH2):
+                delta = dt - H
+                if delta == 0:
+                    S[:, row] += Ptile[dt, :, row]
+                    continue
+                src = lane + delta
+                if 0 <= src < 32:
+                    S[:, row] += Ptile[dt, :, quad * 32 + src]
+                a = abs(delta)
+                idx = lane if delta > 0 else lane - (32 - a)
+                if 0 <= idx < a:
+                    pub[quad, (0 if delta > 0 else HH) + a * (a - 1) // 2 + idx] = Ptile[dt, :, row]
+    for quad in range(4):
+        for lane in range(32):
+            row = quad * 32 + lane
+            for a in range(1, H + 1):
+                if quad < 3 and lane >= 32 - a:
+                    S[:, row] += pub[quad + 1, a * (a - 1) // 2 + lane + a - 32]
+                if quad > 0 and lane < a:
+                    S[:, row] += pub[quad - 1, HH + a * (a - 1) // 2 + lane]
+    return S
 
 
-@pytest.mark.parametrize("name", list(CASES))
-def test_fused_second_conv_decomposition(weights_np, name):
-    key, C, KH, KW, FLT, HALO, W = CASES[name]
+def _fused_layer(x_rows, w2, bias, KH2, KW, FLT, HALO, W, rpw, G0, n_windows, n_split, extra=None):
+    """Emulates conv_tc_kernel's fused epilogue + edge_fix_kernel for all M-tiles; returns out [n_windows][T][W]."""
+    H = (KH2 - 1) // 2
+    MS = 128 - 2 * H
+    KE = 2 * HALO
+    n_rows = n_windows * rpw
+    n_mtiles = (n_rows + MS - 1) // MS
+    n_ft = (W + FLT - 1) // FLT
+    n_groups = G0
+    P = _thread_partials(x_rows, w2, KH2, KW, FLT, HALO, W)  # rows indexed by m + pad
+    pad = 128 + 8
+    out = np.full((n_windows, T, W), np.nan)
+    edge = np.full((2 * n_split, 2, KE, n_mtiles * MS), np.nan)
+
+    def finish(b, t, f, val):
+        v = val + bias
+        if extra is not None:
+            v += extra[b, t, f]
+        assert np.isnan(out[b, t, f]), "bin finished twice"
+        out[b, t, f] = 1.0 / (1.0 + np.exp(-v))
+
+    for mt in range(n_mtiles):
+        m0 = mt * MS - H  # row (window, frame) index of tile row 0
+        for q in range(n_split):
+            g0, g1 = q * n_groups // n_split, (q + 1) * n_groups // n_split
+            for slot in range(2):
+                e_lo = slot * n_split + q
+                e_hi = slot * n_split + q + 1 if q + 1 < n_split else (n_split if slot == 0 else -1)
+                carry = np.zeros((KE, 128))
+                for g in range(g0, g1):
+                    ft = g + slot * G0
+                    if ft >= n_ft:
+                        continue
+                    first, last = g == g0, (g == g1 - 1) or (ft == n_ft - 1)
+                    S = _time_sum_tile(P[ft][:, :, m0 + pad : m0 + pad + 128], H)
+                    lower = ft > 0
+                    rows_ok = []
+                    for row in range(H, 128 - H):
+                        m = m0 + row
+                        b, t = divmod(m, rpw) if m >= 0 else (0, -1)
+                        if m >= 0 and b < n_windows and t < T:
+                            rows_ok.append((row, b, t, mt * MS + row - H))
+                    if first:
+                        if lower:
+                            for row, b, t, R in rows_ok:
+                                edge[e_lo, 0, :, R] = S[:KE, row]
+                    else:
+                        S[:KE] += carry
+                    jlo = (KE if lower else HALO) if first else 0
+                    jhi = FLT + (HALO if (FLT == 4 and ft == n_ft - 1) else 0)  # pitch layers: the last tile finishes its top bin
+                    for row, b, t, R in rows_ok:
+                        for j in range(jlo, jhi):
+                            f = FLT * ft - HALO + j
+                            if 0 <= f < W:
+                                finish(b, t, f, S[j, row])
+                    carry = S[FLT : FLT + KE].copy()
+                    if last and ft < n_ft - 1 and e_hi >= 0:
+                        for row, b, t, R in rows_ok:
+                            edge[e_hi, 1, :, R] = S[FLT : FLT + KE, row]
+    # edge_fix_kernel
+    for e in range(2 * n_split):
+        es, eq = divmod(e, n_split)
+        ft_b = eq * n_groups // n_split + es * G0
+        if ft_b <= 0 or ft_b >= n_ft:
+            continue
+        for R in range(n_rows):
+            b, t = divmod(R, rpw)
+            if b >= n_windows or t >= T:
+                continue
+            for k in range(KE):
+                f = FLT * ft_b - HALO + k
+                if 0 <= f < W:
+                    finish(b, t, f, edge[e, 0, k, R] + edge[e, 1, k, R])
+    return out
+
+
+@pytest.mark.parametrize("name,n_split", [("contour2", 1), ("contour2", 4), ("note2", 1), ("note2", 5), ("onset2", 1), ("onset2", 12)])
+def test_fused_second_conv_structure(weights_np, name, n_split):
+    key, C, KH2, KW, FLT, HALO, W, rpw, G0 = CASES[name]
     assert KW == 2 * HALO + 1
-    rng = np.random.default_rng(len(name))
-    T = 23
-    x = np.maximum(rng.standard_normal((C, T, W)), 0.0)  # relu(conv1)
+    rng = np.random.default_rng(len(name) + n_split)
+    n_windows = 2
+    x = np.maximum(rng.standard_normal((n_windows, C, T, W)), 0.0)  # relu(conv1) per window
     w_full = weights_np[key].astype(np.float64)  # [1][C(+1)][KH][KW]
     bias = float(weights_np[key[:-2] + "_b"].reshape(-1)[0])
-    PT = KH // 2
+    PT = KH2 // 2
     if name == "onset2":
-        note = rng.random((T, W))
-        w2 = w_full[0, 1:]
-        wx = w_full[0, 0]
-        extra = F.conv2d(torch.from_numpy(note)[None, None], torch.from_numpy(wx)[None, None], padding=(1, 1))[0, 0].numpy()
-        full_in = np.concatenate([note[None], x])
+        note = rng.random((n_windows, T, W))
+        w2, wx = w_full[0, 1:], w_full[0, 0]
+        extra = F.conv2d(torch.from_numpy(note)[:, None], torch.from_numpy(wx)[None, None], padding=(1, 1))[:, 0].numpy()
+        full_in = np.concatenate([note[:, None], x], axis=1)
     else:
-        w2 = w_full[0]
-        extra = None
-        full_in = x
-    Q = _epilogue_planes(x, w2, KH, KW, FLT, HALO, W)
-    got = _tapsum(Q, bias, KH, PT, FLT, HALO, W, extra)
-    ref = torch.sigmoid(F.conv2d(torch.from_numpy(full_in)[None], torch.from_numpy(w_full), torch.tensor([bias], dtype=torch.float64),
-                                 padding=(PT, HALO)))[0, 0].numpy()
-    assert got.shape == ref.shape == (T, W)
+        w2, extra, full_in = w_full[0], None, x
+    # rows of the (window, frame) space, generously padded; rows that are not live frames hold zeros (the kernel zeroes
+    # relu(conv1) of separator rows: they are the zero padding of the next conv in time)
+    pad = 128 + 8
+    n_rows = n_windows * rpw
+    x_rows = np.zeros((C, n_rows + 2 * pad + 128, W))
+    for b in range(n_windows):
+        x_rows[:, pad + b * rpw : pad + b * rpw + T, :] = x[b]
+    got = _fused_layer(x_rows, w2, bias, KH2, KW, FLT, HALO, W, rpw, G0, n_windows, n_split, extra)
+    ref = torch.sigmoid(F.conv2d(torch.from_numpy(full_in), torch.from_numpy(w_full), torch.tensor([bias], dtype=torch.float64),
+                                 padding=(PT, HALO)))[:, 0].numpy()
+    assert not np.isnan(got).any(), f"{int(np.isnan(got).sum())} cells never finished"
+    assert got.shape == ref.shape == (n_windows, T, W)
     assert np.abs(got - ref).max() < 1e-12
 
 
