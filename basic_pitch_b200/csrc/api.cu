@@ -103,17 +103,6 @@ __global__ void desc_upload_kernel(const int4* __restrict__ a_src, int4* __restr
   }
 }
 
-// centre 142 frames of every window -> unwrapped position (reference: inference.py:247-279)
-__global__ void unwrap_kernel(const float* __restrict__ raw, float* __restrict__ out, const UnwrapDesc* __restrict__ ud,
-                              int width) {
-  const int w = blockIdx.y;
-  const UnwrapDesc d = ud[w];
-  const int n = d.rows * width;
-  const float* src = raw + ((size_t)w * kFrames + kOverlapHalf) * width;
-  float* dst = out + d.dst_base * width;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) dst[i] = src[i];
-}
-
 __global__ void compact_notes_kernel(const long long* __restrict__ frame_off, const long long* __restrict__ slot_off,
                                      const int* __restrict__ note_off, const int* __restrict__ s_start,
                                      const int* __restrict__ s_end, const int* __restrict__ s_pitch,
@@ -157,7 +146,11 @@ struct bp_model {
   size_t chl_zeroed = 0;  // elements of chl known to hold zeros in every row/bin the kernels never write
   int64_t launches = 0;
   // forward workspace (chunk windows)
-  DevBuf<float> chain, y, c1, n1, o1, raw_note, raw_onset, raw_contour;
+  DevBuf<float> chain, y, c1, n1, o1;
+  DevBuf<float> raw_note, raw_onset, raw_contour;  // row-major raw windows [nb][172][*] (FP32 path inside run_inference)
+  DevBuf<float> i_note, i_onset, i_contour;        // internal raw: pm [88][chunk*172], cm [33][chunk*172][8] (tensor-core paths)
+  DevBuf<float> u_note, u_onset, u_contour;        // internal unwrapped posteriorgrams of a call: pm [88][F], cm [33][F][8]
+  bool y_is_log = false;  // tensor-core paths: `y` still holds the raw log-magnitudes (bp_debug_activation normalises)
   DevBuf<unsigned int> minmax;
   DevBuf<float> edge;  // partial sums where two frequency-tile ranges of a fused conv meet (tc_conv.cu)
   DevBuf<WinDesc> wdesc;
@@ -327,6 +320,12 @@ int ensure_forward_ws(bp_model* m, int nb) {
     CK(m->o1.reserve((size_t)nb * 32 * kFrames * kPitches));
   }
   CK(m->minmax.reserve((size_t)nb * 2));
+  if (m->path >= 1) {
+    const size_t fr = (size_t)m->chunk * kFrames;
+    CK(m->i_note.reserve(kPitches * fr));
+    CK(m->i_onset.reserve(kPitches * fr));
+    if (m->path == 1) CK(m->i_contour.reserve((size_t)kContourBins * fr));
+  }
   CK(m->edge.reserve(std::max({tc_edge_floats(tc_contour_spec(), nb), tc_edge_floats(tc_onset_spec(), nb),
                                tc_edge_floats(tc_note_spec(), nb)})));
   // split layouts use the row stride of a full chunk whatever the batch size (see launch_conv_tc)
@@ -364,13 +363,19 @@ struct ProfScope {
   }
 };
 
-// HCQT + CNN for `nb` windows (nb <= chunk); outputs raw [nb][172][*].
-// note / onset / contour: raw [nb][172][*] outputs.  With `ud` (bp_run_inference_*), the centre frames of every window
-// also go to their unwrapped position in u_note / u_onset / u_contour: fused into the tap-sum kernels on the tensor-core
-// path (then only the raw note rows are still written, the onset conv reads them), separate copies otherwise.
+// Internal (frame-fastest) posteriorgrams of a call, see TcOut in kernels.cuh.
+struct PostI {
+  float *note, *onset, *contour;  // pm [88][stride], pm [88][stride], cm [33][stride][8]
+  long long stride;
+};
+
+// HCQT + CNN for `nb` windows (nb <= chunk).
+// Without `ud` (bp_forward_*): raw row-major outputs note / onset / contour [nb][172][*].
+// With `ud` (bp_run_inference_*): the centre frames of every window go to their unwrapped position in the internal
+// posteriorgrams `u` — straight from the fused epilogues on the tensor-core path, through a layout conversion of the
+// row-major raw windows on the FP32 path; note / onset / contour are then optional row-major scratch.
 int forward_chunk(bp_model* m, const float* audio, const WinDesc* desc, int nb, float* note, float* onset,
-                  float* contour, cudaStream_t st, const UnwrapDesc* ud = nullptr, float* u_note = nullptr,
-                  float* u_onset = nullptr, float* u_contour = nullptr) {
+                  float* contour, cudaStream_t st, const UnwrapDesc* ud = nullptr, const PostI* u = nullptr) {
   float* chain = m->chain.p;
   if (m->profile_which >= 0) m->prof_windows += nb;
   std::unique_lock<std::mutex> const_lock;
@@ -385,51 +390,77 @@ int forward_chunk(bp_model* m, const float* audio, const WinDesc* desc, int nb, 
   }
   const TcConvSpec cs = tc_contour_spec(), ns = tc_note_spec();
   const int ystride = tc_rows_total(m->chunk, cs.rows_per_window), cstride = tc_rows_total(m->chunk, ns.rows_per_window);
+  const long long fr = (long long)m->chunk * kFrames;  // frame stride of the internal raw buffers
+  const long long nfr = (long long)nb * kFrames;
   {
     ProfScope ps(m, 2, st);
     if (m->path >= 1) {
       launch_cqt_tc(audio, desc, chain, m->cqt_wtc.p, m->d_params + ParamLayout::cqt_scale, m->y.p, m->minmax.p, nb,
                     m->n_sms, st);
-      // NormalizedLog + BatchNorm and the bf16 hi/lo split the convs read, one pass
+      // NormalizedLog + BatchNorm straight into the bf16 hi/lo split the convs read
       launch_lognorm_split(m->y.p, m->minmax.p, m->d_params + ParamLayout::bn, m->yhl.p, cs, nb, ystride, st);
+      m->y_is_log = true;
     } else {
       launch_cqt(audio, desc, chain, m->d_derived + DerivedLayout::cqt_wt, m->d_params + ParamLayout::cqt_scale, m->y.p,
                  m->minmax.p, nb, st);
       launch_lognorm(m->y.p, m->minmax.p, m->d_params + ParamLayout::bn, nb, st);
+      m->y_is_log = false;
     }
   }
+  int extra = 0;  // launches beyond the fixed sequence
   if (m->path >= 1) {
     {
       ProfScope ps(m, 0, st);
       TcOut o;
-      o.raw = m->path == 1 ? contour : m->c1.p;  // path 1: the finished raw contour rows; path 2: channels-last activations
       o.edge = m->edge.p;
+      if (m->path == 1) {  // fused contour conv2: finished posteriorgram (internal layouts) + the note conv's operand
+        o.raw = ud ? nullptr : m->i_contour.p;
+        o.raw_rows = fr;
+        o.ud = ud;
+        o.unwrapped = ud ? u->contour : nullptr;
+        o.frame_stride = ud ? u->stride : 0;
+        o.chl = m->chl.p;
+        o.chl_rows = cstride;
+        o.chl_chunks = ns.chunks8;
+        o.chl_rpw = ns.rows_per_window;
+        o.chl_lead = ns.lead_rows;
+      } else {
+        o.act = m->c1.p;  // channels-last activations
+      }
       launch_conv_tc(m->yhl.p, m->tc_contour.dev, o, nb, ystride, m->n_sms, st, /*fuse_next=*/m->path == 1);
     }
     {
       ProfScope ps(m, 4, st);
-      if (m->path == 1) {
-        launch_contour_split(contour, m->chl.p, nb, cstride, st, ud, u_contour);
-      } else {
+      if (m->path == 2) {
         launch_contour2_tc(m->c1.p, m->cw, contour, m->chl.p, cstride, nb, st);
-        if (ud) unwrap_kernel<<<dim3(16, nb), 256, 0, st>>>(contour, u_contour, ud, kContourBins);
+        if (ud) launch_rows_to_cm(contour, 0, u->contour, u->stride, 0, st, ud, nb), ++extra;
       }
       TcOut o;
-      o.raw = note;  // the onset conv2 reads the raw note rows of the whole window
-      o.unwrapped = u_note;
+      o.raw = m->i_note.p;  // the onset conv2 reads the raw note rows of the whole window
+      o.raw_rows = fr;
       o.ud = ud;
+      o.unwrapped = ud ? u->note : nullptr;
+      o.frame_stride = ud ? u->stride : 0;
       o.edge = m->edge.p;
       launch_conv_tc(m->chl.p, m->tc_note.dev, o, nb, cstride, m->n_sms, st);
     }
     {
       ProfScope ps(m, 1, st);
       TcOut o;
-      o.raw = ud ? nullptr : onset;
-      o.unwrapped = u_onset;
+      o.raw = ud ? nullptr : m->i_onset.p;
+      o.raw_rows = fr;
       o.ud = ud;
-      o.note_raw = note;
+      o.unwrapped = ud ? u->onset : nullptr;
+      o.frame_stride = ud ? u->stride : 0;
+      o.note_raw = m->i_note.p;
       o.edge = m->edge.p;
       launch_conv_tc(m->yhl.p, m->tc_onset.dev, o, nb, ystride, m->n_sms, st);
+    }
+    if (!ud) {  // raw windows for the caller: internal -> row-major
+      launch_pm_to_rows(m->i_note.p, fr, 0, nfr, kPitches, note, st);
+      launch_pm_to_rows(m->i_onset.p, fr, 0, nfr, kPitches, onset, st);
+      if (m->path == 1) launch_cm_to_rows(m->i_contour.p, fr, 0, nfr, contour, st), ++extra;
+      extra += 2;
     }
   } else {
     {
@@ -450,17 +481,17 @@ int forward_chunk(bp_model* m, const float* audio, const WinDesc* desc, int nb, 
       ProfScope ps(m, 4, st);
       launch_onset2(note, m->o1.p, m->cw, onset, nb, st);
     }
-  }
-  if (ud && m->path == 0) {
-    unwrap_kernel<<<dim3(8, nb), 256, 0, st>>>(note, u_note, ud, kPitches);
-    unwrap_kernel<<<dim3(8, nb), 256, 0, st>>>(onset, u_onset, ud, kPitches);
-    unwrap_kernel<<<dim3(16, nb), 256, 0, st>>>(contour, u_contour, ud, kContourBins);
+    if (ud) {
+      launch_rows_to_pm(note, 0, kPitches, u->note, u->stride, 0, st, ud, nb);
+      launch_rows_to_pm(onset, 0, kPitches, u->onset, u->stride, 0, st, ud, nb);
+      launch_rows_to_cm(contour, 0, u->contour, u->stride, 0, st, ud, nb);
+      extra += 3;
+    }
   }
   CKL();
-  // decimation (4 + tail), min/max init + CQT, log-normalise (+ split); tensor-core convs: 3 x (conv + edge fix) +
-  // contour split (path 2: + contour conv2 instead of one edge fix); FP32 path: 6 convs
-  m->launches += 5 + 2 + 1 + (m->path >= 1 ? 7 : 6);
-  if (ud) m->launches += m->path == 0 ? 3 : (m->path == 2 ? 1 : 0);  // separate unwrap copies
+  // decimation (4 + tail), min/max init + CQT, log-normalise (+ split); tensor-core convs: 3 x (conv + edge fix)
+  // (path 2: contour conv2 instead of one edge fix); FP32 path: 6 convs
+  m->launches += 5 + 2 + 1 + 6 + extra;
   m->last_path = m->path;
   return BP_OK;
 }
@@ -589,6 +620,8 @@ void bp_model_destroy(bp_model_t* m) {
   }
   m->chain.release(); m->y.release(); m->c1.release(); m->n1.release(); m->o1.release();
   m->raw_note.release(); m->raw_onset.release(); m->raw_contour.release(); m->minmax.release(); m->edge.release();
+  m->i_note.release(); m->i_onset.release(); m->i_contour.release(); m->u_note.release(); m->u_onset.release();
+  m->u_contour.release();
   m->wdesc.release(); m->udesc.release(); m->st_audio.release(); m->st_note.release(); m->st_onset.release();
   m->st_contour.release(); m->d_frame_off.release(); m->d_slot_off.release(); m->d_note_base.release();
   m->energy.release(); m->d_amp.release(); m->candbits.release(); m->max_onset.release(); m->max_fd.release();
@@ -681,18 +714,16 @@ int bp_forward_host(bp_model_t* m, const float* h_audio, int64_t n_windows, floa
   return BP_OK;
 }
 
-int bp_run_inference_device(bp_model_t* m, const float* d_audio, const int64_t* h_sample_off, int32_t n_files,
-                            float* d_note, float* d_onset, float* d_contour, int64_t* h_frame_off, void* stream) {
-  if (!m || !h_sample_off || !h_frame_off || n_files < 0)
-    return fail(BP_E_INVALID, "bp_run_inference_device: bad argument");
-  DeviceGuard g(m->device);
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
+// HCQT + CNN + unwrap for a batch of files into the internal posteriorgrams `u` (frames of file i at
+// frame_base + h_frame_off[i] ..); h_frame_off is relative to the batch (h_frame_off[0] = 0).
+static int run_inference_internal(bp_model* m, const float* d_audio, const int64_t* h_sample_off, int32_t n_files,
+                                  const PostI& u, int64_t frame_base, int64_t* h_frame_off, cudaStream_t st) {
   std::vector<WinDesc> wd;
   std::vector<UnwrapDesc> ud;
   h_frame_off[0] = 0;
   for (int i = 0; i < n_files; ++i) {
     const int64_t n = h_sample_off[i + 1] - h_sample_off[i];
-    if (n < 0) return fail(BP_E_INVALID, "bp_run_inference_device: sample offsets must be non-decreasing");
+    if (n < 0) return fail(BP_E_INVALID, "run_inference: sample offsets must be non-decreasing");
     const int64_t nw = bp_num_windows(n), nf = bp_num_frames(n);
     for (int64_t w = 0; w < nw; ++w) {
       const int64_t s = w * kHopSamples - kLeadZeros;  // window start relative to the file
@@ -701,24 +732,26 @@ int bp_run_inference_device(bp_model_t* m, const float* d_audio, const int64_t* 
       d.lo = (int)std::max<int64_t>(0, -s);
       d.hi = (int)std::max<int64_t>(d.lo, std::min<int64_t>(kWinSamples, n - s));
       wd.push_back(d);
-      UnwrapDesc u;
-      u.dst_base = h_frame_off[i] + w * kHopFrames;
-      u.rows = (int)std::max<int64_t>(0, std::min<int64_t>(kHopFrames, nf - w * kHopFrames));
-      u.pad = 0;
-      ud.push_back(u);
+      UnwrapDesc x;
+      x.dst_base = frame_base + h_frame_off[i] + w * kHopFrames;
+      x.rows = (int)std::max<int64_t>(0, std::min<int64_t>(kHopFrames, nf - w * kHopFrames));
+      x.pad = 0;
+      ud.push_back(x);
     }
     h_frame_off[i + 1] = h_frame_off[i] + nf;
   }
   const int64_t nwin = (int64_t)wd.size();
   if (nwin == 0) return BP_OK;
-  if (!d_audio || !d_note || !d_onset || !d_contour) return fail(BP_E_INVALID, "bp_run_inference_device: null buffer");
+  if (!d_audio) return fail(BP_E_INVALID, "run_inference: null audio");
   const int chunk = m->chunk;
   int rc = ensure_forward_ws(m, (int)std::min<int64_t>(nwin, chunk));
   if (rc) return rc;
   const int nbmax = (int)std::min<int64_t>(nwin, chunk);
-  CK(m->raw_note.reserve((size_t)nbmax * kFrames * kPitches));
-  CK(m->raw_onset.reserve((size_t)nbmax * kFrames * kPitches));
-  CK(m->raw_contour.reserve((size_t)nbmax * kFrames * kContourBins));
+  if (m->path == 0) {  // row-major raw windows of the FP32 kernels, converted + unwrapped per chunk
+    CK(m->raw_note.reserve((size_t)nbmax * kFrames * kPitches));
+    CK(m->raw_onset.reserve((size_t)nbmax * kFrames * kPitches));
+  }
+  if (m->path != 1) CK(m->raw_contour.reserve((size_t)nbmax * kFrames * kContourBins));
   CK(m->wdesc.reserve(nwin));
   CK(m->udesc.reserve(nwin));
   // descriptors go through pinned staging owned by the model, guarded by an event that completes with the copy (not with
@@ -749,15 +782,57 @@ int bp_run_inference_device(bp_model_t* m, const float* d_audio, const int64_t* 
       reinterpret_cast<const int4*>(m->h_wd), reinterpret_cast<int4*>(m->wdesc.p), reinterpret_cast<const int4*>(m->h_ud),
       reinterpret_cast<int4*>(m->udesc.p), (int)nwin);
   CKL();
+  m->launches += 1;
   CK(cudaEventRecord(m->desc_ev, st));
   m->desc_pending = true;
   for (int64_t c0 = 0; c0 < nwin; c0 += chunk) {
     const int nb = (int)std::min<int64_t>(chunk, nwin - c0);
     rc = forward_chunk(m, d_audio, m->wdesc.p + c0, nb, m->raw_note.p, m->raw_onset.p, m->raw_contour.p, st,
-                       m->udesc.p + c0, d_note, d_onset, d_contour);
+                       m->udesc.p + c0, &u);
     if (rc) return rc;
   }
   m->last_forward_n = std::min<int64_t>(nwin, chunk) == nwin ? nwin : 0;
+  return BP_OK;
+}
+
+// internal posteriorgram buffers of the model for `total_frames` frames
+static int reserve_internal(bp_model* m, int64_t total_frames, PostI* u) {
+  const size_t F = (size_t)((total_frames + 31) / 32 * 32 + 32);
+  CK(m->u_note.reserve(kPitches * F));
+  CK(m->u_onset.reserve(kPitches * F));
+  CK(m->u_contour.reserve((size_t)kContourBins * F));
+  *u = PostI{m->u_note.p, m->u_onset.p, m->u_contour.p, (long long)F};
+  return BP_OK;
+}
+
+// internal -> the row-major arrays of the C ABI (any of the destinations may be null)
+static void internal_to_rows(bp_model* m, const PostI& u, int64_t total_frames, float* d_note, float* d_onset,
+                             float* d_contour, cudaStream_t st) {
+  if (d_note) launch_pm_to_rows(u.note, u.stride, 0, total_frames, kPitches, d_note, st), m->launches += 1;
+  if (d_onset) launch_pm_to_rows(u.onset, u.stride, 0, total_frames, kPitches, d_onset, st), m->launches += 1;
+  if (d_contour) launch_cm_to_rows(u.contour, u.stride, 0, total_frames, d_contour, st), m->launches += 1;
+}
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+int bp_run_inference_device(bp_model_t* m, const float* d_audio, const int64_t* h_sample_off, int32_t n_files,
+                            float* d_note, float* d_onset, float* d_contour, int64_t* h_frame_off, void* stream) {
+  if (!m || !h_sample_off || !h_frame_off || n_files < 0)
+    return fail(BP_E_INVALID, "bp_run_inference_device: bad argument");
+  DeviceGuard g(m->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int64_t total_frames = 0;
+  for (int i = 0; i < n_files; ++i) total_frames += bp_num_frames(h_sample_off[i + 1] - h_sample_off[i]);
+  if (total_frames > 0 && (!d_audio || !d_note || !d_onset || !d_contour))
+    return fail(BP_E_INVALID, "bp_run_inference_device: null buffer");
+  if (!aligned16(d_contour)) return fail(BP_E_INVALID, "bp_run_inference_device: d_contour must be 16-byte aligned");
+  PostI u;
+  int rc = reserve_internal(m, total_frames, &u);
+  if (rc) return rc;
+  rc = run_inference_internal(m, d_audio, h_sample_off, n_files, u, 0, h_frame_off, st);
+  if (rc) return rc;
+  internal_to_rows(m, u, total_frames, d_note, d_onset, d_contour, st);
+  CKL();
   return BP_OK;
 }
 
@@ -1029,14 +1104,19 @@ int bp_transcribe_device(bp_model_t* m, const float* d_audio, const int64_t* h_s
   int rc = validate_params(params);
   if (rc) return rc;
   DeviceGuard g(m->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
   int64_t total_frames = 0;
   for (int i = 0; i < n_files; ++i) total_frames += bp_num_frames(h_sample_off[i + 1] - h_sample_off[i]);
-  CK(m->st_note.reserve((size_t)total_frames * kPitches + 1));
-  CK(m->st_onset.reserve((size_t)total_frames * kPitches + 1));
-  CK(m->st_contour.reserve((size_t)total_frames * kContourBins + 1));
-  rc = bp_run_inference_device(m, d_audio, h_sample_off, n_files, m->st_note.p, m->st_onset.p, m->st_contour.p,
-                               h_frame_off, stream);
+  CK(m->st_note.reserve((size_t)total_frames * kPitches + 4));
+  CK(m->st_onset.reserve((size_t)total_frames * kPitches + 4));
+  CK(m->st_contour.reserve((size_t)total_frames * kContourBins + 4));
+  PostI u;
+  rc = reserve_internal(m, total_frames, &u);
   if (rc) return rc;
+  rc = run_inference_internal(m, d_audio, h_sample_off, n_files, u, 0, h_frame_off, st);
+  if (rc) return rc;
+  internal_to_rows(m, u, total_frames, m->st_note.p, m->st_onset.p, m->st_contour.p, st);
+  CKL();
   return bp_decode_device(m, m->st_note.p, m->st_onset.p, m->st_contour.p, h_frame_off, n_files, params, notes, stream);
 }
 
@@ -1058,9 +1138,12 @@ int bp_transcribe_host(bp_model_t* m, const float* h_audio, const int64_t* h_sam
     if (rel[i + 1] < rel[i]) return fail(BP_E_INVALID, "bp_transcribe_host: sample offsets must be non-decreasing");
     total_frames += bp_num_frames(rel[i + 1] - rel[i]);
   }
-  CK(m->st_note.reserve((size_t)total_frames * kPitches + 1));
-  CK(m->st_onset.reserve((size_t)total_frames * kPitches + 1));
-  CK(m->st_contour.reserve((size_t)total_frames * kContourBins + 1));
+  CK(m->st_note.reserve((size_t)total_frames * kPitches + 4));
+  CK(m->st_onset.reserve((size_t)total_frames * kPitches + 4));
+  CK(m->st_contour.reserve((size_t)total_frames * kContourBins + 4));
+  PostI u;
+  rc = reserve_internal(m, total_frames, &u);
+  if (rc) return rc;
 
   // Sub-batches of files (about 4 internal chunks of windows each): all host->device copies are queued on the copy
   // stream up front, the compute stream waits for sub-batch k only, so the PCIe transfer of k+1.. overlaps the kernels.
@@ -1103,11 +1186,12 @@ int bp_transcribe_host(bp_model_t* m, const float* h_audio, const int64_t* h_sam
     CK(cudaStreamWaitEvent(st, m->copy_ev[k], 0));
     sub_off.assign(f1 - f0 + 1, 0);
     const int64_t base = h_frame_off[f0];
-    rc = bp_run_inference_device(m, m->st_audio.p, rel.data() + f0, f1 - f0, m->st_note.p + base * kPitches,
-                                 m->st_onset.p + base * kPitches, m->st_contour.p + base * kContourBins, sub_off.data(), st);
+    rc = run_inference_internal(m, m->st_audio.p, rel.data() + f0, f1 - f0, u, base, sub_off.data(), st);
     if (rc) return rc;
     for (int i = f0; i < f1; ++i) h_frame_off[i + 1] = base + sub_off[i - f0 + 1];
   }
+  internal_to_rows(m, u, total_frames, m->st_note.p, m->st_onset.p, m->st_contour.p, st);
+  CKL();
   rc = bp_decode_device(m, m->st_note.p, m->st_onset.p, m->st_contour.p, h_frame_off, n_files, params, notes, st);
   if (rc) return rc;
   if (total_frames > 0) {
@@ -1186,6 +1270,11 @@ int bp_debug_activation(bp_model_t* m, int which, float* h_out, int64_t n_window
     return fail(BP_E_INVALID, "bp_debug_activation: path 1 reduces the contour activations in the epilogue "
                               "(use bp_model_set_path(m, 2) or 0)");
   CK(cudaDeviceSynchronize());
+  if (which == 0 && m->y_is_log) {  // the tensor-core paths normalise straight into the split operand: finish `y` now
+    launch_lognorm(m->y.p, m->minmax.p, m->d_params + ParamLayout::bn, (int)m->last_forward_n, m->stream);
+    CK(cudaStreamSynchronize(m->stream));
+    m->y_is_log = false;
+  }
   CK(cudaMemcpy(h_out, src, sizeof(float) * per * n_windows, cudaMemcpyDeviceToHost));
   if (which == 1 && m->last_path == 2) {  // the tensor-core path keeps this activation channels-last: return NCHW
     std::vector<float> tmp(h_out, h_out + per * n_windows);

@@ -80,24 +80,30 @@ struct UnwrapDesc {
   int rows;            // how many of its 142 centre frames are kept (may be <= 0)
   int pad;
 };
-// NormalizedLog + folded BatchNorm of the CQT log-magnitudes (in place, fp32) and their bf16 hi/lo split in the
-// k-chunk-major row layout of tc_contour_spec() / tc_onset_spec() in one pass.
+// NormalizedLog + folded BatchNorm of the CQT log-magnitudes straight into the bf16 hi/lo split operand (k-chunk-major
+// row layout of tc_contour_spec() / tc_onset_spec()); `y` itself is left untouched (launch_lognorm makes the fp32 copy).
 // rows_stride: row stride of the split layout (>= tc_rows_total(n_windows, ...)); fixed per model so that rows the
 // kernels never write (separators, pads) keep their zeros across batches of different size
-void launch_lognorm_split(float* y, const unsigned int* minmax, const float* bn, __nv_bfloat16* dst, const TcConvSpec& spec,
-                          int n_windows, int rows_stride, cudaStream_t st);
-// raw contour posteriorgram [B][172][264] -> split operand of the note conv (+ centre frames to their unwrapped place)
-void launch_contour_split(const float* raw_contour, __nv_bfloat16* chl, int n_windows, int rows_stride, cudaStream_t st,
-                          const UnwrapDesc* ud = nullptr, float* unwrapped = nullptr);
-// Outputs of a fused layer: the finished posteriorgram rows go to `raw` ([B][172][WOUT], may be null) and / or, with `ud`,
-// the centre frames of every window straight to their unwrapped position in `unwrapped`.  EPI 0 (path 2): `raw` is the
-// channels-last activation buffer.
+void launch_lognorm_split(const float* y, const unsigned int* minmax, const float* bn, __nv_bfloat16* dst,
+                          const TcConvSpec& spec, int n_windows, int rows_stride, cudaStream_t st);
+// Outputs of a fused layer.  Device-internal posteriorgram layouts have the FRAME index fastest, so that the epilogue
+// threads (one frame each, 32 consecutive frames per warp) store coalesced, and so that the decode kernels read coalesced:
+//   note / onset   pitch-major   pm[pitch][frame]                 frame stride = number of frames the buffer holds
+//   contour        chunk-major   cm[8-bin chunk (33)][frame][8]
+// `raw` holds all 172 frames of every window of the chunk (frame index b*172 + t, stride `raw_rows`); with `ud` the centre
+// frames of every window also / instead go to their unwrapped position (reference: inference.py:247-279) in `unwrapped`,
+// whose frame stride is `frame_stride`.
 struct TcOut {
   float* raw = nullptr;
   float* unwrapped = nullptr;
+  long long frame_stride = 0;
+  long long raw_rows = 0;           // frame stride of `raw` and `note_raw`
   const UnwrapDesc* ud = nullptr;
-  const float* note_raw = nullptr;  // onset layer: the raw note posteriorgram (input channel 0 of its conv2)
+  const float* note_raw = nullptr;  // onset layer: the raw pitch-major note posteriorgram (input channel 0 of its conv2)
+  __nv_bfloat16* chl = nullptr;     // contour layer: split operand of the note conv [2][chl_chunks][chl_rows][8]
+  int chl_rows = 0, chl_chunks = 0, chl_rpw = 0, chl_lead = 0;
   float* edge = nullptr;            // >= tc_edge_floats(spec, n_windows) floats of scratch
+  float* act = nullptr;             // EPI 0 (path 2): channels-last activations [B][172][WOUT][COUT]
 };
 // fuse_next (contour layer only; the other two always fuse): also compute the following conv in the epilogue instead
 // of storing the channels-last activations
@@ -114,7 +120,19 @@ void cqt_tc_setup();
 void launch_cqt_tc(const float* audio, const WinDesc* desc, const float* chain, const uint16_t* wtc, const float* scale,
                    float* logmag, unsigned int* minmax, int n_windows, int n_sms, cudaStream_t st);
 
-// ---- unwrap (api.cu) / decode.cu ----------------------------------------------------------------
+// ---- layout.cu: internal frame-fastest layouts (pm / cm, see TcOut) <-> row-major [frame][bins] of the C ABI ------
+// rows -> internal: without `ud` frames [0, n_frames) go to dst_frame0 ..; with `ud` `rows` is a chunk of raw windows
+// [n_windows][172][bins] and the kept centre frames of every window go to their unwrapped position
+void launch_rows_to_pm(const float* rows, long long n_frames, int width, float* pm, long long stride, long long dst_frame0,
+                       cudaStream_t st, const UnwrapDesc* ud = nullptr, int n_windows = 0);
+void launch_rows_to_cm(const float* rows, long long n_frames, float* cm, long long stride, long long dst_frame0,
+                       cudaStream_t st, const UnwrapDesc* ud = nullptr, int n_windows = 0);
+void launch_pm_to_rows(const float* pm, long long stride, long long src_frame0, long long n_frames, int width, float* rows,
+                       cudaStream_t st);
+void launch_cm_to_rows(const float* cm, long long stride, long long src_frame0, long long n_frames, float* rows,
+                       cudaStream_t st);
+
+// ---- decode.cu ----------------------------------------------------------------------------------
 struct DecodeParamsDev {
   double onset_thresh, frame_thresh;
   int min_note_len, energy_tol, infer_onsets, melodia, lo_col, hi_col;

@@ -12,8 +12,10 @@
 // completely, so neither the 8- / 32-channel activations nor any partial sums of them reach HBM:
 //   * channels and frequency taps are reduced inside the thread that owns the frame (packed FP32 FMAs),
 //   * the time taps are summed across the lanes of the warp (the 32 lanes hold 32 consecutive frames: shuffles) and
-//     across the four epilogue warps of an accumulator slot through a 480-byte shared-memory exchange; M-tiles overlap
-//     by KH2 - 1 rows, so every frame is complete in exactly one tile,
+//     across the four epilogue warps of an accumulator slot through a small shared-memory exchange; M-tiles overlap
+//     by KH2 - 1 rows, so every frame is complete in exactly one tile.  The thread of tile row r finishes the output
+//     frame r - H (H = KH2 / 2), so every tap comes from a lane at or below its own: each lane adds its taps in the
+//     same order whatever its position in the tile, and a frame's value does not depend on the batch around it,
 //   * the frequency halo between neighbouring tiles is a register carry: a slot walks its frequency tiles in ascending
 //     order; only where two tile RANGES meet (slot 0 | slot 1, or the group splits of a small batch) the two partial
 //     sums go to a small edge buffer and edge_fix_kernel finishes those 4 (contour) / 2 bins,
@@ -75,10 +77,9 @@ constexpr int kThreads = 352;  // 11 warps: 2 x 4 epilogue warps, producer, 2 MM
 // (producer, MMA issuers) get the highest ids and are never starved by the FFMA streams of the epilogue warps.
 constexpr int kProducerWarp = 8, kMmaWarp0 = 9, kMmaWarp1 = 10;
 // time-halo exchange between the four epilogue warps of a slot: [slot 2][buffer 2][warp 4][kXchgFloats]
-constexpr int kXchgFloats = 120;  // contour: 6 published lanes x 20 output offsets (note 12 x 6, onset 2 x 6)
+constexpr int kXchgFloats = 200;  // contour: 10 published lane values x 20 output offsets (note 21 x 6, onset 3 x 6)
 constexpr int kXchgBytes = 2 * 2 * 4 * kXchgFloats * 4;
 constexpr int kSmemBytes = kMaxDataBytes + kStages * kTileBytes + kXchgBytes + 512;
-constexpr int kMaxEdges = 32;  // frequency tiles at which a tile range may start (edge buffer slots)
 // step word of a slot: [0,14) A start-address offset >> 4, [15] first MMA into that accumulator; kNoUse = the
 // slot's frequency tile does not use this step's weight tile
 constexpr uint32_t kUseFirstAcc = 1u << 15, kNoUse = 0xffffffffu;
@@ -316,10 +317,10 @@ int tc_upload_program(int layer, const TcConvPlan& pl, cudaStream_t st) {
 // fp32 rows -> bf16 hi/lo planes in the k-chunk-major row layout the MMA reads:
 //   dst[plane][q8 (chunks8)][row d (rows_total)][8],  d = lead + b*rows_per_window + t, every other row zero.
 // lognorm_split_kernel: the log-magnitude of the CQT kernel -> NormalizedLog (reference: layers/signal.py:177-183:
-//   (L - min) / (max - min), 0 when max == min) + folded BatchNorm (models.py:188-189), written back in place as fp32
-//   (FP32 path, activation tests) AND as the split operand of the contour / onset convs (309 bins -> 40 chunks).
-// contour_split_kernel: the contour posteriorgram (264 bins -> 34 chunks) as the operand of the note conv, and its
-//   centre frames to their unwrapped position (reference: inference.py:247-279).
+//   (L - min) / (max - min), 0 when max == min) + folded BatchNorm (models.py:188-189) as the split operand of the
+//   contour / onset convs (309 bins -> 40 chunks).  (The fp32 copy is only produced on request: launch_lognorm.)
+// The contour posteriorgram reaches the note conv in the same layout (264 bins -> 34 chunks), written by the contour
+// epilogue itself.
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void store_split8(const float (&v)[8], __nv_bfloat16* dst, size_t off, size_t plane) {
   __align__(16) __nv_bfloat16 hi[8], lo[8];
@@ -332,7 +333,7 @@ __device__ __forceinline__ void store_split8(const float (&v)[8], __nv_bfloat16*
   *reinterpret_cast<uint4*>(dst + plane + off) = *reinterpret_cast<const uint4*>(lo);
 }
 
-__global__ void lognorm_split_kernel(float* __restrict__ y, const unsigned int* __restrict__ minmax,
+__global__ void lognorm_split_kernel(const float* __restrict__ y, const unsigned int* __restrict__ minmax,
                                      const float* __restrict__ bn, __nv_bfloat16* __restrict__ dst, int n_windows,
                                      int rows_used, int rows_total /* stride */, int chunks8, int rows_per_window, int lead) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // one (row, q8) per thread
@@ -350,42 +351,16 @@ __global__ void lognorm_split_kernel(float* __restrict__ y, const unsigned int* 
       const float bn_scale = __ldg(bn), bn_bias = __ldg(bn + 1);
       const float mn = ordered_to_float(minmax[2 * b]);
       const float mx = __fsub_rn(ordered_to_float(minmax[2 * b + 1]), mn);
-      float* p = y + ((size_t)b * kFrames + t) * kCqtBins + q8 * 8;
+      const float* p = y + ((size_t)b * kFrames + t) * kCqtBins + q8 * 8;
 #pragma unroll
       for (int j = 0; j < 8; ++j)
         if (q8 * 8 + j < kCqtBins) {
-          const float q = (mx == 0.f) ? 0.f : __fdiv_rn(__fsub_rn(p[j], mn), mx);
+          const float q = (mx == 0.f) ? 0.f : __fdiv_rn(__fsub_rn(__ldg(p + j), mn), mx);
           v[j] = __fadd_rn(__fmul_rn(q, bn_scale), bn_bias);
-          p[j] = v[j];
         }
     }
   }
   store_split8(v, dst, ((size_t)q8 * rows_total + d) * 8, (size_t)chunks8 * rows_total * 8);
-}
-
-__global__ void contour_split_kernel(const float* __restrict__ raw /* [B][172][264] */, __nv_bfloat16* __restrict__ dst,
-                                     int n_windows, int rows_total, int chunks8, int rows_per_window, int lead,
-                                     const UnwrapDesc* __restrict__ ud, float* __restrict__ unwrapped) {
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // one (frame, q8) per thread, frames fastest
-  const long long total = (long long)n_windows * kFrames * (kContourBins / 8);
-  if (idx >= total) return;
-  const int fr = (int)(idx % ((long long)n_windows * kFrames));
-  const int q8 = (int)(idx / ((long long)n_windows * kFrames));
-  const int b = fr / kFrames, t = fr - b * kFrames;
-  const float4* p = reinterpret_cast<const float4*>(raw + (size_t)fr * kContourBins + q8 * 8);
-  const float4 x0 = __ldg(p), x1 = __ldg(p + 1);
-  const float v[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
-  const size_t d = (size_t)lead + (size_t)b * rows_per_window + t;
-  store_split8(v, dst, ((size_t)q8 * rows_total + d) * 8, (size_t)chunks8 * rows_total * 8);
-  if (ud) {
-    const UnwrapDesc u = ud[b];
-    const int tt = t - kOverlapHalf;
-    if ((unsigned)tt < (unsigned)max(u.rows, 0)) {
-      float4* o = reinterpret_cast<float4*>(unwrapped + (size_t)(u.dst_base + tt) * kContourBins + q8 * 8);
-      o[0] = x0;
-      o[1] = x1;
-    }
-  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -394,12 +369,8 @@ __global__ void contour_split_kernel(const float* __restrict__ raw /* [B][172][2
 struct TcArgs {
   const __nv_bfloat16* data;    // [2][chunks8][rows_total][8]
   const uint16_t* tiles;        // [n_tiles][8192 B]
-  float* out;                   // EPI 0: [B][172][WOUT][COUT] channels-last ; EPI 1/2/3: raw [B][172][WOUT] (may be null)
-  float* out_unw;               // EPI 1/2: unwrapped [frames][WOUT] (with ud)
-  const UnwrapDesc* ud;
-  const float* note_raw;        // EPI 1: the note posteriorgram [B][172][88] (input channel 0 of the onset conv2)
-  float* edge;                  // [edge slot][side 2][KE][edge_rows]: partial sums where two tile ranges meet
-  int edge_rows;
+  TcOut o;                      // where the results go (kernels.cuh)
+  int edge_rows;                // row stride of o.edge: [edge slot][side 2][KE][edge_rows]
   int layer;                    // which constant-memory program (0 contour, 1 onset, 2 note)
   int rows_total, n_mtiles, n_windows;
   int n_groups, n_split;        // an item covers groups [s*n_groups/n_split, (s+1)*n_groups/n_split)
@@ -415,42 +386,35 @@ __device__ __forceinline__ void slot_barrier(int slot) {  // the four epilogue w
   asm volatile("bar.sync %0, 128;" ::"r"(1 + slot) : "memory");
 }
 
-// Time taps of the fused conv2 across frames.  P are the per-frame partial sums of time tap dt2 (delta = dt2 - H):
-// output frame r needs P of frame r + delta, i.e. lane + delta; lanes whose source lies in the neighbouring warp get it
-// from that warp's published values after the slot barrier (time_edges).  Published entries of a warp:
-//   delta = +a (a = 1..H): its lanes 0 .. a-1          -> entries a(a-1)/2 + lane
-//   delta = -a           : its lanes 32-a .. 31        -> entries H(H+1)/2 + a(a-1)/2 + lane - (32 - a)
+// Time taps of the fused conv2 across frames.  The thread of tile row r finishes output frame q = r - H of the tile's row
+// space: out[q] = sum_dt P_dt[q + dt - H] = sum_a P_{2H-a}[row r - a], a = 0 .. 2H, i.e. every source is `a` lanes BELOW the
+// thread.  Sources inside the warp come by shuffle; lanes < a of warps 1..3 take them from the values the previous warp
+// published (lanes 32-a .. 31 -> entries a(a-1)/2 + lane - (32-a)) after the slot barrier (time_edges).  A lane adds
+// a = 0, 1, .., 2H in this order in both places, so the rounding of a frame does not depend on its row in the tile.
 template <int H, int NJ>
-__device__ __forceinline__ void time_tap(float (&S)[NJ], const float (&P)[NJ], int delta, int lane, float* pub) {
-  if (delta == 0) {
+__device__ __forceinline__ void time_tap(float (&S)[NJ], const float (&P)[NJ], int a, int lane, float* pub) {
+  if (a == 0) {
 #pragma unroll
     for (int j = 0; j < NJ; ++j) S[j] += P[j];
     return;
   }
-  const int src = lane + delta;
-  const bool ok = (unsigned)src < 32u;
-  const int a = delta > 0 ? delta : -delta;
-  const int idx = delta > 0 ? lane : lane - (32 - a);
-  const bool publish = (unsigned)idx < (unsigned)a;
-  float* e = pub + ((delta > 0 ? 0 : H * (H + 1) / 2) + a * (a - 1) / 2 + idx) * NJ;
+  const bool ok = lane >= a;
+  const bool publish = lane >= 32 - a;
+  float* e = pub + (a * (a - 1) / 2 + lane - (32 - a)) * NJ;
 #pragma unroll
   for (int j = 0; j < NJ; ++j) {
-    const float v = __shfl_sync(0xffffffffu, P[j], src & 31);
+    const float v = __shfl_up_sync(0xffffffffu, P[j], a);
     if (ok) S[j] += v;
     if (publish) e[j] = P[j];
   }
 }
 template <int H, int NJ>
 __device__ __forceinline__ void time_edges(float (&S)[NJ], int quad, int lane, const float* xb /* [4][kXchgFloats] */) {
+  if (quad == 0) return;
 #pragma unroll
-  for (int a = 1; a <= H; ++a) {
-    if (quad < 3 && lane >= 32 - a) {  // delta = +a from the next warp
-      const float* e = xb + (quad + 1) * tc::kXchgFloats + (a * (a - 1) / 2 + lane + a - 32) * NJ;
-#pragma unroll
-      for (int j = 0; j < NJ; ++j) S[j] += e[j];
-    }
-    if (quad > 0 && lane < a) {  // delta = -a from the previous warp
-      const float* e = xb + (quad - 1) * tc::kXchgFloats + (H * (H + 1) / 2 + a * (a - 1) / 2 + lane) * NJ;
+  for (int a = 1; a <= 2 * H; ++a) {
+    if (lane < a) {  // source `a` rows below: lane 32 - a + lane of the previous warp
+      const float* e = xb + (quad - 1) * tc::kXchgFloats + (a * (a - 1) / 2 + lane) * NJ;
 #pragma unroll
       for (int j = 0; j < NJ; ++j) S[j] += e[j];
     }
@@ -460,35 +424,37 @@ __device__ __forceinline__ void time_edges(float (&S)[NJ], int quad, int lane, c
 // Edge-buffer slot of the tile range that slot `s` of split `q` walks (it starts at tile g0(q) + s * G0): s * n_split + q.
 // The range that ENDS below it is slot s of split q - 1, or, for (s, q) = (1, 0), slot 0 of the last split.
 
-// what the epilogue thread of one frame knows about where its results go
+// What the epilogue thread of one frame knows about where its results go.  All stores are coalesced: the 32 lanes of a
+// warp hold 32 consecutive frames, and every layout below has the frame index fastest.
+//   pitch layers (note / onset)  pitch-major planes  [pitch][frame]
+//   contour                      chunk-major         [8-bin chunk][frame][8]  (fp32), same shape as the bf16 hi/lo
+//                                split layout [plane][chunk][row][8] that the note conv reads
 struct RowOut {
-  float* raw;    // raw [B][172][WOUT] row of this frame (nullptr: not stored)
-  float* unw;    // unwrapped row (nullptr: not stored)
+  float* raw;    // pitch layers: raw_pm + b*172 + t        ; contour: raw_cm + (b*172 + t)*8            (nullptr: not stored)
+  float* unw;    // pitch layers: unw_pm + unwrapped frame  ; contour: unw_cm + unwrapped frame * 8      (nullptr: not stored)
+  __nv_bfloat16* chl;  // contour: chl + data row * 8
   float* edge;   // edge buffer column of this frame: edge + R (nullptr: row not complete / not live)
-  const float* note_rows[3];  // EPI 1: rows t-1, t, t+1 of the raw note posteriorgram (nullptr outside the window)
-  bool ok;       // live frame whose time taps are complete in this M-tile
+  const float* note_col;  // EPI 1: note_raw_pm + b*172 + t
+  int t;         // frame inside the window (of the OUTPUT frame this thread finishes)
+  bool ok;       // live output frame whose time taps are complete in this M-tile
   int e_lo, e_hi;  // edge slots of this range's start and of the range above its end (-1: none)
 };
 
 // Time taps of one output column (onset / note layers): acc holds the KH2 per-frame partial sums of the column as pairs
-// of time taps; returns the sum over the taps available inside the warp and publishes the edge lanes (see time_tap).
+// of time taps; returns the sum over the taps available inside the warp and publishes the top lanes (see time_tap).
 template <int KH2>
 __device__ __forceinline__ float time_taps_col(const float2 (&acc)[(KH2 + 1) / 2], int lane, float* pub_col /* pub + j */) {
-  constexpr int H = KH2 / 2;
   float s = 0.f;
 #pragma unroll
-  for (int dt = 0; dt < KH2; ++dt) {
+  for (int a = 0; a < KH2; ++a) {
+    const int dt = KH2 - 1 - a;
     const float p = (dt & 1) ? acc[dt >> 1].y : acc[dt >> 1].x;
-    const int delta = dt - H;
-    if (delta == 0) {
+    if (a == 0) {
       s += p;
     } else {
-      const int src = lane + delta;
-      const float v = __shfl_sync(0xffffffffu, p, src & 31);
-      if ((unsigned)src < 32u) s += v;
-      const int a = delta > 0 ? delta : -delta;
-      const int idx = delta > 0 ? lane : lane - (32 - a);
-      if ((unsigned)idx < (unsigned)a) pub_col[((delta > 0 ? 0 : H * (H + 1) / 2) + a * (a - 1) / 2 + idx) * 6] = p;
+      const float v = __shfl_up_sync(0xffffffffu, p, a);
+      if (lane >= a) s += v;
+      if (lane >= 32 - a) pub_col[(a * (a - 1) / 2 + lane - (32 - a)) * 6] = p;
     }
   }
   return s;
@@ -574,17 +540,16 @@ __device__ __forceinline__ void finish_pitch_tile(const TcArgs& a, const RowOut&
   const int jhi = (ft == a.n_ft - 1) ? 5 : 4;  // the last tile also finishes its top bin (no tile above)
   if (ro.ok) {
     float nv[3][6];
-    if constexpr (EPI == 1) {  // note rows t-1 .. t+1, columns 4 ft - 2 .. 4 ft + 3 (zero outside the image)
+    if constexpr (EPI == 1) {  // note frames t-1 .. t+1, pitches 4 ft - 2 .. 4 ft + 3 (zero outside the image); lanes run along t
 #pragma unroll
-      for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 6; ++c) {
+        const int f = 4 * ft - 2 + c;
+        const bool fin = (unsigned)f < (unsigned)kPitches;
+        const float* col = ro.note_col + (size_t)f * a.o.raw_rows;
 #pragma unroll
-        for (int q = 0; q < 3; ++q) {
-          const int c0 = 4 * ft - 2 + 2 * q;
-          float2 x = make_float2(0.f, 0.f);
-          if (ro.note_rows[r] && c0 >= 0 && c0 < kPitches) x = __ldg(reinterpret_cast<const float2*>(ro.note_rows[r] + c0));
-          nv[r][2 * q] = x.x;
-          nv[r][2 * q + 1] = x.y;
-        }
+        for (int r = 0; r < 3; ++r)
+          nv[r][c] = (fin && (unsigned)(ro.t + r - 1) < (unsigned)kFrames) ? __ldg(col + r - 1) : 0.f;
+      }
     }
 #pragma unroll
     for (int j = 0; j < 5; ++j) {
@@ -596,11 +561,11 @@ __device__ __forceinline__ void finish_pitch_tile(const TcArgs& a, const RowOut&
         for (int r = 0; r < 3; ++r)
 #pragma unroll
           for (int df = 0; df < 3; ++df)
-            if (j + df < 6) x = fmaf(nv[r][j + df], c_onset_note_w[r * 3 + df], x);  // column f + df - 1 = 4 ft - 2 + (j + df)
+            if (j + df < 6) x = fmaf(nv[r][j + df], c_onset_note_w[r * 3 + df], x);  // pitch f + df - 1 = 4 ft - 2 + (j + df)
       }
       const float v = sigmoidf_fast(x);
-      if (ro.raw) ro.raw[f] = v;
-      if (ro.unw) ro.unw[f] = v;
+      if (ro.raw) ro.raw[(size_t)f * a.o.raw_rows] = v;
+      if (ro.unw) ro.unw[(size_t)f * a.o.frame_stride] = v;
     }
   }
   carry[0] = S[4];
@@ -609,6 +574,23 @@ __device__ __forceinline__ void finish_pitch_tile(const TcArgs& a, const RowOut&
     float* e = ro.edge + (size_t)(ro.e_hi * 2 + 1) * 2 * a.edge_rows;
     e[0] = S[4];
     e[a.edge_rows] = S[5];
+  }
+}
+
+// One finished 8-bin chunk of the contour posteriorgram for one frame: bf16 hi/lo into the operand layout of the note
+// conv, fp32 into the chunk-major posteriorgram.
+__device__ __forceinline__ void store_contour_chunk(const TcArgs& a, const RowOut& ro, int chunk, const float (&v)[8]) {
+  store_split8(v, ro.chl, (size_t)chunk * a.o.chl_rows * 8, (size_t)a.o.chl_chunks * a.o.chl_rows * 8);
+  const float4 x0 = make_float4(v[0], v[1], v[2], v[3]), x1 = make_float4(v[4], v[5], v[6], v[7]);
+  if (ro.raw) {
+    float4* d = reinterpret_cast<float4*>(ro.raw + (size_t)chunk * a.o.raw_rows * 8);
+    d[0] = x0;
+    d[1] = x1;
+  }
+  if (ro.unw) {
+    float4* d = reinterpret_cast<float4*>(ro.unw + (size_t)chunk * a.o.frame_stride * 8);
+    d[0] = x0;
+    d[1] = x1;
   }
 }
 
@@ -638,7 +620,7 @@ __device__ __forceinline__ void contour_pair(const uint32_t (&v)[16], int dt, fl
 
 __device__ __forceinline__ void contour_tile(const TcArgs& a, const RowOut& ro, uint32_t taddr, int n_valid, bool live,
                                              int ft, bool first, bool last, int quad, int lane, int slot, float* xb,
-                                             float (&carry)[4]) {
+                                             float (&carry)[4], float (&hold)[6]) {
 #pragma unroll 1
   for (int c4 = 0; c4 < 4; ++c4) {
     uint32_t v[32];
@@ -657,7 +639,8 @@ __device__ __forceinline__ void contour_tile(const TcArgs& a, const RowOut& ro, 
   for (int j = 0; j < 20; ++j) S[j] = 0.f;
   float* pub = xb + quad * tc::kXchgFloats;
 #pragma unroll 1
-  for (int dt = 0; dt < 5; ++dt) {
+  for (int ta = 0; ta < 5; ++ta) {  // source row `ta` below the thread's: time tap dt = 4 - ta (see time_tap)
+    const int dt = 4 - ta;
     float2 acc[10];  // output offsets j = 0 .. 19 as pairs
 #pragma unroll
     for (int j = 0; j < 10; ++j) acc[j] = make_float2(0.f, 0.f);
@@ -676,41 +659,52 @@ __device__ __forceinline__ void contour_tile(const TcArgs& a, const RowOut& ro, 
     float P[20];
 #pragma unroll
     for (int j = 0; j < 10; ++j) P[2 * j] = acc[j].x, P[2 * j + 1] = acc[j].y;
-    time_tap<2, 20>(S, P, dt - 2, lane, pub);
+    time_tap<2, 20>(S, P, ta, lane, pub);
   }
   __syncwarp();
   slot_barrier(slot);
   time_edges<2, 20>(S, quad, lane, xb);
-  // frequency halo: S[j] <-> bin 16 ft - 2 + j; bins 16 ft - 2 .. 16 ft + 1 also get the top four sums of the tile below
+  // frequency halo: S[j] <-> bin 16 ft - 2 + j; bins 16 ft - 2 .. 16 ft + 1 also get the top four sums of the tile below.
+  // Finished bins leave in aligned 8-bin chunks: chunk 2 ft - 1 = the six bins held back from the previous tile + j = 0, 1;
+  // chunk 2 ft = j = 2 .. 9; j = 10 .. 15 are held for the next tile.  Where a range starts / ends, the four partial sums
+  // AND the six finished bins next to them go to the edge buffer (10 values per side); edge_fix_kernel assembles the two
+  // chunks around the boundary.
   const bool lower = ft > 0;
   if (first) {
     if (lower && ro.edge) {
-      float* e = ro.edge + (size_t)(ro.e_lo * 2 + 0) * 4 * a.edge_rows;
+      float* e = ro.edge + (size_t)(ro.e_lo * 2 + 0) * 10 * a.edge_rows;
 #pragma unroll
       for (int k = 0; k < 4; ++k) e[(size_t)k * a.edge_rows] = S[k];
+#pragma unroll
+      for (int k = 0; k < 6; ++k) e[(size_t)(4 + k) * a.edge_rows] = sigmoidf_fast(S[4 + k] + c_bias2[0]);  // bins 16 ft + 2 .. + 7
     }
   } else {
 #pragma unroll
     for (int k = 0; k < 4; ++k) S[k] += carry[k];
   }
-  if (ro.ok) {
-    const int jlo = first ? (lower ? 4 : 2) : 0;
-    float* dst = ro.raw + 16 * ft - 2;
+  float fin[16];
 #pragma unroll
-    for (int j = 0; j < 16; j += 2) {
-      if (j < jlo || 16 * ft - 2 + j >= kContourBins) continue;
-      float2 o;
-      o.x = sigmoidf_fast(S[j] + c_bias2[0]);
-      o.y = sigmoidf_fast(S[j + 1] + c_bias2[0]);
-      *reinterpret_cast<float2*>(dst + j) = o;
+  for (int j = 0; j < 16; ++j) fin[j] = sigmoidf_fast(S[j] + c_bias2[0]);
+  if (ro.ok) {
+    if (!first) {  // chunk 2 ft - 1: bins 16 ft - 8 .. 16 ft - 1
+      const float v[8] = {hold[0], hold[1], hold[2], hold[3], hold[4], hold[5], fin[0], fin[1]};
+      store_contour_chunk(a, ro, 2 * ft - 1, v);
+    }
+    if (!first || !lower) {  // chunk 2 ft: bins 16 ft .. 16 ft + 7 (at a range start above tile 0 the fix-up writes it)
+      const float v[8] = {fin[2], fin[3], fin[4], fin[5], fin[6], fin[7], fin[8], fin[9]};
+      store_contour_chunk(a, ro, 2 * ft, v);
     }
   }
 #pragma unroll
+  for (int k = 0; k < 6; ++k) hold[k] = fin[10 + k];
+#pragma unroll
   for (int k = 0; k < 4; ++k) carry[k] = S[16 + k];
   if (last && ft < a.n_ft - 1 && ro.edge && ro.e_hi >= 0) {
-    float* e = ro.edge + (size_t)(ro.e_hi * 2 + 1) * 4 * a.edge_rows;
+    float* e = ro.edge + (size_t)(ro.e_hi * 2 + 1) * 10 * a.edge_rows;
 #pragma unroll
     for (int k = 0; k < 4; ++k) e[(size_t)k * a.edge_rows] = S[16 + k];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) e[(size_t)(4 + k) * a.edge_rows] = fin[10 + k];  // bins 16 ft + 8 .. + 13
   }
 }
 
@@ -856,29 +850,38 @@ __global__ void __launch_bounds__(tc::kThreads, 1) conv_tc_kernel(const TcArgs a
     for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
       const int mt = it / a.n_split, sp = it % a.n_split;
       const int g0 = sp * a.n_groups / a.n_split, g1 = (sp + 1) * a.n_groups / a.n_split;
+      // conv1 row of this thread (it provides relu(conv1) of that frame to the fused conv2) ...
       const int m = mt * a.ms - a.h2 + row;  // row of the (window, frame) space: m = b * rows_per_window + t
-      const int b = m >= 0 ? m / a.rows_per_window : 0, t = m - b * a.rows_per_window;
-      const bool live = m >= 0 && (b < a.n_windows) && (t < kFrames);
+      const int b1 = m >= 0 ? m / a.rows_per_window : 0, t1 = m - b1 * a.rows_per_window;
+      const bool live = m >= 0 && (b1 < a.n_windows) && (t1 < kFrames);
+      // ... and the output frame it finishes: h2 rows earlier (all time taps of the fused conv2 then lie at or below the
+      // thread's own row, see time_tap); rows < 2 h2 of the tile are finished by the previous tile
+      const int q = m - a.h2;
+      const int b = q >= 0 ? q / a.rows_per_window : 0, t = q - b * a.rows_per_window;
       RowOut ro{};
       float carry[4] = {0.f, 0.f, 0.f, 0.f};
+      float hold[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
       if constexpr (EPI != 0) {
         ro.e_lo = slot * a.n_split + sp;
         ro.e_hi = (sp + 1 < a.n_split) ? slot * a.n_split + sp + 1 : (slot == 0 ? a.n_split : -1);
-        ro.ok = live && row >= a.h2 && row < kMTile - a.h2;
+        ro.ok = row >= 2 * a.h2 && q >= 0 && b < a.n_windows && t < kFrames;
+        ro.t = t;
         if (ro.ok) {
-          ro.edge = a.edge + (size_t)mt * a.ms + (row - a.h2);
-          if (a.out) ro.raw = a.out + ((size_t)b * kFrames + t) * a.wout;
-          if (a.ud) {
-            const UnwrapDesc u = a.ud[b];
+          ro.edge = a.o.edge + q;
+          int uf = -1;  // unwrapped frame (reference: inference.py:247-279), if this frame is kept
+          if (a.o.ud) {
+            const UnwrapDesc u = a.o.ud[b];
             const int tt = t - kOverlapHalf;
-            if ((unsigned)tt < (unsigned)max(u.rows, 0)) ro.unw = a.out_unw + (size_t)(u.dst_base + tt) * a.wout;
+            if ((unsigned)tt < (unsigned)max(u.rows, 0)) uf = (int)(u.dst_base + tt);
           }
-          if constexpr (EPI == 1) {
-#pragma unroll
-            for (int r = 0; r < 3; ++r)
-              ro.note_rows[r] = ((unsigned)(t + r - 1) < (unsigned)kFrames)
-                                    ? a.note_raw + ((size_t)b * kFrames + t + r - 1) * kPitches
-                                    : nullptr;
+          if constexpr (EPI == 3) {
+            ro.chl = a.o.chl + ((size_t)a.o.chl_lead + (size_t)b * a.o.chl_rpw + t) * 8;
+            if (a.o.raw) ro.raw = a.o.raw + ((size_t)b * kFrames + t) * 8;
+            if (uf >= 0) ro.unw = a.o.unwrapped + (size_t)uf * 8;
+          } else {
+            if (a.o.raw) ro.raw = a.o.raw + (size_t)b * kFrames + t;
+            if (uf >= 0) ro.unw = a.o.unwrapped + uf;
+            if constexpr (EPI == 1) ro.note_col = a.o.note_raw + (size_t)b * kFrames + t;
           }
         }
       }
@@ -896,7 +899,7 @@ __global__ void __launch_bounds__(tc::kThreads, 1) conv_tc_kernel(const TcArgs a
           if constexpr (EPI == 0) {
             // contour: 16 bins x 8 channels, bias + ReLU, channels-last rows of 128 contiguous floats
             const int n_valid = min(a.flt, a.wout - ft * a.flt) * a.cout;
-            float* dst = a.out + ((size_t)b * kFrames + t) * ((size_t)a.wout * a.cout) + (size_t)ft * 128;
+            float* dst = a.o.act + ((size_t)b * kFrames + t) * ((size_t)a.wout * a.cout) + (size_t)ft * 128;
 #pragma unroll 1
             for (int c4 = 0; c4 < 4; ++c4) {
               uint32_t v[32];
@@ -917,7 +920,7 @@ __global__ void __launch_bounds__(tc::kThreads, 1) conv_tc_kernel(const TcArgs a
           } else if constexpr (EPI == 3) {
             const int n_valid = min(a.flt, a.wout - ft * a.flt) * a.cout;
             float* xb = s_x + (slot * 2 + xbuf) * 4 * kXchgFloats;
-            contour_tile(a, ro, taddr, n_valid, live, ft, first, last, quad, lane, slot, xb, carry);
+            contour_tile(a, ro, taddr, n_valid, live, ft, first, last, quad, lane, slot, xb, carry, hold);
             xbuf ^= 1u;
           } else {
             // onset / note: the tile is 4 bins x 32 channels; the whole next conv (32 -> 1, KH2 x 3) follows
@@ -955,55 +958,87 @@ __global__ void __launch_bounds__(tc::kThreads, 1) conv_tc_kernel(const TcArgs a
 }
 
 // ------------------------------------------------------------------------------------------------
-// Where two tile ranges meet (frequency tile ft_b = first tile of a range, ft_b > 0) the KE = 2 * HALO bins
-// SF2... FLT * ft_b - HALO + k (k < KE) got one partial sum from each side: finish them here.
+// Where two tile ranges meet (frequency tile ft_b = first tile of a range, ft_b > 0) the 2 * HALO bins
+// FLT * ft_b - HALO + k got one partial sum from each side: finish them here.  Pitch layers: 2 bins per frame.  Contour:
+// 4 bins, and with the six finished bins each side left next to them the two 8-bin chunks around the boundary.
 // ------------------------------------------------------------------------------------------------
 struct EdgeFixArgs {
-  const float* edge;
+  TcOut o;
   int edge_rows, n_rows;        // rows of the (window, frame) space covered by the M-tiles
   int n_edges;                  // 2 * n_split slots: slot e = s * n_split + q starts at tile q * n_groups / n_split + s * G0
   int n_split, n_groups, g0, n_ft;
-  int layer, flt, halo, wout, rows_per_window, n_windows;
-  float* raw;
-  float* unw;
-  const UnwrapDesc* ud;
-  const float* note_raw;
+  int layer, wout, rows_per_window, n_windows;
 };
 
 __global__ void edge_fix_kernel(const EdgeFixArgs a) {
-  const int ke = 2 * a.halo;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long total = (long long)a.n_rows * a.n_edges * ke;
+  const int per_edge = a.layer == 0 ? 1 : 2;  // contour: one thread per (frame, edge); pitch layers: per (frame, edge, bin)
+  const long long total = (long long)a.n_rows * a.n_edges * per_edge;
   if (idx >= total) return;
-  const int R = (int)(idx % a.n_rows);  // rows fastest: coalesced reads of the edge buffer
+  const int R = (int)(idx % a.n_rows);  // rows fastest: coalesced reads of the edge buffer, coalesced stores
   const int ek = (int)(idx / a.n_rows);
-  const int e = ek / ke, k = ek - e * ke;
+  const int e = ek / per_edge, k = ek - e * per_edge;
   const int b = R / a.rows_per_window, t = R - b * a.rows_per_window;
   if (b >= a.n_windows || t >= kFrames) return;
   const int es = e / a.n_split, eq = e - es * a.n_split;
   const int ft_b = eq * a.n_groups / a.n_split + es * a.g0;
   if (ft_b <= 0 || ft_b >= a.n_ft) return;  // not a boundary between two ranges
-  const int f = a.flt * ft_b - a.halo + k;
+  int uf = -1;
+  if (a.o.ud) {
+    const UnwrapDesc u = a.o.ud[b];
+    const int tt = t - kOverlapHalf;
+    if ((unsigned)tt < (unsigned)max(u.rows, 0)) uf = (int)(u.dst_base + tt);
+  }
+  if (a.layer == 0) {
+    const float* lo = a.o.edge + (size_t)(e * 2 + 0) * 10 * a.edge_rows + R;  // from the range that starts at ft_b
+    const float* hi = a.o.edge + (size_t)(e * 2 + 1) * 10 * a.edge_rows + R;  // from the range that ends at ft_b - 1
+    float fx[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q)  // (S + carry) + bias, the order of the in-kernel carry
+      fx[q] = sigmoidf_fast((lo[(size_t)q * a.edge_rows] + hi[(size_t)q * a.edge_rows]) + c_bias2[0]);
+    float va[8], vb[8];
+#pragma unroll
+    for (int q = 0; q < 6; ++q) {
+      va[q] = hi[(size_t)(4 + q) * a.edge_rows];      // bins 16 ft_b - 8 .. - 3
+      vb[2 + q] = lo[(size_t)(4 + q) * a.edge_rows];  // bins 16 ft_b + 2 .. + 7
+    }
+    va[6] = fx[0], va[7] = fx[1], vb[0] = fx[2], vb[1] = fx[3];
+    __nv_bfloat16* chl = a.o.chl + ((size_t)a.o.chl_lead + (size_t)b * a.o.chl_rpw + t) * 8;
+    const size_t plane = (size_t)a.o.chl_chunks * a.o.chl_rows * 8;
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      const int chunk = 2 * ft_b - 1 + c;
+      const float(&v)[8] = c ? vb : va;
+      store_split8(v, chl, (size_t)chunk * a.o.chl_rows * 8, plane);
+      const float4 x0 = make_float4(v[0], v[1], v[2], v[3]), x1 = make_float4(v[4], v[5], v[6], v[7]);
+      if (a.o.raw) {
+        float4* d = reinterpret_cast<float4*>(a.o.raw + ((size_t)chunk * a.o.raw_rows + (size_t)b * kFrames + t) * 8);
+        d[0] = x0, d[1] = x1;
+      }
+      if (uf >= 0) {
+        float4* d = reinterpret_cast<float4*>(a.o.unwrapped + ((size_t)chunk * a.o.frame_stride + uf) * 8);
+        d[0] = x0, d[1] = x1;
+      }
+    }
+    return;
+  }
+  const int f = 4 * ft_b - 1 + k;
   if (f < 0 || f >= a.wout) return;
-  float x = c_bias2[a.layer] + a.edge[((size_t)(e * 2 + 0) * ke + k) * a.edge_rows + R] +
-            a.edge[((size_t)(e * 2 + 1) * ke + k) * a.edge_rows + R];
-  if (a.note_raw) {
+  float x = (a.o.edge[((size_t)(e * 2 + 0) * 2 + k) * a.edge_rows + R] +
+             a.o.edge[((size_t)(e * 2 + 1) * 2 + k) * a.edge_rows + R]) + c_bias2[a.layer];  // (S + carry) + bias
+  if (a.o.note_raw) {
 #pragma unroll
     for (int dt = 0; dt < 3; ++dt)
 #pragma unroll
       for (int df = 0; df < 3; ++df) {
         const int tt = t + dt - 1, ff = f + df - 1;
         if ((unsigned)tt < (unsigned)kFrames && (unsigned)ff < (unsigned)kPitches)
-          x = fmaf(__ldg(a.note_raw + ((size_t)b * kFrames + tt) * kPitches + ff), c_onset_note_w[dt * 3 + df], x);
+          x = fmaf(__ldg(a.o.note_raw + (size_t)ff * a.o.raw_rows + (size_t)b * kFrames + tt), c_onset_note_w[dt * 3 + df], x);
       }
   }
   const float v = sigmoidf_fast(x);
-  if (a.raw) a.raw[((size_t)b * kFrames + t) * a.wout + f] = v;
-  if (a.ud) {
-    const UnwrapDesc u = a.ud[b];
-    const int tt = t - kOverlapHalf;
-    if ((unsigned)tt < (unsigned)max(u.rows, 0)) a.unw[(size_t)(u.dst_base + tt) * a.wout + f] = v;
-  }
+  if (a.o.raw) a.o.raw[(size_t)f * a.o.raw_rows + (size_t)b * kFrames + t] = v;
+  if (uf >= 0) a.o.unwrapped[(size_t)f * a.o.frame_stride + uf] = v;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1019,26 +1054,19 @@ void tc_setup() {
   cudaFuncSetAttribute(conv_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes);
 }
 
-void launch_lognorm_split(float* y, const unsigned int* minmax, const float* bn, __nv_bfloat16* dst, const TcConvSpec& sp,
-                          int n_windows, int rows_stride, cudaStream_t st) {
+void launch_lognorm_split(const float* y, const unsigned int* minmax, const float* bn, __nv_bfloat16* dst,
+                          const TcConvSpec& sp, int n_windows, int rows_stride, cudaStream_t st) {
   const int rows_used = tc_rows_total(n_windows, sp.rows_per_window);  // <= rows_stride
   const long long cells = (long long)rows_used * sp.chunks8;
   lognorm_split_kernel<<<(unsigned)((cells + 255) / 256), 256, 0, st>>>(y, minmax, bn, dst, n_windows, rows_used, rows_stride,
                                                                        sp.chunks8, sp.rows_per_window, sp.lead_rows);
 }
 
-void launch_contour_split(const float* raw_contour, __nv_bfloat16* chl, int n_windows, int rows_stride, cudaStream_t st,
-                          const UnwrapDesc* ud, float* unwrapped) {
-  const TcConvSpec sp = tc_note_spec();
-  const long long cells = (long long)n_windows * kFrames * (kContourBins / 8);
-  contour_split_kernel<<<(unsigned)((cells + 255) / 256), 256, 0, st>>>(raw_contour, chl, n_windows, rows_stride, sp.chunks8,
-                                                                       sp.rows_per_window, sp.lead_rows, ud, unwrapped);
-}
-
 size_t tc_edge_floats(const TcConvSpec& sp, int n_windows) {
   const int ms = tc::kMTile - (sp.KH2 - 1);
   const int n_mtiles = (n_windows * sp.rows_per_window + ms - 1) / ms;
-  return (size_t)2 * sp.G0 * 2 * (2 * sp.HALO) * ((size_t)n_mtiles * ms);  // at most 2 * G0 range starts
+  const int per_side = sp.epi == 0 ? 10 : 2;
+  return (size_t)2 * sp.G0 * 2 * per_side * ((size_t)n_mtiles * ms);  // at most 2 * G0 range starts
 }
 
 void launch_conv_tc(const __nv_bfloat16* data, const TcConvDev& dev, const TcOut& o, int n_windows, int rows_stride,
@@ -1048,11 +1076,7 @@ void launch_conv_tc(const __nv_bfloat16* data, const TcConvDev& dev, const TcOut
   TcArgs a{};
   a.data = data;
   a.tiles = dev.tiles;
-  a.out = o.raw;
-  a.out_unw = o.unwrapped;
-  a.ud = o.ud;
-  a.note_raw = o.note_raw;
-  a.edge = o.edge;
+  a.o = o;
   a.layer = dev.layer;
   a.rows_total = rows_stride;  // row stride of the split layout (fixed per model, independent of the batch)
   a.h2 = fused ? (sp.KH2 - 1) / 2 : 0;
@@ -1081,12 +1105,6 @@ void launch_conv_tc(const __nv_bfloat16* data, const TcConvDev& dev, const TcOut
   a.wout = sp.WOUT;
   a.n_ft = (sp.WOUT + sp.FLT - 1) / sp.FLT;
   a.g0 = sp.G0;
-  EdgeFixArgs ef{};
-  ef.n_edges = fused ? 2 * split : 0;  // slot s of split q covers tiles [g0(q) + s*G0, g1(q) + s*G0): edge slot s*split + q
-  ef.n_split = split;
-  ef.n_groups = dev.n_groups;
-  ef.g0 = sp.G0;
-  ef.n_ft = a.n_ft;
   const int n_items = a.n_mtiles * a.n_split;
   const int grid = n_items < n_sms ? n_items : n_sms;
   if (sp.epi == 0 && fuse_next)
@@ -1097,21 +1115,21 @@ void launch_conv_tc(const __nv_bfloat16* data, const TcConvDev& dev, const TcOut
     conv_tc_kernel<1><<<grid, tc::kThreads, tc::kSmemBytes, st>>>(a);
   else
     conv_tc_kernel<2><<<grid, tc::kThreads, tc::kSmemBytes, st>>>(a);
-  if (fused && ef.n_edges > 0) {
-    ef.edge = o.edge;
+  if (fused) {  // slot s of split q covers tiles [g0(q) + s*G0, g1(q) + s*G0): edge slot s*split + q
+    EdgeFixArgs ef{};
+    ef.o = o;
     ef.edge_rows = a.edge_rows;
     ef.n_rows = n_windows * sp.rows_per_window;
-    ef.layer = sp.epi == 0 ? 0 : sp.epi;  // c_bias2 index: 0 contour, 1 onset, 2 note
-    ef.flt = sp.FLT;
-    ef.halo = sp.HALO;
+    ef.n_edges = 2 * split;
+    ef.n_split = split;
+    ef.n_groups = dev.n_groups;
+    ef.g0 = sp.G0;
+    ef.n_ft = a.n_ft;
+    ef.layer = sp.epi;  // c_bias2 index: 0 contour, 1 onset, 2 note
     ef.wout = sp.WOUT;
     ef.rows_per_window = sp.rows_per_window;
     ef.n_windows = n_windows;
-    ef.raw = o.raw;
-    ef.unw = o.unwrapped;
-    ef.ud = o.ud;
-    ef.note_raw = o.note_raw;
-    const long long total = (long long)ef.n_rows * ef.n_edges * 2 * sp.HALO;
+    const long long total = (long long)ef.n_rows * ef.n_edges * (sp.epi == 0 ? 1 : 2);
     edge_fix_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(ef);
   }
 }

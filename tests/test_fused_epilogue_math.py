@@ -4,9 +4,9 @@ restated in NumPy with the SAME structure and compared with the direct convoluti
 
   * per frequency tile of FLT bins the thread of a frame reduces relu(conv1) over channels and frequency taps into
     P[dt][j], j = 0 .. FLT + 2*HALO - 1 (output bin FLT*ft - HALO + j),
-  * time taps: output row r takes P[dt] of row r + dt - H — from lane + delta inside the warp (32 consecutive rows), from
-    the published edge lanes of the neighbouring warp otherwise; M-tiles advance by 128 - 2H rows, rows H .. 127-H of a
-    tile are complete,
+  * time taps: the thread of tile row r finishes output row r - H, which takes P[dt] of row r - (2H - dt): always a row
+    at or below its own — from a lower lane inside the warp (32 consecutive rows), from the published top lanes of the
+    previous warp otherwise; M-tiles advance by 128 - 2H rows, rows 2H .. 127 of a tile finish an output row,
   * frequency halo: a slot walks its tile range in ascending order carrying the top 2*HALO sums; where two ranges meet
     (slot 0 | slot 1, group splits) both sides go to the edge buffer and the fix-up adds them.
 
@@ -45,34 +45,30 @@ def _thread_partials(x, w2, KH2, KW, FLT, HALO, W):
 
 
 def _time_sum_tile(Ptile, H):
-    """Ptile [KH2][J][128] (rows of one M-tile) -> S [J][128] exactly like time_tap + time_edges: 4 warps of 32 lanes."""
+    """Ptile [KH2][J][128] (conv1 rows of one M-tile) -> S [J][128] exactly like time_tap + time_edges: 4 warps of 32
+    lanes; the thread of tile row r finishes output row r - H, so tap dt comes from `a = 2H - dt` rows below it."""
     KH2, J, _ = Ptile.shape
     S = np.zeros((J, 128))
-    HH = H * (H + 1) // 2
-    pub = np.full((4, 2 * HH, J), np.nan)  # published entries per warp
+    n_pub = H * (2 * H + 1)
+    pub = np.full((4, n_pub, J), np.nan)  # published entries per warp
     for quad in range(4):
         for lane in range(32):
             row = quad * 32 + lane
-            for dt in range(KH2):
-                delta = dt - H
-                if delta == 0:
+            for a in range(2 * H + 1):
+                dt = 2 * H - a
+                if a == 0:
                     S[:, row] += Ptile[dt, :, row]
                     continue
-                src = lane + delta
-                if 0 <= src < 32:
-                    S[:, row] += Ptile[dt, :, quad * 32 + src]
-                a = abs(delta)
-                idx = lane if delta > 0 else lane - (32 - a)
-                if 0 <= idx < a:
-                    pub[quad, (0 if delta > 0 else HH) + a * (a - 1) // 2 + idx] = Ptile[dt, :, row]
-    for quad in range(4):
+                if lane >= a:
+                    S[:, row] += Ptile[dt, :, row - a]
+                if lane >= 32 - a:
+                    pub[quad, a * (a - 1) // 2 + lane - (32 - a)] = Ptile[dt, :, row]
+    for quad in range(1, 4):
         for lane in range(32):
             row = quad * 32 + lane
-            for a in range(1, H + 1):
-                if quad < 3 and lane >= 32 - a:
-                    S[:, row] += pub[quad + 1, a * (a - 1) // 2 + lane + a - 32]
-                if quad > 0 and lane < a:
-                    S[:, row] += pub[quad - 1, HH + a * (a - 1) // 2 + lane]
+            for a in range(1, 2 * H + 1):
+                if lane < a:
+                    S[:, row] += pub[quad - 1, a * (a - 1) // 2 + lane]
     return S
 
 
@@ -113,11 +109,11 @@ def _fused_layer(x_rows, w2, bias, KH2, KW, FLT, HALO, W, rpw, G0, n_windows, n_
                     S = _time_sum_tile(P[ft][:, :, m0 + pad : m0 + pad + 128], H)
                     lower = ft > 0
                     rows_ok = []
-                    for row in range(H, 128 - H):
-                        m = m0 + row
+                    for row in range(2 * H, 128):
+                        m = m0 + row - H  # output row of this thread
                         b, t = divmod(m, rpw) if m >= 0 else (0, -1)
                         if m >= 0 and b < n_windows and t < T:
-                            rows_ok.append((row, b, t, mt * MS + row - H))
+                            rows_ok.append((row, b, t, m))
                     if first:
                         if lower:
                             for row, b, t, R in rows_ok:
