@@ -23,7 +23,7 @@ EXPORTS = [
     "bp_model_create", "bp_model_destroy", "bp_model_device", "bp_model_param_block", "bp_model_refresh",
     "bp_model_launch_count", "bp_forward_device", "bp_forward_host", "bp_run_inference_device",
     "bp_run_inference_host", "bp_decode_device", "bp_decode_host", "bp_transcribe_host", "bp_transcribe_device",
-    "bp_infer_onsets_host", "bp_pitch_bends_host", "bp_debug_activation", "bp_model_chunk_windows", "bp_model_set_path", "bp_model_profile", "bp_model_profile_read", "bp_debug_tc_plan",
+    "bp_infer_onsets_host", "bp_pitch_bends_host", "bp_debug_activation", "bp_model_chunk_windows", "bp_model_set_path", "bp_model_profile", "bp_model_profile_read", "bp_debug_tc_plan", "bp_debug_tc_b2",
 ]  # fmt: skip
 
 
@@ -108,6 +108,7 @@ def load() -> C.CDLL:
     lib.bp_pitch_bends_host.argtypes = [vp, vp, i64, i32, vp, vp, vp, vp, vp, i64]
     lib.bp_debug_activation.argtypes = [vp, C.c_int, vp, i64]
     lib.bp_debug_tc_plan.argtypes = [C.c_int, vp, vp, vp, vp, vp, vp, vp]
+    lib.bp_debug_tc_b2.argtypes = [C.c_int, vp, vp, vp]
     lib.bp_model_profile.argtypes = [vp, C.c_int]
     lib.bp_model_profile_read.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(i64), C.POINTER(i64)]
     for name in EXPORTS:

@@ -137,7 +137,7 @@ struct bp_model {
   struct TcLayer {
     TcConvPlan plan;
     TcConvDev dev{};
-    DevBuf<uint16_t> tiles;
+    DevBuf<uint16_t> tiles, b2;
   } tc_contour, tc_onset, tc_note;
   DevBuf<__nv_bfloat16> yhl, chl;
   std::vector<float> h_params;  // host copy of the parameter block (weight-dependent __constant__ data is re-uploaded
@@ -267,8 +267,7 @@ int upload_constants(bp_model* m, cudaStream_t st) {
     CK(cudaDeviceSynchronize());  // kernels of the previous owner may still be reading the bank
   upload_lowpass(hp + ParamLayout::lowpass, st);
   tc_upload_epilogue(hp + ParamLayout::contour1_b, hp + ParamLayout::onset1_b, hp + ParamLayout::note1_b,
-                     hp + ParamLayout::onset2_w, hp + ParamLayout::note2_w, hp + ParamLayout::contour2_w,
-                     hp + ParamLayout::contour2_b, hp + ParamLayout::onset2_b, hp + ParamLayout::note2_b, st);
+                     hp + ParamLayout::onset2_w, hp + ParamLayout::contour2_b, hp + ParamLayout::onset2_b, hp + ParamLayout::note2_b, st);
   CKL();
   if (m->device >= 0 && m->device < 64) g_const_owner[m->device] = m;
   return BP_OK;
@@ -287,6 +286,8 @@ int derive(bp_model* m, cudaStream_t st) {
   bp_model::TcLayer* layers[3] = {&m->tc_contour, &m->tc_onset, &m->tc_note};
   const float* wsrc[3] = {hp.data() + ParamLayout::contour1_w, hp.data() + ParamLayout::onset1_w,
                           hp.data() + ParamLayout::note1_w};
+  const float* w2src[3] = {hp.data() + ParamLayout::contour2_w, hp.data() + ParamLayout::onset2_w,
+                           hp.data() + ParamLayout::note2_w};
   for (int l = 0; l < 3; ++l) {
     bp_model::TcLayer& L = *layers[l];
     L.plan.build(specs[l], wsrc[l]);
@@ -296,7 +297,12 @@ int derive(bp_model* m, cudaStream_t st) {
     CK(L.tiles.reserve(pl.tiles.size()));
     CK(cudaMemcpyAsync(L.tiles.p, pl.tiles.data(), pl.tiles.size() * 2, cudaMemcpyHostToDevice, st));
     CK(cudaStreamSynchronize(st));
-    L.dev = TcConvDev{pl.spec, L.tiles.p, pl.n_groups, l};
+    std::vector<uint16_t> b2;
+    tc_build_b2(l, w2src[l], b2);
+    CK(L.b2.reserve(b2.size()));
+    CK(cudaMemcpyAsync(L.b2.p, b2.data(), b2.size() * 2, cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));
+    L.dev = TcConvDev{pl.spec, L.tiles.p, L.b2.p, pl.n_groups, l};
   }
   {
     std::vector<uint16_t> wtc;
@@ -594,7 +600,10 @@ static int model_init(bp_model* m, const std::vector<float>& params, const cudaD
                      P + ParamLayout::onset1_b,      D + DerivedLayout::onset2_wT, P + ParamLayout::onset2_b};
   hcqt_setup();
   cnn_setup();
-  tc_setup();
+  if (tc_setup() != 0) {
+    cudaGetLastError();
+    return fail(BP_E_CUDA, "tensor-core conv kernels: shared-memory opt-in failed");
+  }
   cqt_tc_setup();
   m->n_sms = prop.multiProcessorCount;
   // largest chunk whose M-tiles make at most two per SM in every layer.  M-tiles advance by 128 - (KH2 - 1) rows (they
@@ -631,7 +640,7 @@ void bp_model_destroy(bp_model_t* m) {
   m->yhl.release();
   m->chl.release();
   m->cqt_wtc.release();
-  for (bp_model::TcLayer* L : {&m->tc_contour, &m->tc_onset, &m->tc_note}) L->tiles.release();
+  for (bp_model::TcLayer* L : {&m->tc_contour, &m->tc_onset, &m->tc_note}) L->tiles.release(), L->b2.release();
   if (m->d_params) cudaFree(m->d_params);
   if (m->d_derived) cudaFree(m->d_derived);
   if (m->d_gauss) cudaFree(m->d_gauss);
@@ -1221,6 +1230,20 @@ int bp_debug_tc_plan(int which, const float* w, int32_t* sizes, uint16_t* tiles,
   }
   if (group_step_off) std::memcpy(group_step_off, pl.group_step_off.data(), pl.group_step_off.size() * 4);
   if (group_ft) std::memcpy(group_ft, pl.group_ft.data(), pl.group_ft.size() * 4);
+  return BP_OK;
+}
+
+int bp_debug_tc_b2(int which, const float* w2, int32_t* sizes, uint16_t* tiles) {
+  if (!w2 || !sizes || which < 0 || which > 2) return fail(BP_E_INVALID, "bp_debug_tc_b2: bad argument");
+  std::vector<uint16_t> t;
+  tc_build_b2(which, w2, t);
+  const int n2 = which == 1 ? 16 : 32;
+  sizes[0] = (int32_t)(t.size() / (2 * 16 * n2));
+  sizes[1] = n2;
+  sizes[2] = which == 0 ? 5 : which == 1 ? 3 : 7;
+  sizes[3] = which == 0 ? 104 : which == 1 ? 32 : 64;
+  sizes[4] = which == 0 ? 5 : which == 1 ? 4 : 8;
+  if (tiles) std::memcpy(tiles, t.data(), t.size() * 2);
   return BP_OK;
 }
 

@@ -64,16 +64,18 @@ struct TcConvPlan {  // host side: weight tiles + the per-group MMA programs
 struct TcConvDev {
   TcConvSpec spec;
   const uint16_t* tiles;
+  const uint16_t* b2;  // conv2 weight tiles of the fused epilogue (tc_build_b2)
   int n_groups;
   int layer;  // index of the program in constant memory (0 contour, 1 onset, 2 note)
 };
 int tc_upload_program(int layer, const TcConvPlan& plan, cudaStream_t st);  // 0 on success
 void tc_upload_epilogue(const float* contour1_b, const float* onset1_b, const float* note1_b, const float* onset2_w,
-                        const float* note2_w, const float* contour2_w, const float* contour2_b, const float* onset2_b,
-                        const float* note2_b, cudaStream_t st);
+                        const float* contour2_b, const float* onset2_b, const float* note2_b, cudaStream_t st);
+// bf16 hi/lo weight tiles of the fused second conv (epi: 0 contour, 1 onset, 2 note; w2 = that conv's weights), see TcB2
+void tc_build_b2(int epi, const float* w2, std::vector<uint16_t>& out);
 int tc_rows_total(int n_windows, int rows_per_window);
 size_t tc_edge_floats(const TcConvSpec& spec, int n_windows);  // size of the edge buffer of a fused layer
-void tc_setup();
+int tc_setup();  // 0 on success
 // Where window w's centre frames go in the unwrapped (per-file) posteriorgrams (reference: inference.py:247-279).
 struct UnwrapDesc {
   long long dst_base;  // first output frame this window contributes to

@@ -3,6 +3,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
 
 namespace bp {
 
@@ -33,6 +34,35 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "}\n" ::"r"(smem_u32(bar)),
       "r"(parity)
       : "memory");
+}
+// mbar_wait with a watchdog: after ~2 s of spinning it reports who waits on what and traps, so that a protocol error
+// shows up as a launch failure with a message instead of a hung GPU.  `tag` identifies the wait site.
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+static __device__ __noinline__ void mbar_deadlock(int tag, uint32_t parity) {
+  if ((threadIdx.x & 31) == 0)
+    printf("libbp_b200: mbarrier wait timed out: block %d warp %d site %d parity %u\n", (int)blockIdx.x, (int)(threadIdx.x >> 5),
+           tag, parity);
+  __trap();
+}
+__device__ __forceinline__ void mbar_wait_wd(uint64_t* bar, uint32_t parity, int tag) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if ((++spins & 0x3ffu) == 0 && clock64() - t0 > 4000000000ll) mbar_deadlock(tag, parity);
+  }
 }
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
@@ -158,6 +188,61 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32
         "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]),
         "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
       : "memory");
+}
+
+// ---- A operand in tensor memory (tcgen05.mma "TS" form) -------------------------------------------------------------
+// kind::f16, M = 128: row = TMEM lane, two 16-bit elements per 32-bit column (element 2c in the low half), so a K = 16 step
+// reads 8 columns starting at the given column (measured with tools/ubench/umma_ts.cu, which also shows that the D
+// operand of a small-N MMA may start at ANY column).  The three split-precision products, all accumulating:
+//   D += Ahi*Bhi ; D += Ahi*Blo ; D += Alo*Bhi        (issued by the elected lane only)
+__device__ __forceinline__ void umma_ts_bf16_x3(uint32_t tmem_d, uint32_t tmem_a_hi, uint32_t tmem_a_lo, uint32_t b_hi_lo32,
+                                                uint32_t b_lo_lo32, uint32_t desc_hi32, uint32_t idesc, uint32_t leader) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred q, t;\n\t"
+      ".reg .b64 dbh, dbl;\n\t"
+      "setp.ne.b32 q, %7, 0;\n\t"
+      "setp.eq.b32 t, 0, 0;\n\t"
+      "mov.b64 dbh, {%3, %5};\n\t"
+      "mov.b64 dbl, {%4, %5};\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], dbh, %6, t;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], dbl, %6, t;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%2], dbh, %6, t;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "r"(tmem_a_hi), "r"(tmem_a_lo), "r"(b_hi_lo32), "r"(b_lo_lo32), "r"(desc_hi32), "r"(idesc), "r"(leader)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld2_nowait(uint32_t taddr, uint32_t (&v)[2]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(v[0]), "=r"(v[1]) : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      :
+      : "r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
+        "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
+// zero `N` consecutive columns of the calling warp's 32 lanes (N = 8, 16 or 32)
+template <int N>
+__device__ __forceinline__ void tmem_zero(uint32_t taddr) {
+  static_assert(N == 8 || N == 16 || N == 32, "tmem_zero");
+  const uint32_t z = 0u;
+  if constexpr (N == 8) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1};" ::"r"(taddr), "r"(z) : "memory");
+  } else if constexpr (N == 16) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};" ::"r"(taddr),
+        "r"(z)
+        : "memory");
+  } else {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, "
+        "%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};" ::"r"(taddr),
+        "r"(z)
+        : "memory");
+  }
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 

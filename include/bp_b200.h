@@ -182,6 +182,12 @@ int bp_model_set_path(bp_model_t* m, int path);
 int bp_debug_tc_plan(int which, const float* w, int32_t* sizes, uint16_t* tiles, int32_t* tile_seq, uint32_t* slot_words,
                      int32_t* group_step_off, int32_t* group_ft);
 
+/* Host-only: the bf16 hi/lo weight tiles of the fused SECOND convolution of a tensor-core layer (csrc/tc_conv.cu, TcB2):
+ * which = 0 contour conv2 (w2 = [1][8][5][5], reference models.py:254-262), 1 onset conv2 ([1][33][3][3], models.py:305-313),
+ * 2 note conv2 ([1][32][7][3], models.py:282-290).  sizes[5] = {n_tiles, N, time taps, accumulator columns, columns per output offset}; tiles
+ * (may be NULL to query sizes): n_tiles x [plane hi/lo][k-chunk 2][n N][8] bf16. */
+int bp_debug_tc_b2(int which, const float* w2, int32_t* sizes, uint16_t* tiles);
+
 /* Per-kernel device timing for the roofline line of bench.py: records CUDA events on the launching
  * stream around every launch of one kernel family (0 = contour conv 3x39, 1 = onset conv 5x5,
  * 2 = CQT projection + log-normalise, 3 = decimation chain, 4 = the remaining small convs,

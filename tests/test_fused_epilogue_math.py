@@ -180,19 +180,59 @@ def test_fused_second_conv_structure(weights_np, name, n_split):
     assert np.abs(got - ref).max() < 1e-12
 
 
-def test_packed_tap_pairs_of_the_contour_epilogue(weights_np):
-    """The contour epilogue pairs output offsets for the packed FMAs: an input bin at even offset bl feeds the pairs
-    (bl,bl+1), (bl+2,bl+3), (bl+4,bl+5) with (w4,w3), (w2,w1), (w0,0); at odd bl the pairs (bl-1,bl), (bl+1,bl+2), (bl+3,bl+4)
-    with (0,w4), (w3,w2), (w1,w0)  [output offset j = bl + 4 - df] — same sums as the plain five taps."""
-    w = weights_np["contour2_w"].astype(np.float64)[0, 3, 2]  # one (channel, dt) row of 5 frequency taps
-    for bl in range(16):
-        plain = np.zeros(22)
-        for df in range(5):
-            plain[bl + 4 - df] += w[df]
-        packed = np.zeros(22)
-        j2 = bl >> 1
-        pairs = [(w[4], w[3]), (w[2], w[1]), (w[0], 0.0)] if bl % 2 == 0 else [(0.0, w[4]), (w[3], w[2]), (w[1], w[0])]
-        for k, (a, b) in enumerate(pairs):
-            packed[2 * (j2 + k)] += a
-            packed[2 * (j2 + k) + 1] += b
-        np.testing.assert_array_equal(plain, packed)
+def _b2_tiles(which, w2):
+    from basic_pitch_b200 import _lib
+
+    lib = _lib.load()
+    sizes = np.zeros(5, np.int32)
+    wc = np.ascontiguousarray(w2, np.float32)
+    lib.bp_debug_tc_b2(which, wc.ctypes.data, sizes.ctypes.data, None)
+    n_tiles, n2, kh2, width, js = (int(v) for v in sizes)
+    tiles = np.zeros((n_tiles, 2, 2, n2, 8), np.uint16)
+    lib.bp_debug_tc_b2(which, wc.ctypes.data, sizes.ctypes.data, tiles.ctypes.data)
+    f = (tiles.astype(np.uint32) << 16).view(np.float32).astype(np.float64)
+    full = (f[:, 0] + f[:, 1]).transpose(0, 1, 3, 2).reshape(n_tiles, 16, n2)  # [tile][k][n], hi + lo
+    return full, n2, kh2, width, js
+
+
+@pytest.mark.parametrize("name,which", [("contour2", 0), ("onset2", 1), ("note2", 2)])
+def test_conv2_mma_windows_reproduce_thread_partials(weights_np, name, which):
+    """The fused conv2 as a second tensor-core contraction (tc_conv.cu, TcB2 / tc_build_b2): the A operand is the row of
+    relu(conv1) in accumulator order k = fl * COUT + c; K step ks multiplies elements 16 ks .. 16 ks + 15 by ONE small
+    weight tile and accumulates into a window of conv2-accumulator columns (column j * JS + dt) that starts at
+    10 ks (contour) / JS * (ks // 2) (onset, note; JS = 4 / 8).  Emulated here with the tiles the library builds (hi + lo planes
+    summed) and compared with the per-thread partial sums P[dt][j] the epilogue needs (_thread_partials)."""
+    key, C, KH2, KW, FLT, HALO, W, rpw, G0 = CASES[name]
+    w2_full = weights_np[key].astype(np.float64)  # [1][C (+1)][KH2][KW]
+    w2 = w2_full[0, 1:] if name == "onset2" else w2_full[0]
+    tiles, n2, kh2, width, js = _b2_tiles(which, weights_np[key])
+    assert kh2 == KH2
+    rng = np.random.default_rng(which)
+    R = 7
+    x = np.abs(rng.standard_normal((C, R, W)))
+    P = _thread_partials(x, w2, KH2, KW, FLT, HALO, W)  # [ft][dt][j][row]
+    n_ft = (W + FLT - 1) // FLT
+    J = FLT + 2 * HALO
+    # the library rounds the weights to bf16 hi + lo (~2^-17 relative): compare against partial sums of the same weights
+    worst = 0.0
+    for ft in range(n_ft):
+        a2 = np.zeros((R, 128))
+        for fl in range(FLT):
+            g = FLT * ft + fl
+            if g < W:
+                a2[:, fl * C : (fl + 1) * C] = x[:, :, g].T
+        d2 = np.zeros((R, width + 32))
+        for ks in range(8):
+            if which == 0:
+                col, tile = 10 * ks, 0
+            else:
+                col, tile = js * (ks // 2), ks % 2
+            assert col % 2 == 0  # the D start column of an MMA must be even
+            d2[:, col : col + n2] += a2[:, 16 * ks : 16 * ks + 16] @ tiles[tile]
+        assert np.all(d2[:, width:] == 0), "a window writes past the accumulator"
+        got = d2[:, : J * js].reshape(R, J, js)
+        assert np.all(got[:, :, KH2:] == 0)
+        got = got[:, :, :KH2]
+        ref = P[ft].transpose(2, 1, 0)  # [row][j][dt]
+        worst = max(worst, float(np.abs(got - ref).max()))
+    assert worst < 2e-4 * float(np.abs(P).max()), worst  # bf16 hi + lo weights: relative 2^-16
