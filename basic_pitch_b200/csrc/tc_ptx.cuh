@@ -56,6 +56,7 @@ static __device__ __noinline__ void mbar_deadlock(int tag, uint32_t parity) {
            tag, parity);
   __trap();
 }
+#ifdef BP_MBAR_DEBUG
 __device__ __forceinline__ void mbar_wait_wd(uint64_t* bar, uint32_t parity, int tag) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
@@ -64,6 +65,30 @@ __device__ __forceinline__ void mbar_wait_wd(uint64_t* bar, uint32_t parity, int
     if ((++spins & 0x3ffu) == 0 && clock64() - t0 > 4000000000ll) mbar_deadlock(tag, parity);
   }
 }
+#else
+// Production form: the whole spin loop is one asm block (a C++ loop on the returned predicate makes the compiler treat the
+// issuing warps' loop state as divergent, which takes the MMA loops off the uniform datapath: R2UR before every UTCHMMA),
+// bounded by a spin count (each try_wait suspends for a hardware-defined time first) and ending in a trap.
+// Build with -DBP_MBAR_DEBUG to get the message with the wait site instead.
+__device__ __forceinline__ void mbar_wait_wd(uint64_t* bar, uint32_t parity, int /*tag*/) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, q;\n\t"
+      ".reg .u32 spins;\n\t"
+      "mov.u32 spins, 0;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra WAIT_DONE;\n\t"
+      "add.u32 spins, spins, 1;\n\t"
+      "setp.lt.u32 q, spins, 0x4000000;\n\t"
+      "@q bra WAIT_LOOP;\n\t"
+      "trap;\n\t"
+      "WAIT_DONE:\n\t"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+#endif
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
   asm volatile(
