@@ -7,6 +7,7 @@ or `make -C basic_pitch_b200/csrc`.
 from __future__ import annotations
 
 import ctypes as C
+import os
 import pathlib
 from typing import Optional
 
@@ -75,7 +76,8 @@ def load() -> C.CDLL:
             f"{LIB_PATH} not found: the CUDA extension has not been built "
             "(run `make -C basic_pitch_b200/csrc`). There is no CPU fallback."
         )
-    lib = C.CDLL(str(LIB_PATH))
+    # BP_B200_LIB: load an instrumented build of the same library instead (tools/: trace / debug builds)
+    lib = C.CDLL(os.environ.get("BP_B200_LIB") or str(LIB_PATH))
     vp, i32, i64, sz = C.c_void_p, C.c_int32, C.c_int64, C.c_size_t
     lib.bp_version.restype = C.c_int
     lib.bp_last_error.restype = C.c_char_p

@@ -56,6 +56,8 @@
 #include <cuda_bf16.h>
 
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <unordered_map>
 #include <vector>
@@ -67,9 +69,7 @@ namespace bp {
 
 namespace tc {
 constexpr int kMTile = 128;
-constexpr int kMaxDataBytes = 2 * 40 * (kMTile + 4) * 16;        // hi + lo planes, 40 chunks x 132 rows = 168960
 constexpr int kTileBytes = 8192;                                 // weight tile: [plane 2][kchunk 2][128][8] bf16
-constexpr int kStages = 6;
 constexpr int kMaxSteps = 1024;                                  // program steps per layer (constant memory)
 constexpr int kMaxGroups = 15;
 constexpr int kThreads = 384;  // 12 warps: 2 x 4 epilogue warps, producer, 2 conv1 MMA issuers, the conv2 MMA issuer
@@ -78,11 +78,29 @@ constexpr int kThreads = 384;  // 12 warps: 2 x 4 epilogue warps, producer, 2 co
 constexpr int kProducerWarp = 8, kMmaWarp0 = 9, kMmaWarp1 = 10, kMma2Warp = 11;
 // time-halo exchange between the four epilogue warps of a slot: [slot 2][buffer 2][warp 3][kXchgFloats] (warps 0..2 of a
 // slot publish their top lanes for the warp above; the last warp has nobody to publish to)
-constexpr int kXchgFloats = 200;  // contour: 10 published lane values x 20 output offsets (note 21 x 6, onset 3 x 6)
-constexpr int kXchgBytes = 2 * 2 * 3 * kXchgFloats * 4;
-constexpr int kB2Bytes = 4096;  // weight tiles of the fused conv2 (see TcB2)
-constexpr int kSmemBytes = kMaxDataBytes + kStages * kTileBytes + kXchgBytes + kB2Bytes + 512;
-static_assert(kSmemBytes <= 232448, "dynamic shared memory per CTA (227 KB opt-in)");
+// Shared memory is laid out per layer: the data tile, then as many weight-tile stages as fit.  The weight ring is what
+// bounds the conv1 MMAs (one 8 KB tile per step, about 2 000 cycles from the request to the release of its stage, most
+// steps used by one slot only = 192 tensor cycles), so every KB goes to stages: contour / onset 7, note 9.
+struct TcSmem {
+  int data_bytes;   // [2 planes][chunks][128 + KH - 1 rows][16 B], rounded up to 1 KB
+  int xchg_floats;  // per publishing warp (contour 10 lane values x 20 offsets, note 21 x 6, onset 3 x 6)
+  int b2_bytes;     // conv2 weight tiles (TcB2)
+  int stages;
+  __host__ __device__ constexpr int xchg_bytes() const { return 2 * 2 * 3 * xchg_floats * 4; }
+  __host__ __device__ constexpr int total() const { return data_bytes + stages * kTileBytes + xchg_bytes() + b2_bytes + 512; }
+};
+constexpr int kMaxSmem = 232448;  // 227 KB opt-in per CTA
+__host__ __device__ constexpr TcSmem tc_smem(int epi) {  // epi: 0 / 3 contour, 1 onset, 2 note
+  TcSmem s{};
+  const int chunks = epi == 2 ? 33 : 39, rows = kMTile + (epi == 1 ? 4 : epi == 2 ? 6 : 2);
+  s.data_bytes = (2 * chunks * rows * 16 + 1023) / 1024 * 1024;
+  s.xchg_floats = epi == 1 ? 32 : epi == 2 ? 128 : 200;
+  s.b2_bytes = epi == 2 ? 4096 : 2048;
+  s.stages = (kMaxSmem - 512 - s.data_bytes - s.xchg_bytes() - s.b2_bytes) / kTileBytes;
+  return s;
+}
+static_assert(tc_smem(0).stages == 7 && tc_smem(1).stages == 7 && tc_smem(2).stages == 9, "weight ring depth");
+constexpr int kMaxStages = 9;
 // step word of a slot: [0,14) A start-address offset >> 4, [15] first MMA into that accumulator; kNoUse = the
 // slot's frequency tile does not use this step's weight tile
 constexpr uint32_t kUseFirstAcc = 1u << 15, kNoUse = 0xffffffffu;
@@ -215,7 +233,8 @@ void TcConvPlan::build(const TcConvSpec& sp, const float* W /* [COUT][n_ci][KH][
             ++c8;
             continue;
           }
-          const int c = std::min(c8, sp.chunks8 - 2);  // both k-chunks of the step must exist in the data tile
+          const int c = std::min(c8, sp.chunks8 - 3);  // both k-chunks of the step must exist in the data tile, which
+                                                       // holds chunks 0 .. chunks8 - 2 (the last one is padding only)
           const int off = 8 * c - sp.SF * sp.FLT * ft;
           const int tile = find_or_add(dt, c, ft, 8 * (c8 - c));
           if (tile >= 0) cand.push_back(Use{tile, slot, c, dt, off});
@@ -397,6 +416,8 @@ struct TcArgs {
   const __nv_bfloat16* data;    // [2][chunks8][rows_total][8]
   const uint16_t* tiles;        // [n_tiles][8192 B]
   const uint16_t* b2;           // conv2 weight tiles (tc_build_b2), fused layers
+  int dbg_skip_loads;           // -DBP_TC_TRACE builds: the producer only pretends to load weight tiles (timing experiment)
+  long long* trace;             // -DBP_TC_TRACE builds: [tile][8] clock64 stamps of CTA 0 (see tc_trace)
   TcOut o;                      // where the results go (kernels.cuh)
   int edge_rows;                // row stride of o.edge: [edge slot][side 2][KE][edge_rows]
   int layer;                    // which constant-memory program (0 contour, 1 onset, 2 note)
@@ -407,6 +428,20 @@ struct TcArgs {
   int chunks8, rows_per_window;
   int cout, flt, wout, n_ft, g0;
 };
+
+// Pipeline trace (debug builds with -DBP_TC_TRACE and BP_TC_TRACE=1 in the environment): CTA 0 stamps, per frequency tile n,
+// 0 conv1 region acquired, 1 conv1 MMAs issued, 2 epilogue saw the accumulator, 3 split written back, 4 conv2 MMA warp
+// released, 5 conv2 MMAs issued, 6 epilogue saw the conv2 sums, 7 tile finished.
+#ifdef BP_TC_TRACE
+#define TC_TRACE(n, ev)                                                                                       \
+  do {                                                                                                        \
+    if (a.trace && blockIdx.x == 0 && (n) < 256u && lane == 0) a.trace[(n) * 8u + (ev)] = clock64();            \
+  } while (0)
+#else
+#define TC_TRACE(n, ev) \
+  do {                  \
+  } while (0)
+#endif
 
 __device__ __forceinline__ float sigmoidf_fast(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
 
@@ -437,12 +472,12 @@ __device__ __forceinline__ void time_tap(float (&S)[NJ], const float (&P)[NJ], i
   }
 }
 template <int H, int NJ>
-__device__ __forceinline__ void time_edges(float (&S)[NJ], int quad, int lane, const float* xb /* [4][kXchgFloats] */) {
+__device__ __forceinline__ void time_edges(float (&S)[NJ], int quad, int lane, const float* xb /* [3][XF] */, int XF) {
   if (quad == 0) return;
 #pragma unroll
   for (int a = 1; a <= 2 * H; ++a) {
     if (lane < a) {  // source `a` rows below: lane 32 - a + lane of the previous warp
-      const float* e = xb + (quad - 1) * tc::kXchgFloats + (a * (a - 1) / 2 + lane) * NJ;
+      const float* e = xb + (quad - 1) * XF + (a * (a - 1) / 2 + lane) * NJ;
 #pragma unroll
       for (int j = 0; j < NJ; ++j) S[j] += e[j];
     }
@@ -619,7 +654,7 @@ __device__ __forceinline__ void contour_tile(const TcArgs& a, const RowOut& ro, 
                                              bool first, bool last, int quad, int lane, int slot, float* xb,
                                              float (&carry)[4], float (&hold)[6]) {
   float S[20];
-  float* pub = xb + quad * tc::kXchgFloats;
+  float* pub = xb + quad * tc::tc_smem(3).xchg_floats;
   const int pub_from = quad < 3 ? 32 : 64;  // the last warp of a slot publishes nothing
   // one output offset: its five partial sums p[dt] -> time taps (see time_edges for the cross-warp part)
   auto taps = [&](int j, const float (&p)[5]) {
@@ -689,7 +724,7 @@ __device__ __forceinline__ void contour_tile(const TcArgs& a, const RowOut& ro, 
   }
   __syncwarp();
   slot_barrier(slot);
-  time_edges<2, 20>(S, quad, lane, xb);
+  time_edges<2, 20>(S, quad, lane, xb, tc::tc_smem(3).xchg_floats);
   // frequency halo: S[j] <-> bin 16 ft - 2 + j; bins 16 ft - 2 .. 16 ft + 1 also get the top four sums of the tile below.
   // Finished bins leave in aligned 8-bin chunks: chunk 2 ft - 1 = the six bins held back from the previous tile + j = 0, 1;
   // chunk 2 ft = j = 2 .. 9; j = 10 .. 15 are held for the next tile.  Where a range starts / ends, the four partial sums
@@ -742,11 +777,14 @@ __global__ void __launch_bounds__(tc::kThreads, 1) conv_tc_kernel(const TcArgs a
   constexpr TcB2 B2 = tc_b2_spec(EPI);
   constexpr int ND2 = 512 - (int)kD2Base >= 2 * B2.width ? 2 : 1;  // conv2 accumulators that fit behind the ring
   extern __shared__ __align__(128) unsigned char smem[];
-  unsigned char* s_data = smem;                    // [2 planes][40 chunks][data_rows][16 B]
-  unsigned char* s_w = smem + kMaxDataBytes;       // [kStages][8192]
-  float* s_x = reinterpret_cast<float*>(smem + kMaxDataBytes + kStages * kTileBytes);  // [slot][buf][warp][kXchgFloats]
-  unsigned char* s_b2 = smem + kMaxDataBytes + kStages * kTileBytes + kXchgBytes;      // conv2 weight tiles
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_b2 + kB2Bytes);
+  constexpr TcSmem SM = tc_smem(EPI);
+  constexpr int kStages = SM.stages, kXchgFloats = SM.xchg_floats;
+  static_assert(SM.total() <= kMaxSmem && kStages <= kMaxStages, "dynamic shared memory per CTA");
+  unsigned char* s_data = smem;                    // [2 planes][chunks][data_rows][16 B]
+  unsigned char* s_w = smem + SM.data_bytes;       // [kStages][8192]
+  float* s_x = reinterpret_cast<float*>(s_w + kStages * kTileBytes);  // [slot][buf][warp 3][kXchgFloats]
+  unsigned char* s_b2 = reinterpret_cast<unsigned char*>(s_x) + SM.xchg_bytes();  // conv2 weight tiles
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_b2 + SM.b2_bytes);
   uint64_t* full_w = bars;             // [kStages]
   uint64_t* empty_w = bars + kStages;  // [kStages]
   uint64_t* data_full = bars + 2 * kStages;
@@ -768,7 +806,7 @@ __global__ void __launch_bounds__(tc::kThreads, 1) conv_tc_kernel(const TcArgs a
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
   const uint32_t lbo = (uint32_t)a.data_rows * 16u;
-  const uint32_t plane_bytes = (uint32_t)a.chunks8 * lbo;
+  const uint32_t plane_bytes = (uint32_t)(a.chunks8 - 1) * lbo;  // the tile holds chunks 0 .. chunks8 - 2
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) {
@@ -817,7 +855,7 @@ __global__ void __launch_bounds__(tc::kThreads, 1) conv_tc_kernel(const TcArgs a
     if (lane == 0) {
       if constexpr (kFused) {
         constexpr uint32_t b2_bytes = (uint32_t)B2.n_tiles * 2u * 16u * B2.n2 * 2u;
-        static_assert(b2_bytes <= (uint32_t)kB2Bytes, "conv2 weight tiles");
+        static_assert(b2_bytes <= (uint32_t)SM.b2_bytes, "conv2 weight tiles");
         mbar_expect_tx(b2_full, b2_bytes);
         bulk_g2s(s_b2, a.b2, b2_bytes, b2_full);
       }
@@ -830,16 +868,23 @@ __global__ void __launch_bounds__(tc::kThreads, 1) conv_tc_kernel(const TcArgs a
         mbar_expect_tx(data_full, 2 * plane_bytes);
         const size_t row = (size_t)mt * a.ms + a.row0;
         for (int p = 0; p < 2; ++p)
-          for (int c = 0; c < a.chunks8; ++c)
+          for (int c = 0; c < a.chunks8 - 1; ++c)
             bulk_g2s(s_data + p * plane_bytes + c * lbo, a.data + p * plane_elems + ((size_t)c * a.rows_total + row) * 8,
                      lbo, data_full);
         ph_d ^= 1;
         const int s0 = c_group_step_off[a.layer][g0], s1 = c_group_step_off[a.layer][g1];
         for (int s = s0; s < s1; ++s) {
           mbar_wait_wd(empty_w + stage, ph_w ^ 1, 2);
-          mbar_expect_tx(full_w + stage, kTileBytes);
-          bulk_g2s(s_w + stage * kTileBytes, a.tiles + (size_t)c_tile_seq[a.layer][s] * (kTileBytes / 2), kTileBytes,
-                   full_w + stage);
+#ifdef BP_TC_TRACE
+          if (a.dbg_skip_loads) {
+            mbar_arrive(full_w + stage);
+          } else
+#endif
+          {
+            mbar_expect_tx(full_w + stage, kTileBytes);
+            bulk_g2s(s_w + stage * kTileBytes, a.tiles + (size_t)c_tile_seq[a.layer][s] * (kTileBytes / 2), kTileBytes,
+                     full_w + stage);
+          }
           if (++stage == kStages) {
             stage = 0;
             ph_w ^= 1;
@@ -872,6 +917,7 @@ __global__ void __launch_bounds__(tc::kThreads, 1) conv_tc_kernel(const TcArgs a
         if (mine) {
           mbar_wait_wd(tmem_empty + r, (u & 1u) ^ 1u, 4);
           tc_fence_after();
+          TC_TRACE(nm, 0);
         }
         const int s0 = c_group_step_off[a.layer][g], s1 = c_group_step_off[a.layer][g + 1];
         const uint32_t d = tmem_base + r * 128u;
@@ -896,6 +942,7 @@ __global__ void __launch_bounds__(tc::kThreads, 1) conv_tc_kernel(const TcArgs a
           w = w_next;
         }
         if (mine) umma_commit_pred(tmem_full + 2 * r + slot, leader);  // this tile's conv1 accumulator is complete
+        if (mine) TC_TRACE(nm, 1);
         n += two ? 2u : 1u;
       }
       umma_commit_pred(data_empty, leader);  // the data tile may be overwritten
@@ -920,6 +967,7 @@ __global__ void __launch_bounds__(tc::kThreads, 1) conv_tc_kernel(const TcArgs a
             mbar_wait_wd(a2_full + r, u & 1u, 7);
             mbar_wait_wd(d2_empty + b, (v & 1u) ^ 1u, 8);
             tc_fence_after();
+            TC_TRACE(n, 4);
             const uint32_t areg = tmem_base + r * 128u, dacc = tmem_base + kD2Base + b * (uint32_t)B2.width;
 #pragma unroll
             for (int ks = 0; ks < 8; ++ks) {
@@ -931,6 +979,7 @@ __global__ void __launch_bounds__(tc::kThreads, 1) conv_tc_kernel(const TcArgs a
             }
             umma_commit_pred(d2_full + sl, leader);    // conv2 partial sums of this tile are complete
             umma_commit_pred(tmem_empty + r, leader);  // and its region may take the next conv1 tile
+            TC_TRACE(n, 5);
           }
         }
       }
@@ -993,6 +1042,7 @@ __global__ void __launch_bounds__(tc::kThreads, 1) conv_tc_kernel(const TcArgs a
         mbar_wait_wd(tmem_full + 2 * r + slot, (full_bits >> r) & 1u, 9);
         full_bits ^= 1u << r;
         tc_fence_after();
+        if (quad == 0) TC_TRACE(nm, 2);
         const uint32_t taddr = lane_base + r * 128u;
         // first / last tile of this slot's ascending range inside the item
         const bool first = (g == g0);
@@ -1028,11 +1078,13 @@ __global__ void __launch_bounds__(tc::kThreads, 1) conv_tc_kernel(const TcArgs a
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(a2_full + r);
+          if (quad == 0) TC_TRACE(nm, 3);
           // ... and hand back P[j][dt] in the conv2 accumulator
           const uint32_t bb = nm % ND2;
           mbar_wait_wd(d2_full + slot, my_tiles & 1u, 10);
           ++my_tiles;
           tc_fence_after();
+          if (quad == 0) TC_TRACE(nm, 6);
           const uint32_t d2 = lane_base + kD2Base + bb * (uint32_t)B2.width;
           float* xb = s_x + (slot * 2 + xbuf) * 3 * kXchgFloats;
           xbuf ^= 1u;
@@ -1044,12 +1096,13 @@ __global__ void __launch_bounds__(tc::kThreads, 1) conv_tc_kernel(const TcArgs a
             pitch_tile_taps<KH2>(d2, lane, quad, xb + quad * kXchgFloats, d2_empty + bb, S);
             __syncwarp();
             slot_barrier(slot);
-            time_edges<H, 6>(S, quad, lane, xb);
+            time_edges<H, 6>(S, quad, lane, xb, kXchgFloats);
             float c2[2] = {carry[0], carry[1]};
             finish_pitch_tile<EPI>(a, ro, S, c2, ft, first, last);
             carry[0] = c2[0];
             carry[1] = c2[1];
           }
+          if (quad == 0) TC_TRACE(nm, 7);
         }
       }
     }
@@ -1153,10 +1206,10 @@ int tc_rows_total(int n_windows, int rows_per_window) {
 }
 
 int tc_setup() {
-  cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes);
+  cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::tc_smem(0).total());
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::tc_smem(1).total());
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::tc_smem(2).total());
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::tc_smem(3).total());
   return e == cudaSuccess ? 0 : -1;
 }
 
@@ -1214,14 +1267,38 @@ void launch_conv_tc(const __nv_bfloat16* data, const TcConvDev& dev, const TcOut
   a.g0 = sp.G0;
   const int n_items = a.n_mtiles * a.n_split;
   const int grid = n_items < n_sms ? n_items : n_sms;
+#ifdef BP_TC_TRACE
+  static long long* d_trace = nullptr;
+  const bool tracing = getenv("BP_TC_TRACE") != nullptr;
+  if (tracing) {
+    if (!d_trace) cudaMalloc(&d_trace, 256 * 8 * sizeof(long long));
+    cudaMemsetAsync(d_trace, 0, 256 * 8 * sizeof(long long), st);
+    a.trace = d_trace;
+  }
+  a.dbg_skip_loads = getenv("BP_TC_SKIP_LOADS") != nullptr;
+#endif
   if (sp.epi == 0 && fuse_next)
-    conv_tc_kernel<3><<<grid, tc::kThreads, tc::kSmemBytes, st>>>(a);
+    conv_tc_kernel<3><<<grid, tc::kThreads, tc::tc_smem(3).total(), st>>>(a);
   else if (sp.epi == 0)
-    conv_tc_kernel<0><<<grid, tc::kThreads, tc::kSmemBytes, st>>>(a);
+    conv_tc_kernel<0><<<grid, tc::kThreads, tc::tc_smem(0).total(), st>>>(a);
   else if (sp.epi == 1)
-    conv_tc_kernel<1><<<grid, tc::kThreads, tc::kSmemBytes, st>>>(a);
+    conv_tc_kernel<1><<<grid, tc::kThreads, tc::tc_smem(1).total(), st>>>(a);
   else
-    conv_tc_kernel<2><<<grid, tc::kThreads, tc::kSmemBytes, st>>>(a);
+    conv_tc_kernel<2><<<grid, tc::kThreads, tc::tc_smem(2).total(), st>>>(a);
+#ifdef BP_TC_TRACE
+  if (tracing) {
+    static long long h[256 * 8];
+    cudaMemcpyAsync(h, d_trace, sizeof(h), cudaMemcpyDeviceToHost, st);
+    cudaStreamSynchronize(st);
+    long long t0 = h[0];
+    fprintf(stderr, "tc_trace layer %d n_items %d split %d grid %d\n", dev.layer, n_items, a.n_split, grid);
+    for (int n = 0; n < 256 && h[n * 8 + 1]; ++n) {
+      fprintf(stderr, "tile %3d:", n);
+      for (int e = 0; e < 8; ++e) fprintf(stderr, " %8lld", h[n * 8 + e] ? h[n * 8 + e] - t0 : -1);
+      fprintf(stderr, "\n");
+    }
+  }
+#endif
   if (fused) {  // slot s of split q covers tiles [g0(q) + s*G0, g1(q) + s*G0): edge slot s*split + q
     EdgeFixArgs ef{};
     ef.o = o;
