@@ -24,7 +24,7 @@ EXPORTS = [
     "bp_model_create", "bp_model_destroy", "bp_model_device", "bp_model_param_block", "bp_model_refresh",
     "bp_model_launch_count", "bp_forward_device", "bp_forward_host", "bp_run_inference_device",
     "bp_run_inference_host", "bp_decode_device", "bp_decode_host", "bp_transcribe_host", "bp_transcribe_device",
-    "bp_infer_onsets_host", "bp_pitch_bends_host", "bp_debug_activation", "bp_model_chunk_windows", "bp_model_set_path", "bp_model_profile", "bp_model_profile_read", "bp_debug_tc_plan", "bp_debug_tc_b2",
+    "bp_infer_onsets_host", "bp_pitch_bends_host", "bp_debug_activation", "bp_model_chunk_windows", "bp_model_set_path", "bp_model_profile", "bp_model_profile_read", "bp_debug_tc_plan", "bp_debug_tc_b2", "bp_transcribe_files_host", "bp_host_alloc", "bp_host_free", "bp_last_required",
 ]  # fmt: skip
 
 
@@ -111,6 +111,13 @@ def load() -> C.CDLL:
     lib.bp_debug_activation.argtypes = [vp, C.c_int, vp, i64]
     lib.bp_debug_tc_plan.argtypes = [C.c_int, vp, vp, vp, vp, vp, vp, vp]
     lib.bp_debug_tc_b2.argtypes = [C.c_int, vp, vp, vp]
+    lib.bp_transcribe_files_host.argtypes = [vp, vp, vp, i32, C.POINTER(DecodeParams), vp, vp, vp, vp, C.POINTER(Notes)]
+    lib.bp_host_alloc.argtypes = [sz]
+    lib.bp_host_alloc.restype = vp
+    lib.bp_host_free.argtypes = [vp]
+    lib.bp_host_free.restype = None
+    lib.bp_last_required.argtypes = [vp, vp]
+    lib.bp_last_required.restype = None
     lib.bp_model_profile.argtypes = [vp, C.c_int]
     lib.bp_model_profile_read.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(i64), C.POINTER(i64)]
     for name in EXPORTS:

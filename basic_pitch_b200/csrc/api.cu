@@ -2,10 +2,12 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <mutex>
+#include <thread>
 #include <string>
 #include <vector>
 
@@ -157,6 +159,12 @@ struct bp_model {
   DevBuf<UnwrapDesc> udesc;
   // staging for the host entry points
   DevBuf<float> st_audio, st_note, st_onset, st_contour;
+  // bp_transcribe_files_host: pinned gather buffers (one sub-batch of audio each), the device->host stream of the
+  // posteriorgrams and its events
+  float* gather[3] = {nullptr, nullptr, nullptr};
+  size_t gather_cap = 0;  // floats per buffer
+  cudaStream_t d2h_stream = nullptr;
+  std::vector<cudaEvent_t> conv_ev;
   // decode workspace
   DevBuf<long long> d_frame_off, d_slot_off, d_note_base;
   DevBuf<float> energy, d_amp;
@@ -187,6 +195,7 @@ namespace {
 // it enqueues, and a change of owner first drains the device so that kernels of the previous owner that are still in
 // flight never see the new values.  Models with different weights may therefore be used from several host threads;
 // they serialise at chunk granularity.
+thread_local int64_t g_need_notes = 0, g_need_bends = 0;  // bp_last_required
 const bp_model* g_const_owner[64] = {};
 std::mutex g_const_mu[64];
 
@@ -650,6 +659,10 @@ void bp_model_destroy(bp_model_t* m) {
   if (m->h_ud) cudaFreeHost(m->h_ud);
   for (cudaEvent_t e : m->copy_ev) cudaEventDestroy(e);
   if (m->copy_stream) cudaStreamDestroy(m->copy_stream);
+  if (m->d2h_stream) cudaStreamDestroy(m->d2h_stream);
+  for (float* b : m->gather)
+    if (b) cudaFreeHost(b);
+  for (cudaEvent_t e : m->conv_ev) cudaEventDestroy(e);
   if (m->stream) cudaStreamDestroy(m->stream);
   delete m;
 }
@@ -959,7 +972,7 @@ int bp_decode_device(bp_model_t* m, const float* d_note, const float* d_onset, c
     if (n_notes > notes->note_capacity) {
       long long need = 0;
       for (int j = 0; j < n_files; ++j) need += counts[j];
-      return fail(BP_E_CAPACITY, "bp_decode_device: note_capacity too small, need " + std::to_string(need));
+      return g_need_notes = need, fail(BP_E_CAPACITY, "bp_decode_device: note_capacity too small, need " + std::to_string(need));
     }
     notes->note_off[i + 1] = (int32_t)n_notes;
   }
@@ -992,7 +1005,7 @@ int bp_decode_device(bp_model_t* m, const float* d_note, const float* d_onset, c
     notes->bend_off[j + 1] = (int32_t)n_bends;
   }
   if (with_bends && n_bends > notes->bend_capacity)
-    return fail(BP_E_CAPACITY, "bp_decode_device: bend_capacity too small, need " + std::to_string(n_bends));
+    return g_need_bends = n_bends, fail(BP_E_CAPACITY, "bp_decode_device: bend_capacity too small, need " + std::to_string(n_bends));
   if (with_bends && n_bends > 0 && !notes->bends) return fail(BP_E_INVALID, "bp_decode_device: bends array missing");
   CK(m->d_bends.reserve((size_t)n_bends + 1));
   CK(cudaMemcpyAsync(m->d_bend_off.p, notes->bend_off, sizeof(int) * (n_notes + 1), cudaMemcpyHostToDevice, st));
@@ -1209,6 +1222,179 @@ int bp_transcribe_host(bp_model_t* m, const float* h_audio, const int64_t* h_sam
     if (h_contour)
       CK(cudaMemcpyAsync(h_contour, m->st_contour.p, sizeof(float) * total_frames * kContourBins, cudaMemcpyDeviceToHost, st));
   }
+  CK(cudaStreamSynchronize(st));
+  return BP_OK;
+}
+
+void bp_last_required(int64_t* notes, int64_t* bends) {
+  if (notes) *notes = g_need_notes;
+  if (bends) *bends = g_need_bends;
+}
+
+void* bp_host_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) {
+    cudaGetLastError();
+    fail(BP_E_CUDA, "bp_host_alloc: cudaHostAlloc failed");
+    return nullptr;
+  }
+  return p;
+}
+
+void bp_host_free(void* p) {
+  if (p) cudaFreeHost(p);
+}
+
+namespace {
+// copies the audio of files [f0, f1) into one contiguous pinned buffer with a few host threads
+void gather_files(const float* const* audio, const int64_t* rel, int f0, int f1, float* dst, int n_threads) {
+  const int64_t base = rel[f0], total = rel[f1] - base;
+  if (total <= 0) return;
+  n_threads = (int)std::max<int64_t>(1, std::min<int64_t>(n_threads, total / (1 << 20)));
+  auto work = [&](int t) {
+    // thread t copies samples [lo, hi) of the sub-batch: whole files where possible, split files otherwise
+    const int64_t lo = base + total * t / n_threads, hi = base + total * (t + 1) / n_threads;
+    int i = (int)(std::upper_bound(rel + f0, rel + f1 + 1, lo) - rel) - 1;
+    for (; i < f1 && rel[i] < hi; ++i) {
+      const int64_t a = std::max(lo, rel[i]), b = std::min(hi, rel[i + 1]);
+      if (b > a) std::memcpy(dst + (a - base), audio[i] + (a - rel[i]), sizeof(float) * (size_t)(b - a));
+    }
+  };
+  if (n_threads == 1) return work(0);
+  std::vector<std::thread> th;
+  for (int t = 1; t < n_threads; ++t) th.emplace_back(work, t);
+  work(0);
+  for (auto& x : th) x.join();
+}
+}  // namespace
+
+int bp_transcribe_files_host(bp_model_t* m, const float* const* audio, const int64_t* n_samples, int32_t n_files,
+                             const bp_decode_params_t* params, float* h_note, float* h_onset, float* h_contour,
+                             int64_t* h_frame_off, bp_notes_t* notes) {
+  if (!m || !h_frame_off || n_files < 0 || (n_files > 0 && (!audio || !n_samples)))
+    return fail(BP_E_INVALID, "bp_transcribe_files_host: bad argument");
+  int rc = validate_params(params);
+  if (rc) return rc;
+  DeviceGuard g(m->device);
+  cudaStream_t st = m->stream;
+  std::vector<int64_t> rel(n_files + 1, 0);
+  int64_t total_frames = 0;
+  for (int i = 0; i < n_files; ++i) {
+    if (n_samples[i] < 0 || (n_samples[i] > 0 && !audio[i]))
+      return fail(BP_E_INVALID, "bp_transcribe_files_host: file " + std::to_string(i) + ": null audio or negative length");
+    rel[i + 1] = rel[i] + n_samples[i];
+    total_frames += bp_num_frames(n_samples[i]);
+  }
+  const int64_t total_samples = rel[n_files];
+  CK(m->st_audio.reserve((size_t)std::max<int64_t>(total_samples, 1)));
+  CK(m->st_note.reserve((size_t)total_frames * kPitches + 4));
+  CK(m->st_onset.reserve((size_t)total_frames * kPitches + 4));
+  CK(m->st_contour.reserve((size_t)total_frames * kContourBins + 4));
+  PostI u;
+  rc = reserve_internal(m, total_frames, &u);
+  if (rc) return rc;
+  // sub-batches of whole files, about two internal chunks of windows each (the first ones one chunk, so that the
+  // kernels start early)
+  std::vector<int> cut{0};
+  {
+    int64_t w = 0;
+    for (int i = 0; i < n_files; ++i) {
+      const size_t k = cut.size() - 1;
+      const int64_t limit = (k < 2 ? 1 : 2) * (int64_t)m->chunk;
+      const int64_t nw = bp_num_windows(n_samples[i]);
+      if (w > 0 && w + nw > limit) {
+        cut.push_back(i);
+        w = 0;
+      }
+      w += nw;
+    }
+    cut.push_back(n_files);
+  }
+  const size_t n_sub = cut.size() - 1;
+  size_t max_sub = 1;
+  for (size_t k = 0; k < n_sub; ++k) max_sub = std::max<size_t>(max_sub, (size_t)(rel[cut[k + 1]] - rel[cut[k]]));
+  if (max_sub > m->gather_cap) {
+    for (float*& b : m->gather) {
+      if (b) cudaFreeHost(b);
+      b = nullptr;
+    }
+    m->gather_cap = 0;
+    const size_t want = max_sub + max_sub / 8;
+    for (float*& b : m->gather) CK(cudaHostAlloc(&b, want * sizeof(float), cudaHostAllocDefault));
+    m->gather_cap = want;
+  }
+  if (!m->d2h_stream) CK(cudaStreamCreateWithFlags(&m->d2h_stream, cudaStreamNonBlocking));
+  while (m->copy_ev.size() < n_sub || m->conv_ev.size() < n_sub) {
+    cudaEvent_t e;
+    CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    (m->copy_ev.size() < n_sub ? m->copy_ev : m->conv_ev).push_back(e);
+  }
+  int n_threads = (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+  if (const char* e = getenv("BP_B200_GATHER_THREADS")) n_threads = std::max(1, std::min(64, atoi(e)));
+  const bool timing = getenv("BP_B200_TIMING") != nullptr;  // host-side breakdown of this call on stderr
+  auto now = [] { return std::chrono::steady_clock::now(); };
+  auto ms_since = [&](std::chrono::steady_clock::time_point t) { return std::chrono::duration<double, std::milli>(now() - t).count(); };
+  const auto t_call = now();
+  double t_gather = 0, t_wait = 0, t_launch = 0;
+  CK(cudaStreamSynchronize(st));  // st_audio / st_note.. may still be in use by earlier work on the compute stream
+  h_frame_off[0] = 0;
+  std::vector<int64_t> sub_off;
+  for (size_t k = 0; k < n_sub; ++k) {
+    const int f0 = cut[k], f1 = cut[k + 1];
+    const int64_t s0 = rel[f0], s1 = rel[f1];
+    float* stage = m->gather[k % 3];
+    auto t0 = now();
+    if (k >= 3) CK(cudaEventSynchronize(m->copy_ev[k - 3]));  // the buffer's previous upload has left the host
+    t_wait += ms_since(t0);
+    t0 = now();
+    gather_files(audio, rel.data(), f0, f1, stage, n_threads);
+    t_gather += ms_since(t0);
+    t0 = now();
+    if (s1 > s0)
+      CK(cudaMemcpyAsync(m->st_audio.p + s0, stage, sizeof(float) * (size_t)(s1 - s0), cudaMemcpyHostToDevice, m->copy_stream));
+    CK(cudaEventRecord(m->copy_ev[k], m->copy_stream));
+    CK(cudaStreamWaitEvent(st, m->copy_ev[k], 0));
+    sub_off.assign(f1 - f0 + 1, 0);
+    const int64_t base = h_frame_off[f0];
+    rc = run_inference_internal(m, m->st_audio.p, rel.data() + f0, f1 - f0, u, base, sub_off.data(), st);
+    if (rc) return rc;
+    for (int i = f0; i < f1; ++i) h_frame_off[i + 1] = base + sub_off[i - f0 + 1];
+    // this sub-batch's posteriorgrams: internal -> row-major, then to the host on their own stream while the next
+    // sub-batches compute
+    const int64_t nf = h_frame_off[f1] - base;
+    if (nf > 0) {
+      launch_pm_to_rows(u.note, u.stride, base, nf, kPitches, m->st_note.p + base * kPitches, st);
+      launch_pm_to_rows(u.onset, u.stride, base, nf, kPitches, m->st_onset.p + base * kPitches, st);
+      launch_cm_to_rows(u.contour, u.stride, base, nf, m->st_contour.p + base * kContourBins, st);
+      m->launches += 3;
+      CKL();
+      CK(cudaEventRecord(m->conv_ev[k], st));
+      if (h_note || h_onset || h_contour) {
+        CK(cudaStreamWaitEvent(m->d2h_stream, m->conv_ev[k], 0));
+        if (h_note)
+          CK(cudaMemcpyAsync(h_note + base * kPitches, m->st_note.p + base * kPitches, sizeof(float) * nf * kPitches,
+                             cudaMemcpyDeviceToHost, m->d2h_stream));
+        if (h_onset)
+          CK(cudaMemcpyAsync(h_onset + base * kPitches, m->st_onset.p + base * kPitches, sizeof(float) * nf * kPitches,
+                             cudaMemcpyDeviceToHost, m->d2h_stream));
+        if (h_contour)
+          CK(cudaMemcpyAsync(h_contour + base * kContourBins, m->st_contour.p + base * kContourBins,
+                             sizeof(float) * nf * kContourBins, cudaMemcpyDeviceToHost, m->d2h_stream));
+      }
+    }
+    t_launch += ms_since(t0);
+  }
+  const auto t_dec = now();
+  rc = bp_decode_device(m, m->st_note.p, m->st_onset.p, m->st_contour.p, h_frame_off, n_files, params, notes, st);
+  const double ms_dec = ms_since(t_dec);
+  const auto t_d2h = now();
+  cudaError_t e1 = cudaStreamSynchronize(m->d2h_stream);
+  if (timing)
+    fprintf(stderr, "bp_transcribe_files_host: %d files, %zu sub-batches, %d gather threads: gather %.1f ms, staging waits %.1f ms, "
+            "enqueue %.1f ms, decode (incl. waiting for the forward pass) %.1f ms, tail of the posteriorgram copies %.1f ms, total %.1f ms\n",
+            n_files, n_sub, n_threads, t_gather, t_wait, t_launch, ms_dec, ms_since(t_d2h), ms_since(t_call));
+  if (rc) return rc;
+  CK(e1);
   CK(cudaStreamSynchronize(st));
   return BP_OK;
 }

@@ -48,6 +48,64 @@ def _ptr(a: Optional[np.ndarray]) -> Optional[int]:
     return None if a is None else a.ctypes.data
 
 
+class _PinnedBlock:
+    """One page-locked host allocation (bp_host_alloc).  NumPy arrays carved out of it keep it alive through their
+    `.base` chain; when the last of them dies the block goes back to the pool (or is freed)."""
+
+    __slots__ = ("ptr", "nbytes", "pool")
+
+    def __init__(self, ptr: int, nbytes: int, pool: "_PinnedPool"):
+        self.ptr, self.nbytes, self.pool = ptr, nbytes, pool
+
+    def __del__(self):
+        pool, ptr = self.pool, self.ptr
+        self.ptr = 0
+        if ptr:
+            try:
+                pool._release(ptr, self.nbytes)
+            except Exception:  # interpreter shutdown
+                pass
+
+
+class _PinnedPool:
+    """Pool of page-locked output buffers: device->host copies into them are asynchronous (~50 GB/s instead of the
+    ~10 GB/s of pageable memory) and `cudaHostAlloc` itself (~0.2 s per GB) is paid once, not per call."""
+
+    GRANULE = 32 << 20
+    KEEP = 3  # free blocks kept per size class
+
+    def __init__(self, lib):
+        self._lib = lib
+        self._free: Dict[int, List[int]] = {}
+
+    def array(self, shape: Tuple[int, ...], dtype=np.float32) -> np.ndarray:
+        n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        cls = max(1, -(-n // self.GRANULE)) * self.GRANULE
+        lst = self._free.get(cls)
+        ptr = lst.pop() if lst else self._lib.bp_host_alloc(cls)
+        if not ptr:
+            raise MemoryError(f"cannot allocate {cls} bytes of page-locked host memory")
+        carr = (C.c_byte * max(n, 1)).from_address(ptr)
+        carr._block = _PinnedBlock(ptr, cls, self)  # lifetime: carr <- ndarray.base <- every view
+        return np.frombuffer(carr, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+    def _release(self, ptr: int, cls: int) -> None:
+        lst = self._free.setdefault(cls, [])
+        if len(lst) < self.KEEP:
+            lst.append(ptr)
+        else:
+            self._lib.bp_host_free(ptr)
+
+    def __del__(self):
+        for lst in self._free.values():
+            for ptr in lst:
+                try:
+                    self._lib.bp_host_free(ptr)
+                except Exception:
+                    pass
+        self._free = {}
+
+
 def _default_device() -> int:
     for var in ("BP_B200_DEVICE", "LOCAL_RANK"):
         if os.environ.get(var, "") != "":
@@ -82,6 +140,7 @@ class Model:
         self._h = C.c_void_p()
         self.device = _default_device() if device is None else int(device)
         self._lib.bp_model_create(blob, len(blob), self.device, C.byref(self._h))
+        self._pinned = _PinnedPool(self._lib)
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
@@ -195,7 +254,7 @@ class Model:
     def _with_capacity(self, n_files: int, total_frames: int, call):
         note_cap = max(4096, 2 * total_frames)
         bend_cap = max(65536, 24 * total_frames)
-        for _ in range(4):
+        for _ in range(3):  # at most: notes too small, then bends too small, then success
             notes, arrs = self._alloc_notes(n_files, note_cap, bend_cap)
             try:
                 call(notes)
@@ -203,11 +262,11 @@ class Model:
             except _lib.BpError as e:
                 if e.code != _lib.BP_E_CAPACITY:
                     raise
-                need = int(str(e).rsplit("need ", 1)[1])
-                if "note_capacity" in str(e):
-                    note_cap = need
-                else:
-                    bend_cap = need
+                need_n, need_b = C.c_int64(0), C.c_int64(0)
+                self._lib.bp_last_required(C.byref(need_n), C.byref(need_b))
+                if need_n.value <= note_cap and need_b.value <= bend_cap:
+                    raise
+                note_cap, bend_cap = max(note_cap, need_n.value), max(bend_cap, need_b.value)
         raise RuntimeError("decode capacity negotiation failed")
 
     def decode_arrays(self, notes: Sequence[np.ndarray], onsets: Sequence[np.ndarray],
@@ -268,34 +327,40 @@ class Model:
     # ------------------------------------------------------------------ the whole path
     def transcribe_arrays(self, audios: Sequence[np.ndarray], onset_thresh=0.5, frame_thresh=0.3, min_note_len=11,
                           energy_tol=11, infer_onsets=True, melodia_trick=True, include_pitch_bends=True,
-                          min_pitch_idx=0, max_pitch_idx=88, return_model_output: bool = True):
+                          min_pitch_idx=0, max_pitch_idx=88, return_model_output: bool = True, split_notes: bool = True):
         """Audio of a batch of files -> (model outputs | None, note arrays) per file in ONE library call
-        (reference: inference.py:431-506 `predict`, minus file I/O and the MIDI object)."""
-        flat, offs = self._pack_audio(audios)
+        (reference: inference.py:431-506 `predict`, minus file I/O and the MIDI object).  With split_notes=False the
+        second result is the concatenated arrays of the call (note_off, start, end, pitch, amp, bend_off, bends)."""
         n_files = len(audios)
-        frames = [int(self._lib.bp_num_frames(int(offs[i + 1] - offs[i]))) for i in range(n_files)]
+        # one pointer per file: the library gathers the (pageable) arrays into pinned staging itself, sub-batch by
+        # sub-batch, overlapped with the kernels (bp_transcribe_files_host) — no host-side concatenation
+        keep = []
+        for a in audios:
+            if a.ndim != 1:
+                raise ValueError("audio must be mono (1-D)")
+            keep.append(a if (a.dtype == _F32 and a.flags.c_contiguous) else np.ascontiguousarray(a, dtype=_F32))
+        ptrs = (C.c_void_p * max(n_files, 1))(*[a.ctypes.data for a in keep])
+        lens = np.fromiter((a.shape[0] for a in keep), dtype=np.int64, count=n_files)
+        frames = [int(self._lib.bp_num_frames(int(n))) for n in lens]
         total = sum(frames)
         note = onset = contour = None
-        if return_model_output:
-            note = np.empty((total, N_FREQ_BINS_NOTES), _F32)
-            onset = np.empty((total, N_FREQ_BINS_NOTES), _F32)
-            contour = np.empty((total, N_FREQ_BINS_CONTOURS), _F32)
+        if return_model_output:  # page-locked: the posteriorgrams stream back while later sub-batches compute
+            note = self._pinned.array((total, N_FREQ_BINS_NOTES))
+            onset = self._pinned.array((total, N_FREQ_BINS_NOTES))
+            contour = self._pinned.array((total, N_FREQ_BINS_CONTOURS))
         foff = np.zeros(n_files + 1, np.int64)
         p = self._params(onset_thresh, frame_thresh, min_note_len, energy_tol, infer_onsets, melodia_trick,
                          include_pitch_bends, min_pitch_idx, max_pitch_idx)
         arrs = self._with_capacity(
             n_files, total,
-            lambda nt: self._lib.bp_transcribe_host(self._h, _ptr(flat), _ptr(offs), n_files, C.byref(p), _ptr(note),
-                                                    _ptr(onset), _ptr(contour), _ptr(foff), C.byref(nt)),
+            lambda nt: self._lib.bp_transcribe_files_host(self._h, ptrs, _ptr(lens), n_files, C.byref(p), _ptr(note),
+                                                          _ptr(onset), _ptr(contour), _ptr(foff), C.byref(nt)),
         )
-        res = self._split_notes(arrs, n_files)
-        outs: List[Optional[Dict[str, np.ndarray]]] = []
-        for i in range(n_files):
-            if return_model_output:
-                a, b = int(foff[i]), int(foff[i + 1])
-                outs.append({"note": note[a:b], "onset": onset[a:b], "contour": contour[a:b]})
-            else:
-                outs.append(None)
+        res = self._split_notes(arrs, n_files) if split_notes else arrs
+        outs: List[Optional[Dict[str, np.ndarray]]] = [None] * n_files
+        if return_model_output:
+            fo = foff.tolist()
+            outs = [{"note": note[a:b], "onset": onset[a:b], "contour": contour[a:b]} for a, b in zip(fo[:-1], fo[1:])]
         return outs, res, frames
 
 
@@ -475,29 +540,39 @@ def predict_batch(
     midi_tempo: float = DEFAULT_MINIMUM_MIDI_TEMPO,
     return_model_output: bool = True,
     build_midi: bool = True,
+    lazy: bool = True,
 ):
     """`predict` for many clips in one device pass (addition; no reference counterpart).
 
     Items are paths or mono 22 050 Hz float arrays.  Returns a list of
-    (model_output | None, midi_data | None, note_events) in input order."""
+    (model_output | None, midi_data | None, note_events) in input order.  The model outputs are views of three
+    page-locked arrays shared by the batch.  With lazy=True (default) the note events are `NoteEventList`s and the MIDI
+    objects `LazyPrettyMIDI`s: both turn into the reference's Python objects when first read; lazy=False builds
+    everything before returning."""
     model = model_or_model_path if isinstance(model_or_model_path, Model) else default_model(model_or_model_path)
     audios = [a if isinstance(a, np.ndarray) else load_audio(a, sr=AUDIO_SAMPLE_RATE, mono=True)[0] for a in audio]
     min_note_len = int(np.round(minimum_note_length / 1000 * (AUDIO_SAMPLE_RATE / FFT_HOP)))
     lo, hi = infer.frequency_to_column_range(minimum_frequency, maximum_frequency)
-    outs, res, frames = model.transcribe_arrays(
+    outs, arrs, frames = model.transcribe_arrays(
         audios, onset_thresh=onset_threshold, frame_thresh=frame_threshold, min_note_len=min_note_len,
         melodia_trick=melodia_trick, min_pitch_idx=lo, max_pitch_idx=hi, return_model_output=return_model_output,
+        split_notes=False,
     )
-    results = []
-    for i in range(len(audios)):
-        if build_midi and outs[i] is not None:
-            midi, events = _events_and_midi(outs[i], res[i], frames[i], minimum_frequency, maximum_frequency,
-                                            multiple_pitch_bends, midi_tempo)
-        else:
-            events = infer.note_events_from_arrays(res[i], frames[i], include_pitch_bends=True)
-            midi = infer.note_events_to_midi(events, multiple_pitch_bends, midi_tempo) if build_midi else None
-        results.append((outs[i], midi, events))
-    return results
+    n = len(audios)
+    events = infer.note_events_batch(arrs, n, include_pitch_bends=True, lazy=lazy)
+    if return_model_output and (minimum_frequency is not None or maximum_frequency is not None):
+        # the reference zeroes these columns of the returned arrays (note_creation.py:338-341); all files share two arrays
+        flo, fhi = infer.frequency_to_column_range(minimum_frequency, maximum_frequency)
+        for k in ("note", "onset"):
+            whole = outs[0][k].base if n and outs[0][k].base is not None else None
+            for m in ([whole] if isinstance(whole, np.ndarray) and whole.ndim == 2 else [o[k] for o in outs]):
+                m[:, :flo] = 0
+                m[:, fhi:] = 0
+    midis = [infer.LazyPrettyMIDI(ev, multiple_pitch_bends, midi_tempo) if build_midi else None for ev in events]
+    if build_midi and not lazy:
+        for m in midis:
+            m.instruments  # assemble the Instrument / Note / PitchBend objects now
+    return list(zip(outs, midis, events))
 
 
 def predict_and_save(

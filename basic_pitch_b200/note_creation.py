@@ -7,7 +7,7 @@ module converts arguments, maps frames to seconds and assembles the MIDI object.
 from __future__ import annotations
 
 from collections import defaultdict
-from typing import Dict, List, Optional, Tuple
+from typing import Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
 
@@ -148,6 +148,78 @@ def note_events_from_arrays(res: Dict[str, np.ndarray], n_frames: int, include_p
     return events
 
 
+class NoteEventList(Sequence):
+    """The note events of one file as a read-only sequence of the reference's tuples
+    (start_s, end_s, pitch_midi, amplitude, [pitch bends]) backed by the arrays of the batch: tuples are made when an
+    element is read.  A 1 250-clip batch has ~10^5 notes and ~2 x 10^6 pitch-bend values; turning all of them into
+    Python objects costs more host time than the whole GPU pass, and most callers hand the events straight to a writer.
+    Compares equal to the equivalent list; `to_list()` materialises it."""
+
+    __slots__ = ("_st", "_en", "_pitch", "_amp", "_boff", "_flat")
+
+    def __init__(self, st, en, pitch, amp, boff, flat):
+        self._st, self._en, self._pitch, self._amp, self._boff, self._flat = st, en, pitch, amp, boff, flat
+
+    def __len__(self) -> int:
+        return len(self._st)
+
+    def _one(self, j: int) -> NoteEvent:
+        bends = None if self._flat is None else self._flat[self._boff[j] : self._boff[j + 1]].tolist()
+        return (self._st[j], self._en[j], self._pitch[j], self._amp[j], bends)
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self._one(j) for j in range(*i.indices(len(self)))]
+        n = len(self)
+        if i < 0:
+            i += n
+        if not 0 <= i < n:
+            raise IndexError("note event index out of range")
+        return self._one(i)
+
+    def __iter__(self):
+        return iter(self.to_list())
+
+    def to_list(self) -> List[NoteEvent]:
+        n = len(self)
+        if self._flat is None:
+            bends: list = [None] * n
+        else:
+            bo = self._boff.tolist()
+            fl = self._flat[bo[0] : bo[n]].tolist() if n else []
+            b0 = bo[0] if n else 0
+            bends = [fl[bo[j] - b0 : bo[j + 1] - b0] for j in range(n)]
+        return list(zip(list(self._st), list(self._en), list(self._pitch), list(self._amp), bends))
+
+    def __eq__(self, other) -> bool:
+        if isinstance(other, (list, tuple, NoteEventList)):
+            return self.to_list() == (other.to_list() if isinstance(other, NoteEventList) else list(other))
+        return NotImplemented
+
+    def __repr__(self) -> str:
+        return f"NoteEventList({self.to_list()!r})"
+
+
+def note_events_batch(arrs: Dict[str, np.ndarray], n_files: int, include_pitch_bends: bool = True,
+                      lazy: bool = True) -> List[Sequence]:
+    """`note_events_from_arrays` for every file of a batch at once (the concatenated arrays of one library call): the
+    frame -> seconds mapping and the type conversions are vectorised over all notes of the batch.  Same values and
+    element types as the per-file function (np.float64 times, np.int64 pitch, np.float32 amplitude; the pitch bends
+    are Python ints).  lazy=True returns `NoteEventList`s, lazy=False plain lists."""
+    noff = arrs["note_off"]
+    n = int(noff[n_files])
+    start, end = arrs["start"][:n], arrs["end"][:n]
+    times = model_frames_to_time(int(max(int(start.max(initial=0)), int(end.max(initial=0)))) + 1)
+    st, en = times[start], times[end]
+    pitch, amp = arrs["pitch"][:n].astype(np.int64), arrs["amp"][:n]
+    boff = arrs["bend_off"][: n + 1] if include_pitch_bends else None
+    flat = arrs["bends"] if include_pitch_bends else None
+    offs = noff[: n_files + 1].tolist()
+    out = [NoteEventList(st[a:b], en[a:b], pitch[a:b], amp[a:b], None if boff is None else boff[a : b + 1], flat)
+           for a, b in zip(offs[:-1], offs[1:])]
+    return out if lazy else [e.to_list() for e in out]
+
+
 def drop_overlapping_pitch_bends(note_events_with_pitch_bends: List[NoteEvent]) -> List[NoteEvent]:
     """reference: note_creation.py:274-286 — notes overlapping in time lose their pitch bends."""
     ev = sorted(note_events_with_pitch_bends)
@@ -158,6 +230,29 @@ def drop_overlapping_pitch_bends(note_events_with_pitch_bends: List[NoteEvent]) 
             ev[i] = ev[i][:-1] + (None,)
             ev[j] = ev[j][:-1] + (None,)
     return ev
+
+
+class LazyPrettyMIDI(pretty_midi.PrettyMIDI):
+    """The MIDI object of `note_events_to_midi`, assembled on first use.  A batch call returns one per file; most
+    callers only ever `write()` a few of them or hand them to a batch writer, so the Instrument / Note / PitchBend
+    objects (a dozen Python objects per note) are not created until `instruments` is first read."""
+
+    def __init__(self, note_events: List[NoteEvent], multiple_pitch_bends: bool = False, midi_tempo: float = 120):
+        self._pending = None
+        self._instruments: list = []
+        super().__init__(initial_tempo=midi_tempo)
+        self._pending = (note_events, multiple_pitch_bends, midi_tempo)
+
+    @property
+    def instruments(self):
+        if self._pending is not None:
+            pending, self._pending = self._pending, None
+            self._instruments = note_events_to_midi(*pending).instruments
+        return self._instruments
+
+    @instruments.setter
+    def instruments(self, value):
+        self._instruments = value
 
 
 def note_events_to_midi(note_events_with_pitch_bends: List[NoteEvent], multiple_pitch_bends: bool = False,

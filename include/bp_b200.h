@@ -174,6 +174,23 @@ int64_t bp_model_chunk_windows(const bp_model_t* m);
  * 8-channel activations (bp_debug_activation which = 1). */
 int bp_model_set_path(bp_model_t* m, int path);
 
+/* `bp_transcribe_host` for audio that is NOT packed: file i is audio[i][0 .. n_samples[i]) in ordinary (pageable) host
+ * memory — what a caller holding one array per file has (reference: basic_pitch/inference.py:509-604, `predict_and_save`
+ * loops `predict` over `audio_path_list`).  The library gathers the files sub-batch by sub-batch into pinned staging with
+ * a few host threads, so that the gather and upload of sub-batch k+1 overlap the kernels of k, and streams the
+ * posteriorgrams of each finished sub-batch back (h_note / h_onset / h_contour, row-major [total_frames][88 | 88 | 264],
+ * any may be NULL) while later sub-batches compute; buffers from bp_host_alloc make that copy asynchronous.
+ * Everything else (h_frame_off, notes, errors) as bp_transcribe_host. */
+int bp_transcribe_files_host(bp_model_t* m, const float* const* audio, const int64_t* n_samples, int32_t n_files,
+                             const bp_decode_params_t* params, float* h_note, float* h_onset, float* h_contour,
+                             int64_t* h_frame_off, bp_notes_t* notes);
+/* Page-locked host memory for the outputs of the host entry points (cudaHostAlloc / cudaFreeHost); NULL on failure. */
+void* bp_host_alloc(size_t bytes);
+void bp_host_free(void* p);
+/* After a BP_E_CAPACITY failure of a decode / transcribe call on this thread: the capacities that call needed
+ * (0 = that one was sufficient), so that the caller can retry without parsing the error text. */
+void bp_last_required(int64_t* note_capacity, int64_t* bend_capacity);
+
 /* Host-only (no GPU needed): builds the tensor-core plan (split-bf16 Toeplitz weight tiles and the per-group MMA
  * programs, csrc/tc_conv.cu) of the contour conv (which = 0, w = [8][8][3][39]), the onset conv (which = 1,
  * w = [32][8][5][5]) or the note conv (which = 2, w = [32][1][7][7]) so that tests can emulate the program on the CPU.  sizes[4] = {n_tiles, n_steps, n_uses,

@@ -460,3 +460,46 @@ def test_two_models_with_different_weights_do_not_interfere(model, weights_np, t
         np.testing.assert_array_equal(a0[k], a1[k])
         np.testing.assert_array_equal(b0[k], b1[k])
     assert np.abs(a0["note"] - b0["note"]).max() > 1e-3 and np.abs(a0["onset"] - b0["onset"]).max() > 1e-3
+
+
+@pytest.mark.gpu
+def test_transcribe_files_host_equals_packed_entry_point(model):
+    """bp_transcribe_files_host (one pointer per file, pageable memory, gathered and streamed per sub-batch by the library)
+    returns bit-identical posteriorgrams and notes as bp_transcribe_host on the packed batch."""
+    import ctypes as C
+
+    from basic_pitch_b200 import _lib as L, synth
+
+    lib = model._lib
+    rng = np.random.default_rng(5)
+    clips = [synth.tones_clip(float(rng.uniform(0.3, 7.0)), seed=40 + i) for i in range(23)] + [np.zeros(0, np.float32)]
+    clips += [synth.tones_clip(31.0, seed=99)]
+    n = len(clips)
+    flat, offs = model._pack_audio(clips)
+    frames = [int(lib.bp_num_frames(len(c))) for c in clips]
+    total = sum(frames)
+    p = model._params(0.5, 0.3, 11, 11, True, True, True, 0, 88)
+
+    def run(files_api):
+        note, onset = np.zeros((total, 88), np.float32), np.zeros((total, 88), np.float32)
+        contour = np.zeros((total, 264), np.float32)
+        foff = np.zeros(n + 1, np.int64)
+        nt, arrs = model._alloc_notes(n, 4 * total, 64 * total)
+        if files_api:
+            ptrs = (C.c_void_p * n)(*[c.ctypes.data for c in clips])
+            lens = np.array([len(c) for c in clips], np.int64)
+            lib.bp_transcribe_files_host(model.handle, ptrs, lens.ctypes.data, n, C.byref(p), note.ctypes.data,
+                                         onset.ctypes.data, contour.ctypes.data, foff.ctypes.data, C.byref(nt))
+        else:
+            lib.bp_transcribe_host(model.handle, flat.ctypes.data, offs.ctypes.data, n, C.byref(p), note.ctypes.data,
+                                   onset.ctypes.data, contour.ctypes.data, foff.ctypes.data, C.byref(nt))
+        k = int(arrs["note_off"][n])
+        return note, onset, contour, foff, {a: arrs[a][:k].copy() for a in ("start", "end", "pitch", "amp")}, arrs["note_off"].copy()
+
+    a, b = run(False), run(True)
+    for x, y in zip(a[:4], b[:4]):
+        np.testing.assert_array_equal(x, y)
+    for key in a[4]:
+        np.testing.assert_array_equal(a[4][key], b[4][key])
+    np.testing.assert_array_equal(a[5], b[5])
+    assert int(a[5][n]) > 50
