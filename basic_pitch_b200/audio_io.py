@@ -1,4 +1,5 @@
-"""Audio file -> mono float32 at 22 050 Hz (host side, in front of the hot path).
+"""Audio file -> mono float32 at 22 050 Hz, in front of the hot path: `load_audio` on the host (NumPy / SciPy),
+`load_audio_device` with the conversion, down-mix and resampling on the GPU (csrc/ingest.cu, same filter).
 
 Stands in for `librosa.load(path, sr=22050, mono=True)` (reference: basic_pitch/inference.py:239).
 WAV files are decoded with scipy; other containers need `soundfile` (optional).  Files that are not
@@ -53,6 +54,37 @@ def resample(x: np.ndarray, sr_in: int, sr_out: int = AUDIO_SAMPLE_RATE) -> np.n
     up, down = int(sr_out) // g, int(sr_in) // g
     y = scipy.signal.resample_poly(x.astype(np.float64), up, down, window=_resample_filter(up, down))
     return y.astype(np.float32)
+
+
+_PCM_FORMATS = {np.dtype(np.float32): 0, np.dtype(np.int16): 1, np.dtype(np.int32): 2, np.dtype(np.uint8): 3}
+
+
+def read_pcm(path: Union[str, pathlib.Path]) -> Tuple[np.ndarray, int]:
+    """Decode a file to its stored samples — (n,) or (n, channels) in one of the dtypes the device ingest converts
+    itself (float32, int16, int32, uint8) — plus the sample rate."""
+    try:
+        from scipy.io import wavfile
+
+        sr, x = wavfile.read(str(path))
+        x = np.asarray(x)
+        if x.dtype not in _PCM_FORMATS:  # e.g. float64 WAV
+            x = _to_float32(x)
+        return x, int(sr)
+    except Exception:
+        x, sr = read_audio(path)
+        return x, sr
+
+
+def load_audio_device(path: Union[str, pathlib.Path], model) -> Tuple[np.ndarray, int]:
+    """`load_audio(path, 22050, mono=True)` with the sample conversion, down-mix and resampling done on the GPU
+    (csrc/ingest.cu through `bp_load_pcm_host`): the file crosses PCIe as the PCM it was stored as."""
+    x, file_sr = read_pcm(path)
+    x = np.ascontiguousarray(x)
+    n, ch = (x.shape[0], 1) if x.ndim == 1 else x.shape
+    lib = model._lib
+    out = np.empty(int(lib.bp_resampled_length(n, file_sr)), np.float32)
+    lib.bp_load_pcm_host(model.handle, x.ctypes.data, _PCM_FORMATS[x.dtype], n, ch, file_sr, out.ctypes.data)
+    return out, AUDIO_SAMPLE_RATE
 
 
 def read_audio(path: Union[str, pathlib.Path]) -> Tuple[np.ndarray, int]:

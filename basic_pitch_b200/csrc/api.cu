@@ -25,6 +25,12 @@ int fail(int code, const std::string& msg) {
   return code;
 }
 
+}  // namespace
+namespace bp {
+int writer_fail(int code, const std::string& msg) { return fail(code, msg); }  // writers.cu reports through bp_last_error
+}
+namespace {
+
 #define CK(call)                                                                                         \
   do {                                                                                                   \
     cudaError_t e_ = (call);                                                                             \
@@ -159,6 +165,7 @@ struct bp_model {
   DevBuf<UnwrapDesc> udesc;
   // staging for the host entry points
   DevBuf<float> st_audio, st_note, st_onset, st_contour;
+  DevBuf<unsigned char> st_pcm;  // bp_load_pcm_host
   // bp_transcribe_files_host: pinned gather buffers (one sub-batch of audio each), the device->host stream of the
   // posteriorgrams and its events
   float* gather[3] = {nullptr, nullptr, nullptr};
@@ -641,7 +648,7 @@ void bp_model_destroy(bp_model_t* m) {
   m->i_note.release(); m->i_onset.release(); m->i_contour.release(); m->u_note.release(); m->u_onset.release();
   m->u_contour.release();
   m->wdesc.release(); m->udesc.release(); m->st_audio.release(); m->st_note.release(); m->st_onset.release();
-  m->st_contour.release(); m->d_frame_off.release(); m->d_slot_off.release(); m->d_note_base.release();
+  m->st_contour.release(); m->st_pcm.release(); m->d_frame_off.release(); m->d_slot_off.release(); m->d_note_base.release();
   m->energy.release(); m->d_amp.release(); m->candbits.release(); m->max_onset.release(); m->max_fd.release();
   m->note_count.release(); m->slot_start.release(); m->slot_end.release(); m->slot_pitch.release();
   m->overflow.release(); m->d_note_off.release(); m->d_start.release(); m->d_end.release(); m->d_pitch.release();
@@ -1397,6 +1404,53 @@ int bp_transcribe_files_host(bp_model_t* m, const float* const* audio, const int
   CK(e1);
   CK(cudaStreamSynchronize(st));
   return BP_OK;
+}
+
+int64_t bp_resampled_length(int64_t n_frames, int32_t sample_rate) { return ingest_output_length(n_frames, sample_rate); }
+
+int bp_load_pcm_device(bp_model_t* m, const void* d_pcm, int32_t sample_format, int64_t n_frames, int32_t channels,
+                       int32_t sample_rate, float* d_audio, void* stream) {
+  if (!m || n_frames < 0) return fail(BP_E_INVALID, "bp_load_pcm_device: bad argument");
+  if (n_frames == 0) return BP_OK;
+  if (!d_pcm || !d_audio) return fail(BP_E_INVALID, "bp_load_pcm_device: null buffer");
+  DeviceGuard g(m->device);
+  const int rc = launch_ingest(m->device, d_pcm, sample_format, n_frames, channels, sample_rate, d_audio,
+                               static_cast<cudaStream_t>(stream));
+  if (rc == -2)
+    return fail(BP_E_INVALID, "bp_load_pcm_device: unsupported sample format / channel count / sample rate (format 0..3, "
+                              "channels >= 1, rate ratio to 22 050 Hz below ~100)");
+  if (rc) return fail(BP_E_CUDA, std::string("bp_load_pcm_device: ") + cudaGetErrorString(cudaGetLastError()));
+  m->launches += 1;
+  return BP_OK;
+}
+
+int bp_load_pcm_host(bp_model_t* m, const void* h_pcm, int32_t sample_format, int64_t n_frames, int32_t channels,
+                     int32_t sample_rate, float* h_audio) {
+  if (!m || n_frames < 0 || channels < 1 || sample_format < 0 || sample_format > 3)
+    return fail(BP_E_INVALID, "bp_load_pcm_host: bad argument");
+  if (n_frames == 0) return BP_OK;
+  if (!h_pcm || !h_audio) return fail(BP_E_INVALID, "bp_load_pcm_host: null buffer");
+  DeviceGuard g(m->device);
+  cudaStream_t st = m->stream;
+  static const int kBytes[4] = {4, 2, 4, 1};
+  const size_t in_bytes = (size_t)n_frames * channels * kBytes[sample_format];
+  const int64_t n_out = ingest_output_length(n_frames, sample_rate);
+  CK(cudaStreamSynchronize(st));
+  CK(m->st_pcm.reserve(in_bytes));
+  CK(m->st_audio.reserve((size_t)n_out));
+  CK(cudaMemcpyAsync(m->st_pcm.p, h_pcm, in_bytes, cudaMemcpyHostToDevice, st));
+  const int rc = bp_load_pcm_device(m, m->st_pcm.p, sample_format, n_frames, channels, sample_rate, m->st_audio.p, st);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(h_audio, m->st_audio.p, sizeof(float) * (size_t)n_out, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return BP_OK;
+}
+
+int64_t bp_debug_resample_filter(int32_t up, int32_t down, double* taps, int64_t capacity) {
+  if (up < 1 || down < 1) return fail(BP_E_INVALID, "bp_debug_resample_filter: bad argument"), -1;
+  const std::vector<double> h = ingest_filter(up, down);
+  if (taps && capacity >= (int64_t)h.size()) std::memcpy(taps, h.data(), h.size() * sizeof(double));
+  return (int64_t)h.size();
 }
 
 int bp_debug_tc_plan(int which, const float* w, int32_t* sizes, uint16_t* tiles, int32_t* tile_seq, uint32_t* slot_words,

@@ -7,6 +7,7 @@ namespace bp {
 
 // ---- geometry (reference: basic_pitch/constants.py:25-47) -------------
 constexpr int kWinSamples = 43844;
+constexpr int kSampleRate = 22050;  // reference: basic_pitch/constants.py AUDIO_SAMPLE_RATE
 constexpr int kFrames = 172;
 constexpr int kCqtBins = 309;
 constexpr int kContourBins = 264;

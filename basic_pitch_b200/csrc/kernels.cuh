@@ -134,6 +134,12 @@ void launch_pm_to_rows(const float* pm, long long stride, long long src_frame0, 
 void launch_cm_to_rows(const float* cm, long long stride, long long src_frame0, long long n_frames, float* rows,
                        cudaStream_t st);
 
+// ---- ingest.cu: PCM of any rate / channel count -> mono float32 at 22 050 Hz (format: 0 f32, 1 s16, 2 s32, 3 u8) ----
+long long ingest_output_length(long long n_frames, int sample_rate);
+std::vector<double> ingest_filter(int up, int down);  // host-only: the low-pass design (unit DC gain)
+int launch_ingest(int device, const void* d_pcm, int format, long long n_frames, int channels, int sample_rate, float* d_out,
+                  cudaStream_t st);  // 0 ok, -1 CUDA error, -2 unsupported argument
+
 // ---- decode.cu ----------------------------------------------------------------------------------
 struct DecodeParamsDev {
   double onset_thresh, frame_thresh;

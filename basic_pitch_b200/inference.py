@@ -22,7 +22,7 @@ import numpy as np
 
 from . import ICASSP_2022_MODEL_PATH, _lib, weights
 from . import note_creation as infer
-from .audio_io import load_audio
+from .audio_io import load_audio, load_audio_device
 from .constants import (
     ANNOTATIONS_FPS,
     AUDIO_N_SAMPLES,
@@ -431,6 +431,90 @@ def run_inference(audio_path: Union[pathlib.Path, str], model_or_model_path: Uni
     return out
 
 
+def run_inference_stream(audio_blocks: Iterable[np.ndarray], model_or_model_path: Union["Model", pathlib.Path, str] = ICASSP_2022_MODEL_PATH,
+                         windows_per_step: int = 64) -> Iterable[Dict[str, np.ndarray]]:
+    """Bounded-memory inference for long recordings (reference: README.md:196-198 — "we recommend streaming the audio of
+    the file, processing windows of audio at a time").
+
+    audio_blocks: an iterable of consecutive mono 22 050 Hz float blocks of any sizes (e.g. a file read piecewise).
+    Yields dicts {"note", "onset", "contour"} of consecutive unwrapped frames; concatenated they equal
+    `run_inference(whole_file)` bit for bit.  At any time the host holds at most `windows_per_step` windows of audio
+    (~1.6 s each) plus two windows of held-back frames, the device one step of windows: memory does not grow with the
+    length of the recording.  (The final trim of `unwrap_output`, inference.py:247-279, can reach two windows back, so
+    the frames of the last two windows are yielded when the stream ends.)"""
+    model = model_or_model_path if isinstance(model_or_model_path, Model) else default_model(model_or_model_path)
+    n_overlap = DEFAULT_OVERLAPPING_FRAMES * FFT_HOP
+    hop = AUDIO_N_SAMPLES - n_overlap
+    n_olap = DEFAULT_OVERLAPPING_FRAMES // 2
+    per_window = AUDIO_WINDOW_LENGTH * ANNOTATIONS_FPS - DEFAULT_OVERLAPPING_FRAMES  # 142 kept frames per window
+    buf = np.zeros(n_overlap // 2, _F32)  # the reference prepends overlap_len / 2 zeros (inference.py:241)
+    total = 0  # samples of the recording seen so far
+    emitted = 0  # frames yielded so far
+    held: List[Dict[str, np.ndarray]] = []  # frames of the newest windows, not yet safe to yield
+
+    def run(windows: np.ndarray) -> None:
+        out = model.predict(windows)
+        for k in range(windows.shape[0]):
+            held.append({key: out[key][k, n_olap : 172 - n_olap] for key in ("note", "onset", "contour")})
+
+    def drain(keep: int):
+        nonlocal emitted
+        while len(held) > keep:
+            w = held.pop(0)
+            emitted += per_window
+            yield w
+
+    for block in audio_blocks:
+        block = np.asarray(block, dtype=_F32).reshape(-1)
+        total += block.shape[0]
+        buf = np.concatenate([buf, block])
+        n_ready = (buf.shape[0] - AUDIO_N_SAMPLES) // hop + 1 if buf.shape[0] >= AUDIO_N_SAMPLES else 0
+        while n_ready > 0:
+            n = min(n_ready, windows_per_step)
+            idx = np.arange(n)[:, None] * hop + np.arange(AUDIO_N_SAMPLES)[None, :]
+            run(buf[idx])
+            buf = buf[n * hop :]
+            n_ready -= n
+            yield from drain(2)
+    # end of stream: the windows that start inside the remaining samples, zero-padded (inference.py:194-219)
+    tail = []
+    for i in range(0, buf.shape[0], hop):
+        w = buf[i : i + AUDIO_N_SAMPLES]
+        tail.append(np.pad(w, (0, AUDIO_N_SAMPLES - w.shape[0])))
+    for c0 in range(0, len(tail), windows_per_step):
+        run(np.stack(tail[c0 : c0 + windows_per_step]))
+    # the trim of unwrap_output: keep int(n_samples / hop * frames_per_window) frames in all
+    n_final = int(total / hop * per_window)
+    for w in held:
+        take = max(0, min(per_window, n_final - emitted))
+        emitted += take
+        if take > 0:
+            yield {k: v[:take] for k, v in w.items()}
+    held.clear()
+
+
+def predict_stream(audio_blocks: Iterable[np.ndarray], model_or_model_path: Union["Model", pathlib.Path, str] = ICASSP_2022_MODEL_PATH,
+                   onset_threshold: float = DEFAULT_ONSET_THRESHOLD, frame_threshold: float = DEFAULT_FRAME_THRESHOLD,
+                   minimum_note_length: float = DEFAULT_MINIMUM_NOTE_LENGTH_MS, minimum_frequency: Optional[float] = None,
+                   maximum_frequency: Optional[float] = None, multiple_pitch_bends: bool = False, melodia_trick: bool = True,
+                   midi_tempo: float = DEFAULT_MINIMUM_MIDI_TEMPO, windows_per_step: int = 64):
+    """`predict` for a recording delivered block by block: the model runs with bounded memory (`run_inference_stream`), the
+    posteriorgrams (1.76 KB per frame, 86 frames per second) are collected on the host and decoded once — the note
+    decode is global over a file (reference: note_creation.py:409-509).  Returns (model_output, midi_data, note_events)."""
+    model = model_or_model_path if isinstance(model_or_model_path, Model) else default_model(model_or_model_path)
+    parts = list(run_inference_stream(audio_blocks, model, windows_per_step))
+    keys = ("note", "onset", "contour")
+    widths = {"note": N_FREQ_BINS_NOTES, "onset": N_FREQ_BINS_NOTES, "contour": N_FREQ_BINS_CONTOURS}
+    model_output = {k: (np.concatenate([p[k] for p in parts]) if parts else np.zeros((0, widths[k]), _F32)) for k in keys}
+    min_note_len = int(np.round(minimum_note_length / 1000 * (AUDIO_SAMPLE_RATE / FFT_HOP)))
+    midi_data, note_events = infer.model_output_to_notes(
+        model_output, onset_thresh=onset_threshold, frame_thresh=frame_threshold, min_note_len=min_note_len,
+        min_freq=minimum_frequency, max_freq=maximum_frequency, multiple_pitch_bends=multiple_pitch_bends,
+        melodia_trick=melodia_trick, midi_tempo=midi_tempo, model=model,
+    )
+    return model_output, midi_data, note_events
+
+
 class OutputExtensions(enum.Enum):
     MIDI = "mid"
     MODEL_OUTPUT_NPZ = "npz"
@@ -501,7 +585,7 @@ def predict(
     """reference: inference.py:431-506 -> (model_output, midi_data, note_events)."""
     print(f"Predicting MIDI for {audio_path}...")
     model = model_or_model_path if isinstance(model_or_model_path, Model) else default_model(model_or_model_path)
-    audio, _ = load_audio(audio_path, sr=AUDIO_SAMPLE_RATE, mono=True)
+    audio, _ = load_audio_device(audio_path, model)  # decode on the host, convert / down-mix / resample on the GPU
     min_note_len = int(np.round(minimum_note_length / 1000 * (AUDIO_SAMPLE_RATE / FFT_HOP)))
     lo, hi = infer.frequency_to_column_range(minimum_frequency, maximum_frequency)
     outs, res, frames = model.transcribe_arrays(
@@ -550,7 +634,7 @@ def predict_batch(
     objects `LazyPrettyMIDI`s: both turn into the reference's Python objects when first read; lazy=False builds
     everything before returning."""
     model = model_or_model_path if isinstance(model_or_model_path, Model) else default_model(model_or_model_path)
-    audios = [a if isinstance(a, np.ndarray) else load_audio(a, sr=AUDIO_SAMPLE_RATE, mono=True)[0] for a in audio]
+    audios = [a if isinstance(a, np.ndarray) else load_audio_device(a, model)[0] for a in audio]
     min_note_len = int(np.round(minimum_note_length / 1000 * (AUDIO_SAMPLE_RATE / FFT_HOP)))
     lo, hi = infer.frequency_to_column_range(minimum_frequency, maximum_frequency)
     outs, arrs, frames = model.transcribe_arrays(
@@ -594,13 +678,67 @@ def predict_and_save(
     sonification_samplerate: int = DEFAULT_SONIFICATION_SAMPLERATE,
     midi_tempo: float = DEFAULT_MINIMUM_MIDI_TEMPO,
 ) -> None:
-    """reference: inference.py:509-604 — same files, names and failure behaviour (print, then re-raise)."""
+    """reference: inference.py:509-604 — same files, names and failure behaviour (print, then re-raise).
+
+    Several files without `debug_file` go through the batch path: one device pass per `BATCH_FILES` files
+    (`predict_batch`: GPU ingest, one library call) and one `bp_write_note_files` call for their MIDI / CSV files
+    (csrc/writers.cu) instead of a Python loop over files and notes."""
 
     def _saved(kind: str, path) -> None:
         print(f"  ✅ Saved {kind.lower().replace('_', ' ')} to {path}")
 
     def _failed(kind: str, path) -> None:
         print(f"\n🚨 Failed to save {kind.lower().replace('_', ' ')} to {path} \n")
+
+    paths = list(audio_path_list)
+    if len(paths) > 1 and debug_file is None:
+        model = model_or_model_path if isinstance(model_or_model_path, Model) else default_model(model_or_model_path)
+        BATCH_FILES = 64
+        for c0 in range(0, len(paths), BATCH_FILES):
+            chunk = paths[c0 : c0 + BATCH_FILES]
+            for q in chunk:
+                print(f"\nPredicting MIDI for {q}...")
+            results = predict_batch([pathlib.Path(q) for q in chunk], model, onset_threshold, frame_threshold, minimum_note_length,
+                                    minimum_frequency, maximum_frequency, multiple_pitch_bends, melodia_trick, midi_tempo)
+            midi_paths: List[Optional[pathlib.Path]] = [None] * len(chunk)
+            csv_paths: List[Optional[pathlib.Path]] = [None] * len(chunk)
+            for i, (audio_path, (model_output, midi_data, _events)) in enumerate(zip(chunk, results)):
+                if save_model_outputs:
+                    path = build_output_path(audio_path, output_directory, OutputExtensions.MODEL_OUTPUT_NPZ)
+                    try:
+                        np.savez(path, basic_pitch_model_output=model_output)
+                        _saved(OutputExtensions.MODEL_OUTPUT_NPZ.name, path)
+                    except Exception:
+                        _failed(OutputExtensions.MODEL_OUTPUT_NPZ.name, path)
+                        raise
+                if save_midi:
+                    midi_paths[i] = build_output_path(audio_path, output_directory, OutputExtensions.MIDI)
+                if sonify_midi:
+                    path = build_output_path(audio_path, output_directory, OutputExtensions.MIDI_SONIFICATION)
+                    try:
+                        infer.sonify_midi(midi_data, path, sr=sonification_samplerate)
+                        _saved(OutputExtensions.MIDI_SONIFICATION.name, path)
+                    except Exception:
+                        _failed(OutputExtensions.MIDI_SONIFICATION.name, path)
+                        raise
+                if save_notes:
+                    csv_paths[i] = build_output_path(audio_path, output_directory, OutputExtensions.NOTE_EVENTS)
+            if save_midi or save_notes:
+                try:
+                    infer.write_note_files([r[2] for r in results], midi_paths if save_midi else None,
+                                           csv_paths if save_notes else None, multiple_pitch_bends, midi_tempo)
+                except Exception:
+                    for kind, plist in ((OutputExtensions.MIDI, midi_paths), (OutputExtensions.NOTE_EVENTS, csv_paths)):
+                        for path in plist:
+                            if path is not None and not path.exists():
+                                _failed(kind.name, path)
+                    raise
+                for mp, cp in zip(midi_paths, csv_paths):
+                    if mp is not None:
+                        _saved(OutputExtensions.MIDI.name, mp)
+                    if cp is not None:
+                        _saved(OutputExtensions.NOTE_EVENTS.name, cp)
+        return
 
     for audio_path in audio_path_list:
         print("")

@@ -68,6 +68,45 @@ class PrettyMIDI:
         ends = [n.end for i in self.instruments for n in i.notes] + [b.time for i in self.instruments for b in i.pitch_bends]
         return max(ends) if ends else 0.0
 
+    def synthesize(self, fs: int = 44100, wave=None):
+        """Additive synthesis of the notes (what `pretty_midi.PrettyMIDI.synthesize` is used for by the reference's
+        sonify_midi, note_creation.py:119-128): every note is `wave` (default np.sin) at its pitch, bent by the
+        instrument's pitch-bend events (+-2 semitones full scale), scaled by velocity / 127 with 10 ms linear fades; the
+        sum is normalised to a peak of 1.  A behavioural stand-in: not sample-identical to pretty_midi."""
+        import numpy as np
+
+        wave = np.sin if wave is None else wave
+        end_time = self.get_end_time()
+        out = np.zeros(int(fs * (end_time + 1)))
+        if not self.instruments or out.size == 0:
+            return np.array([]) if not self.instruments else out
+        for inst in self.instruments:
+            if inst.is_drum:
+                continue
+            bends = sorted(inst.pitch_bends, key=lambda b: b.time)
+            bt = np.array([b.time for b in bends])
+            bv = np.array([b.pitch for b in bends], dtype=np.float64) * (2.0 / 8192.0)  # semitones
+            for n in inst.notes:
+                a, b = int(fs * n.start), int(fs * n.end)
+                if b <= a:
+                    continue
+                t = np.arange(a, b) / fs
+                semis = np.full(b - a, float(n.pitch))
+                if len(bt):  # zero-order hold of the latest bend event
+                    k = np.searchsorted(bt, t, side="right") - 1
+                    semis = semis + np.where(k >= 0, bv[np.maximum(k, 0)], 0.0)
+                freq = 440.0 * 2.0 ** ((semis - 69.0) / 12.0)
+                phase = 2.0 * np.pi * np.cumsum(freq) / fs
+                env = np.ones(b - a)
+                fade = min(int(0.01 * fs), (b - a) // 2)
+                if fade > 0:
+                    ramp = np.linspace(0.0, 1.0, fade, endpoint=False)
+                    env[:fade] = ramp
+                    env[-fade:] = ramp[::-1]
+                out[a:b] += wave(phase) * env * (n.velocity / 127.0)
+        peak = np.abs(out).max()
+        return out / peak if peak > 0 else out
+
     def write(self, filename: str) -> None:
         tracks = []
         tempo_us = int(round(6e7 / self.initial_tempo))

@@ -6,6 +6,7 @@ module converts arguments, maps frames to seconds and assembles the MIDI object.
 """
 from __future__ import annotations
 
+import os
 from collections import defaultdict
 from typing import Dict, List, Optional, Sequence, Tuple
 
@@ -220,6 +221,57 @@ def note_events_batch(arrs: Dict[str, np.ndarray], n_files: int, include_pitch_b
     return out if lazy else [e.to_list() for e in out]
 
 
+def write_note_files(event_lists: Sequence[Sequence], midi_paths: Optional[Sequence], csv_paths: Optional[Sequence],
+                     multiple_pitch_bends: bool = False, midi_tempo: float = 120, n_threads: int = 0) -> None:
+    """One MIDI file and / or one note-event CSV per file of a batch in a single library call (`bp_write_note_files`,
+    csrc/writers.cu: host threads over the files, no per-note Python objects).  Same bytes as
+    `note_events_to_midi(events, ...).write(path)` with this package's MIDI writer and `inference.save_note_events`.
+    event_lists: one `NoteEventList` (or list of event tuples) per file; paths: one per file, None entries are skipped."""
+    import ctypes as C
+
+    from . import _lib
+
+    n_files = len(event_lists)
+    per = []
+    for ev in event_lists:
+        if isinstance(ev, NoteEventList):
+            n = len(ev)
+            if ev._flat is None or n == 0:
+                boff, flat = np.zeros(n + 1, np.int64), np.zeros(0, np.int32)
+            else:
+                b0, b1 = int(ev._boff[0]), int(ev._boff[n])
+                boff, flat = ev._boff.astype(np.int64) - b0, ev._flat[b0:b1]
+            per.append((ev._st, ev._en, ev._pitch, ev._amp, boff, flat))
+        else:
+            ev = list(ev)
+            bl = [list(e[4]) if e[4] else [] for e in ev]
+            boff = np.zeros(len(ev) + 1, np.int64)
+            boff[1:] = np.cumsum([len(b) for b in bl])
+            per.append((np.array([e[0] for e in ev], np.float64), np.array([e[1] for e in ev], np.float64),
+                        np.array([e[2] for e in ev], np.int64), np.array([e[3] for e in ev], np.float32), boff,
+                        np.array([x for b in bl for x in b], np.int32)))
+    cat = lambda k, dt: np.ascontiguousarray(np.concatenate([p[k] for p in per]) if per else np.zeros(0), dtype=dt)  # noqa: E731
+    noff = np.zeros(n_files + 1, np.int32)
+    noff[1:] = np.cumsum([len(p[0]) for p in per])
+    st, en, pitch, amp, flat = cat(0, np.float64), cat(1, np.float64), cat(2, np.int32), cat(3, np.float32), cat(5, np.int32)
+    boff = np.zeros(int(noff[-1]) + 1, np.int32)
+    base = 0
+    for i, p in enumerate(per):
+        a, b = int(noff[i]), int(noff[i + 1])
+        boff[a : b + 1] = p[4] + base
+        base += int(p[4][-1])
+
+    def c_paths(paths):
+        if paths is None:
+            return None
+        assert len(paths) == n_files
+        return (C.c_char_p * max(n_files, 1))(*[None if q is None else os.fsencode(str(q)) for q in paths])
+
+    _lib.load().bp_write_note_files(n_files, c_paths(midi_paths), c_paths(csv_paths), noff.ctypes.data, st.ctypes.data,
+                                    en.ctypes.data, pitch.ctypes.data, amp.ctypes.data, boff.ctypes.data, flat.ctypes.data,
+                                    int(bool(multiple_pitch_bends)), float(midi_tempo), int(n_threads))
+
+
 def drop_overlapping_pitch_bends(note_events_with_pitch_bends: List[NoteEvent]) -> List[NoteEvent]:
     """reference: note_creation.py:274-286 — notes overlapping in time lose their pitch bends."""
     ev = sorted(note_events_with_pitch_bends)
@@ -282,9 +334,8 @@ def note_events_to_midi(note_events_with_pitch_bends: List[NoteEvent], multiple_
 
 
 def sonify_midi(midi, save_path, sr: Optional[int] = 44100) -> None:
-    """reference: note_creation.py:119-128 — needs the real pretty_midi (synthesis is off the hot path)."""
-    if not hasattr(midi, "synthesize"):
-        raise NotImplementedError("sonify_midi needs the `pretty_midi` package (MIDI synthesis is outside the hot path)")
+    """reference: note_creation.py:119-128 — `midi.synthesize(sr)` written as a WAV.  With the real `pretty_midi` that is
+    its synthesiser; the bundled `midi.PrettyMIDI` (and `LazyPrettyMIDI`) has an additive stand-in of the same shape."""
     from scipy.io import wavfile
 
     wavfile.write(save_path, sr, midi.synthesize(sr))
@@ -294,8 +345,39 @@ SONIFY_FS = 3000  # reference: note_creation.py:41
 
 
 def sonify_salience(gram, semitone_resolution: float, save_path: Optional[str] = None, thresh: float = 0.2):
-    """reference: note_creation.py:131-165 — needs `mir_eval` / `resampy` (sonification is outside the hot path)."""
-    raise NotImplementedError("sonify_salience needs the `mir_eval` and `resampy` packages (sonification is outside the hot path)")
+    """reference: note_creation.py:131-165 -> (audio at SONIFY_FS, SONIFY_FS).  gram: (n_freqs, n_times) salience in 0..1,
+    log-spaced from ANNOTATIONS_BASE_FREQUENCY with `semitone_resolution` bins per semitone; values below `thresh` are
+    zeroed IN PLACE like the reference.  The reference calls mir_eval.sonify.time_frequency and resampy; neither is a
+    dependency here, so this restates what they do for this call: one sinusoid per frequency bin below SONIFY_FS / 2,
+    amplitude = the bin's salience held from frame to frame (nearest frame time), summed and peak-normalised; the saved
+    file is resampled to 44.1 kHz with this package's Kaiser polyphase resampler.  Not sample-identical to mir_eval."""
+    gram = np.asarray(gram)
+    n_bins = int(ANNOTATIONS_N_SEMITONES * semitone_resolution)
+    freqs = ANNOTATIONS_BASE_FREQUENCY * 2.0 ** (np.arange(n_bins) / (12.0 * semitone_resolution))
+    max_freq_idx = int(np.where(freqs > SONIFY_FS / 2)[0][0])
+    hop = AUDIO_N_SAMPLES / ANNOT_N_FRAMES  # "THIS IS THE CORRECT HOP" (reference :154)
+    times = (np.arange(gram.shape[1]) * hop).astype(int) / float(AUDIO_SAMPLE_RATE)
+    gram[gram < thresh] = 0
+    g = gram[:max_freq_idx, :]
+    n_samples = int(times[-1] * SONIFY_FS) if len(times) else 0
+    y = np.zeros(n_samples)
+    if n_samples:
+        t = np.arange(n_samples) / SONIFY_FS
+        # nearest frame of every output sample (mir_eval interpolates the gram with kind="nearest")
+        mid = 0.5 * (times[1:] + times[:-1])
+        frame = np.searchsorted(mid, t, side="right")
+        for k in np.flatnonzero(g.any(axis=1)):
+            y += np.sin(2.0 * np.pi * freqs[k] * t) * g[k, frame]
+        peak = np.abs(y).max()
+        if peak > 0:
+            y /= peak
+    if save_path:
+        from scipy.io import wavfile
+
+        from .audio_io import resample
+
+        wavfile.write(save_path, 44100, resample(y, SONIFY_FS, 44100))
+    return y, SONIFY_FS
 
 
 def get_pitch_bends(contours, note_events, n_bins_tolerance: int = 25, model=None):
@@ -323,7 +405,8 @@ def get_infered_onsets(onsets, frames, n_diff: int = 2, model=None):
 
 
 __all__ = [
-    "model_output_to_notes", "output_to_notes_polyphonic", "note_events_to_midi", "drop_overlapping_pitch_bends",
+    "model_output_to_notes", "output_to_notes_polyphonic", "note_events_to_midi", "write_note_files", "note_events_batch",
+    "NoteEventList", "LazyPrettyMIDI", "drop_overlapping_pitch_bends",
     "model_frames_to_time", "constrain_frequency", "midi_pitch_to_contour_bin", "sonify_midi", "sonify_salience",
     "get_pitch_bends", "get_infered_onsets", "SONIFY_FS",
     "MIDI_OFFSET", "MAX_FREQ_IDX", "N_FREQ_BINS_CONTOURS",

@@ -191,6 +191,35 @@ void bp_host_free(void* p);
  * (0 = that one was sufficient), so that the caller can retry without parsing the error text. */
 void bp_last_required(int64_t* note_capacity, int64_t* bend_capacity);
 
+/* Audio ingest — `librosa.load(path, sr=22050, mono=True)` minus the container decode (reference:
+ * basic_pitch/inference.py:239): interleaved PCM frames of `channels` channels at `sample_rate` Hz -> mono float32 at
+ * 22 050 Hz.  sample_format: 0 float32, 1 int16 (/ 2^15), 2 int32 (/ 2^31; 24-bit WAV left-justified), 3 uint8
+ * ((x - 128) / 128).  Channels are averaged in float32; other rates go through a Kaiser-windowed polyphase FIR (pass
+ * band 0.913 x Nyquist of the lower rate, 125 dB stop band) applied like scipy.signal.resample_poly.  The output has
+ * bp_resampled_length(n_frames, sample_rate) = ceil(n_frames * 22050 / sample_rate) samples.
+ * _device: PCM and output in device memory, asynchronous on `stream` — the output can feed bp_transcribe_device directly;
+ * _host: both in host memory (the PCM crosses PCIe as stored: 2 bytes per sample for 16-bit audio). */
+int64_t bp_resampled_length(int64_t n_frames, int32_t sample_rate);
+int bp_load_pcm_device(bp_model_t* m, const void* d_pcm, int32_t sample_format, int64_t n_frames, int32_t channels,
+                       int32_t sample_rate, float* d_audio, void* stream);
+int bp_load_pcm_host(bp_model_t* m, const void* h_pcm, int32_t sample_format, int64_t n_frames, int32_t channels,
+                     int32_t sample_rate, float* h_audio);
+
+/* Batched writers (host threads, no GPU): one Standard MIDI File and / or one note-event CSV per file of a batch, straight
+ * from the concatenated note arrays (times already in seconds).  Replaces, for batches, note_events_to_midi (reference:
+ * basic_pitch/note_creation.py:222-271, incl. drop_overlapping_pitch_bends :274-286 when multiple_pitch_bends = 0) +
+ * PrettyMIDI.write (inference.py:574-584) and save_note_events (inference.py:409-428).  File i owns notes
+ * [note_off[i], note_off[i+1]); note j owns bends [bend_off[j], bend_off[j+1]) (bend_off may be NULL: no bends).
+ * midi_paths / csv_paths: arrays of n_files paths (the array or single entries may be NULL = skip).  n_threads <= 0: auto. */
+int bp_write_note_files(int32_t n_files, const char* const* midi_paths, const char* const* csv_paths,
+                        const int32_t* note_off, const double* start_s, const double* end_s, const int32_t* pitch_midi,
+                        const float* amplitude, const int32_t* bend_off, const int32_t* bends,
+                        int32_t multiple_pitch_bends, double midi_tempo, int32_t n_threads);
+
+/* Host-only: the low-pass of the ingest resampler for the reduced ratio up / down (unit DC gain, before the gain `up`);
+ * returns the number of taps, copies them if capacity allows.  Tests pin it against scipy.signal.firwin. */
+int64_t bp_debug_resample_filter(int32_t up, int32_t down, double* taps, int64_t capacity);
+
 /* Host-only (no GPU needed): builds the tensor-core plan (split-bf16 Toeplitz weight tiles and the per-group MMA
  * programs, csrc/tc_conv.cu) of the contour conv (which = 0, w = [8][8][3][39]), the onset conv (which = 1,
  * w = [32][8][5][5]) or the note conv (which = 2, w = [32][1][7][7]) so that tests can emulate the program on the CPU.  sizes[4] = {n_tiles, n_steps, n_uses,

@@ -9,6 +9,7 @@ satisfied by oracle/ref_shims (librosa / pretty_midi / mir_eval / resampy stand-
     python oracle/make_golden.py            # rewrites tests/golden/*.npz
 
 Fixtures written (all small, committed):
+  vocadito10_pcm44k.npz the same clip as stored in the reference's test resources (44.1 kHz int16 mono): ingest tests
   vocadito10.npz        reference golden posteriorgrams/events (tests/resources/vocadito_10/*.npz),
                         the 22 050 Hz audio they are checked with, and the events the reference
                         decode emits for the golden posteriorgrams under several parameter sets
@@ -189,6 +190,12 @@ def main() -> None:
     assert np.array_equal(store["decode0/pitch"], store["gold_events/pitch"])
     assert np.array_equal(store["decode0/bend_flat"], store["gold_events/bend_flat"])
     np.savez_compressed(GOLD / "vocadito10.npz", **store)
+    # the clip as stored (44.1 kHz, 16-bit mono): input of the device ingest tests (csrc/ingest.cu)
+    from scipy.io import wavfile
+
+    sr44, pcm = wavfile.read(str(wav))
+    assert sr44 == 44100 and pcm.dtype == np.int16 and pcm.ndim == 1
+    np.savez_compressed(GOLD / "vocadito10_pcm44k.npz", pcm=pcm, sample_rate=np.int32(sr44))
 
     # ---------------------------------------------------------------- B. decode cases
     store = {}

@@ -181,9 +181,35 @@ def test_decode_substep_functions_reject_unsupported_arguments():
         nc.get_pitch_bends(np.zeros((4, 264), np.float32), [(0, 2, 60, 0.5)], n_bins_tolerance=10)
     with pytest.raises(NotImplementedError):
         nc.get_infered_onsets(np.zeros((4, 88), np.float32), np.zeros((4, 88), np.float32), n_diff=3)
-    with pytest.raises(NotImplementedError):
-        nc.sonify_salience(np.zeros((264, 4)), 3)
     assert nc.SONIFY_FS == 3000
+
+
+def test_sonification_helpers(tmp_path):
+    """sonify_midi / sonify_salience (reference: note_creation.py:119-165): same signatures, files and return values; the
+    synthesis itself restates pretty_midi / mir_eval behaviour (sum of sinusoids, peak-normalised)."""
+    from scipy.io import wavfile
+
+    from basic_pitch_b200 import note_creation as nc
+
+    ev = [(0.1, 0.6, 69, np.float32(0.8), [0, 1, 2, 1, 0]), (0.3, 1.0, 76, np.float32(0.5), None)]
+    for midi in (nc.note_events_to_midi(ev), nc.LazyPrettyMIDI(ev)):
+        path = tmp_path / "m.wav"
+        nc.sonify_midi(midi, path, 8000)
+        sr, y = wavfile.read(path)
+        assert sr == 8000 and len(y) == int(8000 * (1.0 + 1)) and abs(np.abs(y).max() - 1.0) < 1e-9
+        seg = y[int(0.12 * sr) : int(0.28 * sr)]  # only the A4 sounds here
+        f = np.fft.rfftfreq(len(seg), 1 / sr)
+        assert abs(f[np.abs(np.fft.rfft(seg * np.hanning(len(seg)))).argmax()] - 440.0) < 12.0
+    gram = np.zeros((264, 100))
+    gram[60, 10:50] = 0.9
+    gram[120, 30:80] = 0.5
+    gram[200, :] = 0.1  # below thresh: zeroed in place
+    y, fs = nc.sonify_salience(gram, 3, str(tmp_path / "s.wav"))
+    assert fs == 3000 and gram[200].max() == 0 and abs(np.abs(y).max() - 1.0) < 1e-9
+    f = np.fft.rfftfreq(len(y), 1 / fs)
+    assert abs(f[np.abs(np.fft.rfft(y)).argmax()] - 27.5 * 2 ** (60 / 36)) < 1.0
+    sr, y44 = wavfile.read(tmp_path / "s.wav")
+    assert sr == 44100 and abs(len(y44) - len(y) * 44100 / 3000) <= 1
 
 
 def test_file_output_helpers_match_reference_behaviour(tmp_path):
@@ -245,3 +271,125 @@ def test_window_audio_file_and_get_audio_input_like_the_reference_tests(golden_d
     assert orig == 200607
     with pytest.raises(AssertionError):
         next(inf.get_audio_input(wav, 3, AUDIO_N_SAMPLES - 3))  # odd overlap, like the reference (inference.py:237)
+
+
+def test_ingest_filter_and_length_match_scipy():
+    """The device resampler (csrc/ingest.cu) designs its Kaiser low-pass itself: same taps as audio_io._resample_filter
+    (scipy.signal.kaiserord + firwin) and the output length of scipy.signal.resample_poly."""
+    import scipy.signal
+
+    from basic_pitch_b200 import _lib, audio_io
+
+    lib = _lib.load()
+    for up, down in ((1, 2), (147, 320), (441, 160), (147, 640)):
+        ref = audio_io._resample_filter(up, down)
+        n = int(lib.bp_debug_resample_filter(up, down, None, 0))
+        assert n == len(ref)
+        h = np.zeros(n)
+        lib.bp_debug_resample_filter(up, down, h.ctypes.data, n)
+        assert np.abs(h - ref).max() < 1e-14
+    for sr, n in ((44100, 401214), (48000, 12345), (16000, 777), (8000, 1), (22050, 99), (96000, 100001)):
+        g = np.gcd(22050, sr)
+        ref_len = len(scipy.signal.resample_poly(np.zeros(n), 22050 // g, sr // g)) if sr != 22050 else n
+        assert int(lib.bp_resampled_length(n, sr)) == ref_len
+
+
+@pytest.mark.parametrize("multi,tempo", [(False, 120.0), (True, 120.0), (False, 97.5)])
+def test_batched_writers_are_byte_identical_to_the_python_path(tmp_path, multi, tempo):
+    """csrc/writers.cu (`bp_write_note_files` through note_creation.write_note_files): the MIDI and CSV files of a batch,
+    written by host threads straight from the note arrays, against note_events_to_midi(...).write() /
+    save_note_events per file (reference: note_creation.py:222-286, inference.py:409-428) — ties, overlapping notes
+    (dropped pitch bends), empty files, one- and zero-length bend lists included."""
+    from basic_pitch_b200 import inference as inf
+    from basic_pitch_b200 import note_creation as nc
+
+    rng = np.random.default_rng(1)
+    n_files = 9
+    per = rng.integers(0, 60, n_files)
+    per[3] = 0
+    noff = np.zeros(n_files + 1, np.int32)
+    noff[1:] = np.cumsum(per)
+    n = int(noff[-1])
+    start = rng.integers(0, 600, n).astype(np.int32)
+    end = start + rng.integers(11, 60, n).astype(np.int32)
+    start[5:9] = start[5]
+    end[5:7] = end[5]
+    bl = end - start
+    bl[10], bl[11] = 1, 0
+    boff = np.zeros(n + 1, np.int32)
+    boff[1:] = np.cumsum(bl)
+    arrs = dict(note_off=noff, start=start, end=end, pitch=rng.integers(21, 108, n).astype(np.int32),
+                amp=rng.random(n).astype(np.float32), bend_off=boff, bends=rng.integers(-40, 40, boff[-1]).astype(np.int32))
+    arrs["pitch"][5:7] = 60
+    arrs["amp"][5:7] = 0.5
+    lazy = nc.note_events_batch(arrs, n_files)
+    eager = nc.note_events_batch(arrs, n_files, lazy=False)
+    for tag, events in (("lazy", lazy), ("eager", eager)):
+        mp = [tmp_path / f"{tag}{i}.mid" for i in range(n_files)]
+        cp = [tmp_path / f"{tag}{i}.csv" for i in range(n_files)]
+        mp[2] = None  # skipped
+        nc.write_note_files(events, mp, cp, multiple_pitch_bends=multi, midi_tempo=tempo, n_threads=3)
+        for i in range(n_files):
+            nc.note_events_to_midi(eager[i], multi, tempo).write(str(tmp_path / "ref.mid"))
+            inf.save_note_events(eager[i], tmp_path / "ref.csv")
+            if mp[i] is not None:
+                assert mp[i].read_bytes() == (tmp_path / "ref.mid").read_bytes(), (tag, i)
+            else:
+                assert not (tmp_path / f"{tag}{i}.mid").exists()
+            assert cp[i].read_bytes() == (tmp_path / "ref.csv").read_bytes(), (tag, i)
+
+
+def test_note_event_list_behaves_like_the_list():
+    from basic_pitch_b200 import note_creation as nc
+
+    noff = np.array([0, 3, 3, 5], np.int32)
+    arrs = dict(note_off=noff, start=np.array([1, 5, 9, 2, 4], np.int32), end=np.array([20, 30, 25, 14, 40], np.int32),
+                pitch=np.array([60, 62, 64, 40, 41], np.int32), amp=np.array([.1, .2, .3, .4, .5], np.float32),
+                bend_off=np.array([0, 2, 2, 5, 6, 6], np.int32), bends=np.array([1, -1, 3, 0, 2, 7], np.int32))
+    lazy, eager = nc.note_events_batch(arrs, 3), nc.note_events_batch(arrs, 3, lazy=False)
+    assert [len(x) for x in lazy] == [3, 0, 2]
+    for a, b in zip(lazy, eager):
+        assert a == b and list(a) == b and a[:] == b and sorted(a) == sorted(b)
+        if len(b):
+            assert a[-1] == b[-1] and a[0][4] == b[0][4]
+    assert lazy[0][0][4] == [1, -1] and lazy[0][1][4] == [] and lazy[2][1][4] == []
+    with pytest.raises(IndexError):
+        lazy[1][0]
+    m = nc.LazyPrettyMIDI(lazy[0])
+    assert len(m.instruments) == 1 and len(m.instruments[0].notes) == 3
+
+
+def test_streaming_windowing_equals_whole_file_windowing():
+    """run_inference_stream (bounded-memory mode, reference: README.md:196-198): block-wise windowing, the two-window
+    hold-back and the final trim reproduce window_audio_file + unwrap_output (inference.py:194-279) for every length /
+    block pattern — checked with a stand-in model on the CPU (the GPU test runs the real one)."""
+    from basic_pitch_b200 import inference as inf
+
+    class FakeModel(inf.Model):
+        def __init__(self):
+            pass
+
+        def __del__(self):
+            pass
+
+        def predict(self, x):
+            x = np.asarray(x)
+            fr = np.stack([x[:, t * 255 : t * 255 + 256].mean(axis=1) for t in range(172)], axis=1).astype(np.float32)
+            return {"note": np.repeat(fr[:, :, None], 88, 2), "onset": np.repeat(2 * fr[:, :, None], 88, 2),
+                    "contour": np.repeat(3 * fr[:, :, None], 264, 2)}
+
+    m = FakeModel()
+    rng = np.random.default_rng(0)
+    hop = 43844 - 30 * 256
+    for n in (0, 1, 3840, hop - 3840, hop - 3839, hop, hop + 1, 2 * hop - 100, 5 * hop + 17, 7 * hop):
+        audio = rng.standard_normal(n).astype(np.float32)
+        padded = np.concatenate([np.zeros(3840, np.float32), audio])
+        wins = [w[:, 0] for w, _ in inf.window_audio_file(padded, hop)]
+        ref = {k: inf.unwrap_output(v, n, 30, hop) for k, v in m.predict(np.stack(wins)).items()} if wins else None
+        for block in (max(n, 1), 50000, 9973):
+            blocks = [audio[p : p + block] for p in range(0, n, block)]
+            parts = list(inf.run_inference_stream(blocks, m, windows_per_step=3))
+            for k, width in (("note", 88), ("onset", 88), ("contour", 264)):
+                got = np.concatenate([q[k] for q in parts]) if parts else np.zeros((0, width), np.float32)
+                want = ref[k] if ref is not None else np.zeros((0, width), np.float32)
+                assert got.shape == want.shape and np.array_equal(got, want), (n, block, k)
