@@ -44,6 +44,9 @@ constexpr int kProducers = 32 * kMTile / kRowsPerWarp;  // 16 producer warps (mo
 constexpr int kThreads = kProducers + 32 + 128;
 constexpr int kTilePitch = 37;                    // epilogue staging: [4 warps][32 rows][36 bins + 1]
 constexpr int kStgPitch = 68;                     // producer staging: [128 rows][64 taps + 4] fp32
+constexpr int kSegOctave = 3;                     // octaves >= this (hop <= 32) stage their signal segment once per item
+constexpr int kSegPlane = (kMTile * kStgPitch * 4 / (3 * 2)) & ~7;  // bf16 elements per plane of the segment (5800)
+static_assert(kSegPlane >= 126 * 32 + 2 * kTaps + 32, "segment of the hop-32 octave");
 constexpr int kSmemBytes = kStages * kStageBytes + 256 + 4 * 32 * kTilePitch * 4 + kMTile * kStgPitch * 4 + kMTile * 24;
 static_assert(kThreads <= 1024 && kRowsPerWarp % 2 == 0 && (kKc * kRowsPerWarp / 32) % 8 == 0, "producer geometry");
 }  // namespace cq
@@ -155,6 +158,74 @@ __global__ void __launch_bounds__(cq::kThreads, 1) cqt_tc_kernel(const CqtTcArgs
       const int mt = it / kOctaves, o = it % kOctaves;
       const int hop = 256 >> o;
       const int len = octave_len(o);
+      if (o >= kSegOctave) {
+        // ---- octaves with hop <= 32: the 128 rows of the item overlap (by 7/8 .. 255/256 of their 256 taps), so the signal
+        // segment they cover is loaded, reflect-padded and split three ways ONCE per item into bf16 planes in shared memory
+        // (it fits where the other path stages its rows), and every chunk's operand tile is then assembled with 16-byte
+        // copies: 6 per thread and chunk instead of a gather + split of 16 samples per thread.
+        // An M-tile may span two windows: part 0 = rows [0, n0) (frames t0.. of window b0), part 1 = rows [n0, 128)
+        // (frames 0.. of window b0 + 1).  Each part's segment starts on a multiple of 8 samples at or below its first tap.
+        __nv_bfloat16* seg = reinterpret_cast<__nv_bfloat16*>(stg);
+        const int m0 = mt * kMTile;
+        const int b0 = m0 / kFrames, t0 = m0 - b0 * kFrames;
+        const int n0 = min(kMTile, kFrames - t0);
+        const int s0 = t0 * hop - 128, a0 = s0 & ~7, d0 = s0 - a0;  // part 0: first tap, aligned start, offset of the tap
+        const int L0 = ((n0 - 1) * hop + kTaps + d0 + 7) & ~7;
+        const int L1 = n0 < kMTile ? (((kMTile - n0 - 1) * hop + kTaps + 7) & ~7) : 0;  // part 1 starts at sample -128
+        asm volatile("bar.sync 1, %0;" ::"n"(kProducers) : "memory");  // the previous item's tile copies are done
+        for (int idx = ptid; idx < L0 + L1; idx += kProducers) {
+          const int part = idx >= L0;
+          const int b = b0 + part;
+          int i = part ? idx - L0 - 128 : a0 + idx;
+          float x = 0.f;
+          if (b < a.n_windows) {
+            if (i < 0) i = -i;
+            if (i >= len) i = 2 * (len - 1) - i;
+            if (i >= 0 && i < len) x = __ldg(a.chain + (size_t)b * kChainStride + chain_off(o) + i);
+          }
+          const __nv_bfloat16 h = __float2bfloat16_rn(x);
+          const float r1 = x - __bfloat162float(h);
+          const __nv_bfloat16 md = __float2bfloat16_rn(r1);
+          seg[idx] = h;
+          seg[kSegPlane + idx] = md;
+          seg[2 * kSegPlane + idx] = __float2bfloat16_rn(r1 - __bfloat162float(md));
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(kProducers) : "memory");
+        for (int c = 0; c < kTaps / kKc; ++c) {
+          mbar_wait(empty + stage, ph ^ 1);
+          unsigned char* sa = smem + stage * kStageBytes;
+          if (ptid == 0) {
+            mbar_expect_tx_only(full + stage, 3 * kWPlane);
+            bulk_g2s(sa + 3 * kAPlane, a.wtc + (size_t)c * (3 * kWPlane / 2), 3 * kWPlane, full + stage);
+          }
+#pragma unroll
+          for (int q = 0; q < 3 * 8 * kMTile / kProducers; ++q) {
+            const int id = ptid + q * kProducers;
+            const int row = id & (kMTile - 1), kc = (id >> 7) & 7, pl = id >> 10;
+            const int e = (row < n0 ? d0 + row * hop : L0 + (row - n0) * hop) + c * kKc + kc * 8;  // element inside a plane
+            const __nv_bfloat16* src = seg + pl * kSegPlane + e;
+            uint4 v;
+            if ((e & 7) == 0) {
+              v = *reinterpret_cast<const uint4*>(src);
+            } else if ((e & 1) == 0) {
+              const uint32_t* w = reinterpret_cast<const uint32_t*>(src);
+              v = make_uint4(w[0], w[1], w[2], w[3]);
+            } else {  // odd element offset (hop 1): five words, shifted by half a word
+              const uint32_t* w = reinterpret_cast<const uint32_t*>(src - 1);
+              v = make_uint4(__funnelshift_r(w[0], w[1], 16), __funnelshift_r(w[1], w[2], 16),
+                             __funnelshift_r(w[2], w[3], 16), __funnelshift_r(w[3], w[4], 16));
+            }
+            *reinterpret_cast<uint4*>(sa + pl * kAPlane + (kc * kMTile + row) * 16) = v;
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          mbar_arrive(full + stage);
+          if (++stage == kStages) {
+            stage = 0;
+            ph ^= 1;
+          }
+        }
+        continue;
+      }
       __syncwarp();
       if (lane < RW) {  // per item: where row RW pw + lane reads its signal
         const int m = mt * kMTile + RW * pw + lane;

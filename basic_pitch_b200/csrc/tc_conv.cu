@@ -246,23 +246,41 @@ void TcConvPlan::build(const TcConvSpec& sp, const float* W /* [COUT][n_ci][KH][
       });
       uses.insert(uses.end(), cand.begin(), cand.end());
     }
-    bool seen[2] = {false, false};
+    struct Step {
+      int tile;
+      uint32_t w[2];
+    };
+    std::vector<Step> steps;
     size_t i = 0;
     while (i < uses.size()) {
       size_t j = i;
       while (j < uses.size() && uses[j].tile == uses[i].tile && (j == i || uses[j].slot != uses[j - 1].slot)) ++j;
-      tile_seq.push_back(uses[i].tile);
-      uint32_t w[2] = {kNoUse, kNoUse};
+      Step stp{uses[i].tile, {kNoUse, kNoUse}};
       for (size_t u = i; u < j; ++u) {
-        const int sl = uses[u].slot;
-        w[sl] = (uint32_t)(uses[u].c8 * lbo16 + uses[u].dt);  // A start offset >> 4: chunk c8, row dt
-        if (!seen[sl]) w[sl] |= kUseFirstAcc;
-        seen[sl] = true;
+        stp.w[uses[u].slot] = (uint32_t)(uses[u].c8 * lbo16 + uses[u].dt);  // A start offset >> 4: chunk c8, row dt
         ++n_uses;
       }
-      slot_words[0].push_back(w[0]);
-      slot_words[1].push_back(w[1]);
+      steps.push_back(stp);
       i = j;
+    }
+    // Software skew between the two slots of a group: the steps only slot 0 uses come first, then the shared ones, then
+    // those only slot 1 uses.  Slot 1's next accumulator region is the one slot 0's previous tile still occupies until
+    // its conv2 MMAs are done (three regions for four tiles in flight); this way slot 0's tile finishes — and frees its
+    // region — early, and slot 1 needs its region late (the issuing warp acquires it at its first use), so neither waits.
+    std::stable_sort(steps.begin(), steps.end(), [](const Step& a, const Step& b) {
+      auto cls = [](const Step& s) { return s.w[1] == kNoUse ? 0 : (s.w[0] == kNoUse ? 2 : 1); };
+      return cls(a) < cls(b);
+    });
+    bool seen[2] = {false, false};
+    for (Step& stp : steps) {
+      for (int sl = 0; sl < 2; ++sl)
+        if (stp.w[sl] != kNoUse) {
+          if (!seen[sl]) stp.w[sl] |= kUseFirstAcc;
+          seen[sl] = true;
+        }
+      tile_seq.push_back(stp.tile);
+      slot_words[0].push_back(stp.w[0]);
+      slot_words[1].push_back(stp.w[1]);
     }
     group_step_off.push_back((int)tile_seq.size());
   }
@@ -914,11 +932,7 @@ __global__ void __launch_bounds__(tc::kThreads, 1) conv_tc_kernel(const TcArgs a
         const bool two = c_group_ft[a.layer][2 * g + 1] >= 0;
         const bool mine = slot == 0 || two;
         const uint32_t nm = n + (uint32_t)slot, r = nm % kRegions, u = nm / kRegions;
-        if (mine) {
-          mbar_wait_wd(tmem_empty + r, (u & 1u) ^ 1u, 4);
-          tc_fence_after();
-          TC_TRACE(nm, 0);
-        }
+        bool acquired = !mine;  // the region is acquired at this slot's first use of the group (see TcConvPlan::build)
         const int s0 = c_group_step_off[a.layer][g], s1 = c_group_step_off[a.layer][g + 1];
         const uint32_t d = tmem_base + r * 128u;
         uint32_t w = prog[s0];
@@ -926,6 +940,11 @@ __global__ void __launch_bounds__(tc::kThreads, 1) conv_tc_kernel(const TcArgs a
           const uint32_t w_next = prog[s + 1];  // (one word past the end is inside the array)
           mbar_wait_wd(full_w + stage, ph_w, 5);
           if (w != kNoUse) {
+            if (!acquired) {
+              mbar_wait_wd(tmem_empty + r, (u & 1u) ^ 1u, 4);
+              acquired = true;
+              TC_TRACE(nm, 0);
+            }
             tc_fence_after();
             const uint32_t off = w & 0x3fffu;
             const uint32_t bl = b_base + stage * (kTileBytes >> 4);

@@ -360,7 +360,9 @@ def main():
         del res_py
         barrier()
         t0 = time.perf_counter()
+        res_py = None
         for _ in range(args.python_steps):
+            del res_py  # (holding the previous step's posteriorgrams would force a fresh 1.9 GB page-locked allocation)
             res_py = predict_batch(clips, model)
         torch.cuda.synchronize()
         py_s = torch.tensor([(time.perf_counter() - t0) / args.python_steps], device=f"cuda:{local}")
@@ -401,6 +403,14 @@ def main():
                 traffic = tj["families"][str(dom)]["dram_bytes_per_window"] * f_win / f_groups
         except (OSError, KeyError, ValueError, TypeError):
             pass
+        # every tensor-core family against the same measured peak (the dominant one is repeated in `roofline`)
+        fam_roof = {}
+        for k in (0, 1, 2, 4):
+            if fam[k]["ms_per_step"] > 0:
+                tf = FAMILIES[k][1] * fam[k]["windows"] / (fam[k]["ms_per_step"] * 1e-3) / 1e12
+                fam_roof[FAMILIES[k][0].split(" (")[0]] = {
+                    "ms_per_step": round(fam[k]["ms_per_step"], 3), "algorithmic_tflops": round(tf, 1), "frac_of_peak": round(tf / peak_tf, 4),
+                    "share_of_step": round(fam[k]["ms_per_step"] / (ms / args.steps), 3)}
         dec_ms = fam[5]["ms_per_step"] + fam[6]["ms_per_step"]
         dec_gbs = n_frames * DECODE_BYTES_PER_FRAME / (dec_ms * 1e-3) / 1e9 if dec_ms > 0 else None
         threads = host_threads()
@@ -436,6 +446,7 @@ def main():
                          "traffic_unit": "DRAM bytes per launch (ncu, profiles/roofline_traffic.json)", "peak_source": peak_src,
                          "avg_launch_ms": f_ms / f_groups, "windows_per_launch": f_win / f_groups,
                          "flop_per_window": FAMILIES[dom][1]},
+            "roofline_families": fam_roof,
             "roofline_decode": {"bound": "hbm", "kernel": "decode_prep + decode_cand + decode_seq + note_finish (decode.cu)",
                                 "achieved": dec_gbs, "peak": peak_bw, "unit": "GB/s", "frac": (dec_gbs / peak_bw) if dec_gbs else None,
                                 "bytes_per_frame": DECODE_BYTES_PER_FRAME, "frames_per_step": n_frames, "ms_per_step": dec_ms,
