@@ -177,6 +177,8 @@ struct bp_model {
   DevBuf<float> energy, d_amp;
   DevBuf<double> d_onset64;
   DevBuf<unsigned int> candbits, max_onset;
+  DevBuf<float> blk_max;
+  DevBuf<int> blk_arg;
   DevBuf<unsigned long long> max_fd;
   DevBuf<int> note_count, slot_start, slot_end, slot_pitch, overflow, d_note_off, d_start, d_end, d_pitch, d_bend_off,
       d_bends;
@@ -649,7 +651,7 @@ void bp_model_destroy(bp_model_t* m) {
   m->u_contour.release();
   m->wdesc.release(); m->udesc.release(); m->st_audio.release(); m->st_note.release(); m->st_onset.release();
   m->st_contour.release(); m->st_pcm.release(); m->d_frame_off.release(); m->d_slot_off.release(); m->d_note_base.release();
-  m->energy.release(); m->d_amp.release(); m->candbits.release(); m->max_onset.release(); m->max_fd.release();
+  m->energy.release(); m->d_amp.release(); m->candbits.release(); m->blk_max.release(); m->blk_arg.release(); m->max_onset.release(); m->max_fd.release();
   m->note_count.release(); m->slot_start.release(); m->slot_end.release(); m->slot_pitch.release();
   m->overflow.release(); m->d_note_off.release(); m->d_start.release(); m->d_end.release(); m->d_pitch.release();
   m->d_bend_off.release(); m->d_bends.release(); m->d_onset64.release();
@@ -938,6 +940,8 @@ int bp_decode_device(bp_model_t* m, const float* d_note, const float* d_onset, c
     CK(m->d_slot_off.reserve(n_files + 1));
     CK(m->energy.reserve(cells + 1));
     CK(m->candbits.reserve(cells / 32 + 2));
+    CK(m->blk_max.reserve((size_t)kPitches * decode_block_slots(total_frames, n_files)));
+    CK(m->blk_arg.reserve((size_t)kPitches * decode_block_slots(total_frames, n_files)));
     CK(m->max_onset.reserve(n_files));
     CK(m->max_fd.reserve(n_files));
     CK(m->note_count.reserve(n_files));
@@ -960,6 +964,8 @@ int bp_decode_device(bp_model_t* m, const float* d_note, const float* d_onset, c
     b.note_end = m->slot_end.p;
     b.note_pitch = m->slot_pitch.p;
     b.overflow = m->overflow.p;
+    b.blk_max = m->blk_max.p;
+    b.blk_arg = m->blk_arg.p;
     {
       ProfScope ps(m, 5, st);
       launch_decode_notes(d_note, d_onset, b, n_files, total_frames, dp, st);

@@ -15,11 +15,11 @@
 // canonical K-major core-matrix layout) by four producer warps that also do the reflect padding and the hi/lo split.
 //
 // item = (M-tile of 128 frames, octave); per item 4 K-chunks of 64 taps, each chunk = 4 k-steps x 6 products:
-//   warps 4-11  producers: gather 128 x 64 samples (128-bit loads where aligned), split, st.shared into
+//   warps 8-23  producers: gather 128 x 64 samples (128-bit loads where aligned), split, st.shared into
 //               [plane][k/8][row][8] ; one lane bulk-copies the matching 30 KB slice of the split kernel matrix W
 //               (UBLKCP) ; fence.proxy.async ; mbarrier arrive
-//   warp 12     MMA issuer (one elected lane): 24 tcgen05.mma per chunk, tcgen05.commit frees the stage / publishes TMEM
-//   warps 0-3   epilogue: tcgen05.ld 80 columns, magnitude * sqrt(len), log-power, store, per-window min/max (atomics)
+//   warp 24     MMA issuer (one elected lane): 24 tcgen05.mma per chunk, tcgen05.commit frees the stage / publishes TMEM
+//   warps 0-7   epilogue (two per TMEM lane quadrant): tcgen05.ld 32 / 40 columns, magnitude * sqrt(len), log-power, store, per-window min/max (atomics)
 // (the issue arbiter prefers high warp ids: the MMA issuer and the producers, which bound the kernel, outrank the epilogue)
 // Shared memory: 2 stages x (48 KB A + 30 KB W); TMEM: 2 accumulators of 128 x 80 (256 columns allocated).
 #include <cuda_bf16.h>
@@ -41,13 +41,15 @@ constexpr int kStageBytes = 3 * kAPlane + 3 * kWPlane;  // 79872
 constexpr int kStages = 2;
 constexpr int kRowsPerWarp = 8;   // rows of the M-tile a producer warp gathers and converts
 constexpr int kProducers = 32 * kMTile / kRowsPerWarp;  // 16 producer warps (more warps in flight hide the gather latency)
-constexpr int kThreads = kProducers + 32 + 128;
-constexpr int kTilePitch = 37;                    // epilogue staging: [4 warps][32 rows][36 bins + 1]
+constexpr int kEpiWarps = 8;                      // two per TMEM lane quadrant: bins 0..15 / 16..35 of the octave
+constexpr int kThreads = kProducers + 32 + 32 * kEpiWarps;
+constexpr int kTilePitch = 21;                    // epilogue staging: [8 warps][32 rows][<= 20 bins + 1]
 constexpr int kStgPitch = 68;                     // producer staging: [128 rows][64 taps + 4] fp32
 constexpr int kSegOctave = 3;                     // octaves >= this (hop <= 32) stage their signal segment once per item
 constexpr int kSegPlane = (kMTile * kStgPitch * 4 / (3 * 2)) & ~7;  // bf16 elements per plane of the segment (5800)
 static_assert(kSegPlane >= 126 * 32 + 2 * kTaps + 32, "segment of the hop-32 octave");
-constexpr int kSmemBytes = kStages * kStageBytes + 256 + 4 * 32 * kTilePitch * 4 + kMTile * kStgPitch * 4 + kMTile * 24;
+constexpr int kEpiBytes = kEpiWarps * 32 * kTilePitch * 4;
+constexpr int kSmemBytes = kStages * kStageBytes + 256 + kEpiBytes + kMTile * kStgPitch * 4 + kMTile * 24;
 static_assert(kThreads <= 1024 && kRowsPerWarp % 2 == 0 && (kKc * kRowsPerWarp / 32) % 8 == 0, "producer geometry");
 }  // namespace cq
 
@@ -112,7 +114,7 @@ __global__ void __launch_bounds__(cq::kThreads, 1) cqt_tc_kernel(const CqtTcArgs
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);  // broadcast: warp-uniform role branches and loop state
   const int lane = threadIdx.x & 31;
-  constexpr int kMmaWarp = 4 + kProducers / 32;
+  constexpr int kMmaWarp = kEpiWarps + kProducers / 32;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) {
@@ -121,7 +123,7 @@ __global__ void __launch_bounds__(cq::kThreads, 1) cqt_tc_kernel(const CqtTcArgs
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(tmem_full + i, 1);
-      mbar_init(tmem_empty + i, 4);
+      mbar_init(tmem_empty + i, kEpiWarps);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -137,7 +139,7 @@ __global__ void __launch_bounds__(cq::kThreads, 1) cqt_tc_kernel(const CqtTcArgs
   const int n_items = a.n_mtiles * kOctaves;
   const int total_frames = a.n_windows * kFrames;
 
-  if (warp >= 4 && warp < kMmaWarp) {
+  if (warp >= kEpiWarps && warp < kMmaWarp) {
     // ------------------------------ producers ------------------------------
     // Phase A (lanes along the taps): warp pw gathers rows RW pw .. RW pw + RW - 1 of the chunk, two rows (2 x 64 taps) per
     // 128-bit load instruction, into the staging tile S[row][64 taps] -- a load instruction touches 4-6 cache lines
@@ -146,12 +148,12 @@ __global__ void __launch_bounds__(cq::kThreads, 1) cqt_tc_kernel(const CqtTcArgs
     constexpr int RW = kRowsPerWarp, NI = RW / 2;  // row pairs per warp
     constexpr int KQ = 32 / RW;                    // phase B: lanes per row
     constexpr int TPL = kKc / KQ;                  // taps per lane in phase B (a multiple of 8)
-    const int ptid = threadIdx.x - 128;            // producer thread
+    const int ptid = threadIdx.x - 32 * kEpiWarps;  // producer thread
     const int pw = ptid >> 5;
     const int r = RW * pw + (lane % RW);  // phase B: the warp converts the rows it gathered, no block-wide barrier
     const int kq = lane / RW;
-    float* stg = reinterpret_cast<float*>(smem + kStages * kStageBytes + 256 + 4 * 32 * kTilePitch * 4);  // [128][kStgPitch]
-    RowP* rowp = reinterpret_cast<RowP*>(smem + kStages * kStageBytes + 256 + 4 * 32 * kTilePitch * 4 +
+    float* stg = reinterpret_cast<float*>(smem + kStages * kStageBytes + 256 + kEpiBytes);  // [128][kStgPitch]
+    RowP* rowp = reinterpret_cast<RowP*>(smem + kStages * kStageBytes + 256 + kEpiBytes +
                                          kMTile * kStgPitch * 4) + RW * pw;  // this warp's rows
     uint32_t stage = 0, ph = 0;
     for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
@@ -173,22 +175,35 @@ __global__ void __launch_bounds__(cq::kThreads, 1) cqt_tc_kernel(const CqtTcArgs
         const int L0 = ((n0 - 1) * hop + kTaps + d0 + 7) & ~7;
         const int L1 = n0 < kMTile ? (((kMTile - n0 - 1) * hop + kTaps + 7) & ~7) : 0;  // part 1 starts at sample -128
         asm volatile("bar.sync 1, %0;" ::"n"(kProducers) : "memory");  // the previous item's tile copies are done
-        for (int idx = ptid; idx < L0 + L1; idx += kProducers) {
-          const int part = idx >= L0;
-          const int b = b0 + part;
-          int i = part ? idx - L0 - 128 : a0 + idx;
-          float x = 0.f;
-          if (b < a.n_windows) {
+        {
+          // <= 9 samples per thread (126 * 32 + 2 * 256 + slack <= 9 * 512): all loads are issued before the first use
+          constexpr int NS = (126 * 32 + 2 * kTaps + 32 + kProducers - 1) / kProducers;
+          float xs[NS];
+#pragma unroll
+          for (int q = 0; q < NS; ++q) {
+            const int idx = ptid + q * kProducers;
+            const int part = idx >= L0;
+            const int b = b0 + part;
+            int i = part ? idx - L0 - 128 : a0 + idx;
             if (i < 0) i = -i;
             if (i >= len) i = 2 * (len - 1) - i;
-            if (i >= 0 && i < len) x = __ldg(a.chain + (size_t)b * kChainStride + chain_off(o) + i);
+            xs[q] = (idx < L0 + L1 && b < a.n_windows && i >= 0 && i < len)
+                        ? __ldg(a.chain + (size_t)b * kChainStride + chain_off(o) + i)
+                        : 0.f;
           }
-          const __nv_bfloat16 h = __float2bfloat16_rn(x);
-          const float r1 = x - __bfloat162float(h);
-          const __nv_bfloat16 md = __float2bfloat16_rn(r1);
-          seg[idx] = h;
-          seg[kSegPlane + idx] = md;
-          seg[2 * kSegPlane + idx] = __float2bfloat16_rn(r1 - __bfloat162float(md));
+#pragma unroll
+          for (int q = 0; q < NS; ++q) {
+            const int idx = ptid + q * kProducers;
+            if (idx < L0 + L1) {
+              const float x = xs[q];
+              const __nv_bfloat16 h = __float2bfloat16_rn(x);
+              const float r1 = x - __bfloat162float(h);
+              const __nv_bfloat16 md = __float2bfloat16_rn(r1);
+              seg[idx] = h;
+              seg[kSegPlane + idx] = md;
+              seg[2 * kSegPlane + idx] = __float2bfloat16_rn(r1 - __bfloat162float(md));
+            }
+          }
         }
         asm volatile("bar.sync 1, %0;" ::"n"(kProducers) : "memory");
         for (int c = 0; c < kTaps / kKc; ++c) {
@@ -353,41 +368,40 @@ __global__ void __launch_bounds__(cq::kThreads, 1) cqt_tc_kernel(const CqtTcArgs
       for (int c = 0; c < kTaps / kKc; ++c) {
         mbar_wait(full + stage, ph);
         tc_fence_after();
+        // descriptors as (low word, shared high word); everything here is warp-uniform, the MMAs themselves are
+        // predicated on the elected lane inside the asm block: the loop stays on the uniform datapath (no R2UR per MMA)
         const uint32_t sa = smem_u32(smem + stage * kStageBytes);
-        if (leader) {
+        const uint32_t desc_hi32 = (128u >> 4) | (1u << 14);
+        const uint32_t a_base = ((sa >> 4) & 0x3fffu) | ((uint32_t)(kMTile * 16 >> 4) << 16);
+        const uint32_t b_base = (((sa + 3 * kAPlane) >> 4) & 0x3fffu) | ((uint32_t)(kN * 16 >> 4) << 16);
 #pragma unroll
-          for (int ks = 0; ks < kKc / 16; ++ks) {
-            // one k-step = 16 taps = two 16-byte k-chunks, LBO apart
-            const uint32_t ao = sa + ks * 2 * (kMTile * 16), bo = sa + 3 * kAPlane + ks * 2 * (kN * 16);
-            const uint64_t a_h = make_desc(ao, kMTile * 16, 128), a_m = make_desc(ao + kAPlane, kMTile * 16, 128),
-                           a_l = make_desc(ao + 2 * kAPlane, kMTile * 16, 128);
-            const uint64_t b_h = make_desc(bo, kN * 16, 128), b_m = make_desc(bo + kWPlane, kN * 16, 128),
-                           b_l = make_desc(bo + 2 * kWPlane, kN * 16, 128);
-            umma_bf16(d, a_h, b_h, idesc, (c | ks) ? 1u : 0u);
-            umma_bf16(d, a_h, b_m, idesc, 1u);
-            umma_bf16(d, a_m, b_h, idesc, 1u);
-            umma_bf16(d, a_h, b_l, idesc, 1u);
-            umma_bf16(d, a_l, b_h, idesc, 1u);
-            umma_bf16(d, a_m, b_m, idesc, 1u);
-          }
-          umma_commit(empty + stage);
+        for (int ks = 0; ks < kKc / 16; ++ks) {
+          // one k-step = 16 taps = two 16-byte k-chunks, LBO apart
+          const uint32_t ao = a_base + (uint32_t)(ks * 2 * (kMTile * 16) >> 4), bo = b_base + (uint32_t)(ks * 2 * (kN * 16) >> 4);
+          umma_bf16_x6(d, ao, ao + (kAPlane >> 4), ao + 2 * (kAPlane >> 4), bo, bo + (kWPlane >> 4), bo + 2 * (kWPlane >> 4),
+                       desc_hi32, idesc, (c | ks) ? 1u : 0u, leader);
         }
+        umma_commit_pred(empty + stage, leader);
         __syncwarp();
         if (++stage == kStages) {
           stage = 0;
           ph ^= 1;
         }
       }
-      if (leader) umma_commit(tmem_full + buf);
-      __syncwarp();
+      umma_commit_pred(tmem_full + buf, leader);
       ++icount;
     }
   } else {
-    // ------------------------------ epilogue (warps 0..3) ------------------------------
-    const int quad = warp & 3;
+    // ------------------------------ epilogue (warps 0..7) ------------------------------
+    // Two warps per TMEM lane quadrant (a warp may only read lanes 32 (warp % 4) ..): warp < 4 takes bins 0..15 of the
+    // octave (accumulator columns 0..31), warp >= 4 bins 16..35 (columns 32..71).  Four warps alone were the bottleneck
+    // of the kernel (busy all the time while the tensor pipe idled at 23 %).
+    const int quad = warp & 3, half = warp >> 2;
     const int row = quad * 32 + lane;
+    const int nb = half ? 20 : 16, bin0 = half ? 16 : 0;
     uint32_t ph_t[2] = {0, 0};
     uint32_t icount = 0;
+    float* tile = reinterpret_cast<float*>(smem + kStages * kStageBytes + 256) + warp * (32 * kTilePitch);
     for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
       const int mt = it / kOctaves, o = it % kOctaves;
       const int m = mt * kMTile + row;
@@ -397,44 +411,56 @@ __global__ void __launch_bounds__(cq::kThreads, 1) cqt_tc_kernel(const CqtTcArgs
       mbar_wait(tmem_full + buf, ph_t[buf]);
       ph_t[buf] ^= 1;
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * 128u;
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * 128u + (uint32_t)(2 * bin0);
       float vmin = INFINITY, vmax = -INFINITY;
-      const int g0 = (8 - o) * kBinsPerOctave - 15;  // global bin of this octave's bin 0 (may be negative for o = 8)
+      const int g0 = (8 - o) * kBinsPerOctave - 15 + bin0;  // global bin of this warp's first bin (negative for the lowest of o = 8)
       // 10*log10(re^2 + im^2 + 1e-10) per bin (MUFU.LG2; the reference's sqrt-then-square differs by < 1e-6 dB), staged
       // per warp in shared memory so that the stores below write runs of consecutive bins instead of one bin of 32 rows
-      float* tile = reinterpret_cast<float*>(smem + kStages * kStageBytes + 256) + quad * (32 * kTilePitch);
-#pragma unroll 1
-      for (int part = 0; part < 5; ++part) {  // 5 x 16 columns = 8 bins each (the last part holds bins 32..35 + padding)
-        uint32_t v[16];
-        tmem_ld16_nowait(taddr + part * 16, v);
-        tmem_ld_wait();
+      uint32_t v[40];
+      tmem_ld32_nowait(taddr, reinterpret_cast<uint32_t(&)[32]>(v[0]));
+      if (half) {
+        uint32_t t8[8];
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                     : "=r"(t8[0]), "=r"(t8[1]), "=r"(t8[2]), "=r"(t8[3]), "=r"(t8[4]), "=r"(t8[5]), "=r"(t8[6]), "=r"(t8[7])
+                     : "r"(taddr + 32));
 #pragma unroll
-        for (int jb = 0; jb < 8; ++jb) {
-          const int j = part * 8 + jb;
+        for (int k = 0; k < 8; ++k) v[32 + k] = t8[k];
+      }
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tmem_empty + buf);  // the accumulator is free: the values are in registers
+#pragma unroll
+      for (int j = 0; j < 20; ++j) {
+        if (j < nb) {
           const int g = g0 + j;
-          if (j < kBinsPerOctave && g >= 0) {
+          float L = 0.f;
+          if (g >= 0) {
             const float s = __ldg(a.scale + g);
-            const float re = __uint_as_float(v[2 * jb]) * s, im = __uint_as_float(v[2 * jb + 1]) * s;
-            const float L = __log2f(fmaf(re, re, im * im) + 1e-10f) * 3.0102999566398120f;
-            tile[lane * kTilePitch + j] = L;
+            const float re = __uint_as_float(v[2 * j]) * s, im = __uint_as_float(v[2 * j + 1]) * s;
+            L = __log2f(fmaf(re, re, im * im) + 1e-10f) * 3.0102999566398120f;
             if (live) {
               vmin = fminf(vmin, L);
               vmax = fmaxf(vmax, L);
             }
           }
+          tile[lane * kTilePitch + j] = L;
         }
       }
-      tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tmem_empty + buf);  // the accumulator is free while the tile is written out
       {
         const int m0 = mt * kMTile + quad * 32;
-#pragma unroll 4
-        for (int i = 0; i < kBinsPerOctave; ++i) {
-          const int e = i * 32 + lane;
-          const int rr = e / kBinsPerOctave, jj = e - rr * kBinsPerOctave;
-          if (m0 + rr < total_frames && g0 + jj >= 0)
-            a.logmag[(size_t)(m0 + rr) * kCqtBins + g0 + jj] = tile[rr * kTilePitch + jj];
+        int rr = half ? lane / 20 : lane >> 4, jj = half ? lane - 20 * rr : lane & 15;
+        for (int i = 0; i < nb; ++i) {  // 32 rows x nb bins, consecutive lanes -> consecutive bins of a row
+          if (m0 + rr < total_frames && g0 + jj >= 0) a.logmag[(size_t)(m0 + rr) * kCqtBins + g0 + jj] = tile[rr * kTilePitch + jj];
+          jj += 32;  // the next element this lane owns is 32 further: one or two rows down
+          if (half) {
+            rr += 1 + (jj >= 40);
+            jj -= jj >= 40 ? 40 : 20;
+          } else {
+            rr += 2;
+            jj -= 32;
+          }
         }
       }
       __syncwarp();  // the staging tile is reused by the next item

@@ -210,6 +210,10 @@ __global__ void __launch_bounds__(256) decode_cand_kernel(const float* __restric
 // ------------------------------------------------------------------------------------------------
 constexpr int kSeqThreads = 128;
 
+// block-maxima entries per pitch column for a batch: file i (frames [base, base + T)) owns entries
+// [base / 256 + i, .. + ceil(T / 256)), which never overlap the next file's
+long long decode_block_slots(long long total_frames, int n_files) { return total_frames / 256 + n_files + 1; }
+
 // Warp-cooperative scan used by both loops: starting at frame i (step +1 or -1) with run counter 0, walk while
 // `in range` and run < tol, counting consecutive cells of column `col` that are below the threshold.
 // Returns the exit index and the run length in *run.  `limit`: forward -> stop when i >= limit (= T-1);
@@ -249,11 +253,18 @@ __device__ __forceinline__ void zero_cols(float* E, int T, int f, int t_lo, int 
   }
 }
 
-__device__ void column_max(const float* col, int T, float* out_v, int* out_t) {
+// The melodia loop needs, after every note, the maximum (value, lowest frame) of the three columns it touched.  A full
+// column scan costs T / 32 dependent loads per warp — 500 for a three-minute file, times thousands of iterations — so
+// every column keeps the maxima of its 256-frame blocks: a note touches one or two blocks, and the column maximum is a
+// reduction over T / 256 block entries.
+constexpr int kDecBlk = 256;
+
+// maximum of frames [t_lo, t_hi) of a column: value and the lowest frame that attains it (warp-cooperative)
+__device__ void range_max(const float* col, int t_lo, int t_hi, float* out_v, int* out_t) {
   const int lane = threadIdx.x & 31;
   float bv = -INFINITY;
   int bt = 0x7fffffff;
-  for (int t = lane; t < T; t += 32) {
+  for (int t = t_lo + lane; t < t_hi; t += 32) {
     float v = col[t];
     if (v > bv) {
       bv = v;
@@ -273,10 +284,47 @@ __device__ void column_max(const float* col, int T, float* out_v, int* out_t) {
   *out_t = bt;
 }
 
+// block maxima of blocks [b_lo, b_hi] of one column, then the column maximum from all its block entries
+__device__ void refresh_column(const float* col, int T, float* bmax, int* barg, int nblk, int b_lo, int b_hi, float* out_v,
+                               int* out_t) {
+  const int lane = threadIdx.x & 31;
+  for (int b = b_lo; b <= b_hi; ++b) {
+    float v;
+    int t;
+    range_max(col, b * kDecBlk, min(T, (b + 1) * kDecBlk), &v, &t);
+    if (lane == 0) {
+      bmax[b] = v;
+      barg[b] = t;
+    }
+  }
+  __syncwarp();
+  float bv = -INFINITY;
+  int bt = 0x7fffffff;
+  for (int b = lane; b < nblk; b += 32) {  // blocks ascend with the frame index: ties keep the lower block
+    const float v = bmax[b];
+    if (v > bv) {
+      bv = v;
+      bt = barg[b];
+    }
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+    int ot = __shfl_xor_sync(0xffffffffu, bt, o);
+    if (ov > bv || (ov == bv && ot < bt)) {
+      bv = ov;
+      bt = ot;
+    }
+  }
+  *out_v = bv;
+  *out_t = bt;
+}
+
 __global__ void __launch_bounds__(kSeqThreads) decode_seq_kernel(
     const long long* __restrict__ frame_off, float* __restrict__ energy, const unsigned int* __restrict__ candbits,
     const long long* __restrict__ slot_off, int* __restrict__ note_count, int* __restrict__ note_start,
-    int* __restrict__ note_end, int* __restrict__ note_pitch, int* __restrict__ overflow, DecodeParamsDev p) {
+    int* __restrict__ note_end, int* __restrict__ note_pitch, int* __restrict__ overflow, float* __restrict__ blk_max,
+    int* __restrict__ blk_arg, DecodeParamsDev p) {
   const int file = blockIdx.x;
   const long long base = frame_off[file];
   const int T = (int)(frame_off[file + 1] - base);
@@ -288,7 +336,7 @@ __global__ void __launch_bounds__(kSeqThreads) decode_seq_kernel(
 
   __shared__ float s_cmax[kPitches];
   __shared__ int s_carg[kPitches];
-  __shared__ int s_pick[3];  // tm, f, done
+  __shared__ int s_pick[5];  // tm, f, done, first and last frame the iteration changed
   __shared__ int s_count;
 
   int count = 0;
@@ -351,10 +399,14 @@ __global__ void __launch_bounds__(kSeqThreads) decode_seq_kernel(
 
   // ---------------- melodia loop ----------------
   if (p.melodia) {
+    // this file's block entries: [88][nblk] behind those of the files before it (see decode_block_slots)
+    const int nblk = (T + kDecBlk - 1) / kDecBlk;
+    float* bmax = blk_max + (size_t)kPitches * (size_t)(base / kDecBlk + file);
+    int* barg = blk_arg + (size_t)kPitches * (size_t)(base / kDecBlk + file);
     for (int f = warp; f < kPitches; f += kSeqThreads / 32) {
       float v;
       int t;
-      column_max(E + (long long)f * T, T, &v, &t);
+      refresh_column(E + (long long)f * T, T, bmax + (size_t)f * nblk, barg + (size_t)f * nblk, nblk, 0, nblk - 1, &v, &t);
       if (lane == 0) {
         s_cmax[f] = v;
         s_carg[f] = t;
@@ -415,6 +467,9 @@ __global__ void __launch_bounds__(kSeqThreads) decode_seq_kernel(
           if (lane == 0) {
             s_pick[0] = tm;
             s_pick[1] = f;
+            // zeroed on three columns: [backward exit + 1, forward exit), i.e. within energy_tol of the note's ends
+            s_pick[3] = max(0, min(t_start - p.energy_tol, tm));
+            s_pick[4] = min(T - 1, max(t_end + p.energy_tol, tm));
           }
         }
         if (lane == 0) s_pick[2] = go ? 0 : 1;
@@ -427,7 +482,8 @@ __global__ void __launch_bounds__(kSeqThreads) decode_seq_kernel(
         if (warp < 3 && f >= 0 && f < kPitches) {
           float v;
           int t;
-          column_max(E + (long long)f * T, T, &v, &t);
+          refresh_column(E + (long long)f * T, T, bmax + (size_t)f * nblk, barg + (size_t)f * nblk, nblk,
+                         s_pick[3] / kDecBlk, s_pick[4] / kDecBlk, &v, &t);
           if (lane == 0) {
             s_cmax[f] = v;
             s_carg[f] = t;
@@ -453,7 +509,8 @@ void launch_decode_notes(const float* note, const float* onset, const DecodeBuff
                                                     b.candbits, p.lo_col, p.hi_col, p.infer_onsets, p.onset_thresh, nullptr);
   }
   decode_seq_kernel<<<n_files, kSeqThreads, 0, st>>>(b.frame_off, b.energy, b.candbits, b.slot_off, b.note_count,
-                                                     b.note_start, b.note_end, b.note_pitch, b.overflow, p);
+                                                     b.note_start, b.note_end, b.note_pitch, b.overflow, b.blk_max,
+                                                     b.blk_arg, p);
 }
 
 // float64 inferred onsets of a batch of files (reference: note_creation.py:289-311): the two cell-parallel kernels of the

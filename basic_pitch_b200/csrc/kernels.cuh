@@ -157,7 +157,10 @@ struct DecodeBuffers {
   int* note_end;
   int* note_pitch;
   int* overflow;                  // [1] set when a file ran out of slots
+  float* blk_max;                 // [88 * decode_block_slots(total_frames, n_files)] per-column maxima of 256-frame blocks
+  int* blk_arg;                   //   (melodia loop of long files) and their frame indices
 };
+long long decode_block_slots(long long total_frames, int n_files);
 void launch_decode_notes(const float* note, const float* onset, const DecodeBuffers& buf, int n_files,
                          long long total_frames, const DecodeParamsDev& p, cudaStream_t st);
 void launch_infer_onsets(const float* note, const float* onset, const DecodeBuffers& buf, int n_files, long long total_frames,
