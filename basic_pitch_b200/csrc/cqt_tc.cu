@@ -160,6 +160,9 @@ __global__ void __launch_bounds__(cq::kThreads, 1) cqt_tc_kernel(const CqtTcArgs
       const int mt = it / kOctaves, o = it % kOctaves;
       const int hop = 256 >> o;
       const int len = octave_len(o);
+      // The staging area is shared by both paths (rows of a warp / planes of the item's segment): nobody may start
+      // writing it for this item while another producer warp still reads it for the previous one.
+      asm volatile("bar.sync 1, %0;" ::"n"(kProducers) : "memory");
       if (o >= kSegOctave) {
         // ---- octaves with hop <= 32: the 128 rows of the item overlap (by 7/8 .. 255/256 of their 256 taps), so the signal
         // segment they cover is loaded, reflect-padded and split three ways ONCE per item into bf16 planes in shared memory
@@ -174,7 +177,6 @@ __global__ void __launch_bounds__(cq::kThreads, 1) cqt_tc_kernel(const CqtTcArgs
         const int s0 = t0 * hop - 128, a0 = s0 & ~7, d0 = s0 - a0;  // part 0: first tap, aligned start, offset of the tap
         const int L0 = ((n0 - 1) * hop + kTaps + d0 + 7) & ~7;
         const int L1 = n0 < kMTile ? (((kMTile - n0 - 1) * hop + kTaps + 7) & ~7) : 0;  // part 1 starts at sample -128
-        asm volatile("bar.sync 1, %0;" ::"n"(kProducers) : "memory");  // the previous item's tile copies are done
         {
           // <= 9 samples per thread (126 * 32 + 2 * 256 + slack <= 9 * 512): all loads are issued before the first use
           constexpr int NS = (126 * 32 + 2 * kTaps + 32 + kProducers - 1) / kProducers;
