@@ -8,7 +8,7 @@ runtime here (the CUDA library in `csrc/`), so the default model file is the pac
 import enum
 import pathlib
 
-__version__ = "0.1.0"
+__version__ = "0.2.0"
 
 
 class FilenameSuffix(enum.Enum):

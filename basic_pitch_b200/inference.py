@@ -422,7 +422,11 @@ def run_inference(audio_path: Union[pathlib.Path, str], model_or_model_path: Uni
     if debug_file:
         n_overlap = DEFAULT_OVERLAPPING_FRAMES * FFT_HOP
         with open(debug_file, "w") as f:
+            hop = AUDIO_N_SAMPLES - n_overlap
+            padded = np.concatenate([np.zeros(n_overlap // 2, _F32), audio])
+            last = padded[(max(len(padded) - 1, 0) // hop) * hop :][:AUDIO_N_SAMPLES]  # the reference dumps the LAST window
             json.dump({
+                "audio_windowed": np.pad(last, (0, AUDIO_N_SAMPLES - len(last))).reshape(1, AUDIO_N_SAMPLES, 1).tolist(),
                 "audio_original_length": int(audio.shape[0]),
                 "hop_size_samples": AUDIO_N_SAMPLES - n_overlap,
                 "overlap_length_samples": n_overlap,
