@@ -2,6 +2,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -1259,26 +1260,58 @@ void bp_host_free(void* p) {
 }
 
 namespace {
-// copies the audio of files [f0, f1) into one contiguous pinned buffer with a few host threads
-void gather_files(const float* const* audio, const int64_t* rel, int f0, int f1, float* dst, int n_threads) {
-  const int64_t base = rel[f0], total = rel[f1] - base;
-  if (total <= 0) return;
-  n_threads = (int)std::max<int64_t>(1, std::min<int64_t>(n_threads, total / (1 << 20)));
-  auto work = [&](int t) {
-    // thread t copies samples [lo, hi) of the sub-batch: whole files where possible, split files otherwise
-    const int64_t lo = base + total * t / n_threads, hi = base + total * (t + 1) / n_threads;
-    int i = (int)(std::upper_bound(rel + f0, rel + f1 + 1, lo) - rel) - 1;
-    for (; i < f1 && rel[i] < hi; ++i) {
-      const int64_t a = std::max(lo, rel[i]), b = std::min(hi, rel[i + 1]);
-      if (b > a) std::memcpy(dst + (a - base), audio[i] + (a - rel[i]), sizeof(float) * (size_t)(b - a));
+// Host threads that copy the files of one sub-batch after the other into pinned staging buffers, running ahead of the
+// caller: worker t copies its share of sub-batch k as soon as the caller has released that buffer (`released` counts the
+// sub-batches whose buffer may be overwritten) and reports it in done[k].  The threads live for one call.
+struct Gatherer {
+  const float* const* audio;
+  const int64_t* rel;        // [n_files + 1] sample offsets
+  const int* cut;            // [n_sub + 1] file index where each sub-batch starts
+  int n_sub, n_threads;
+  float* const* stage;       // 3 staging buffers
+  std::atomic<int> released{0};
+  std::vector<std::atomic<int>> done;
+  std::vector<std::thread> threads;
+  std::atomic<bool> abort{false};
+
+  Gatherer(const float* const* a, const int64_t* r, const int* c, int ns, int nt, float* const* st)
+      : audio(a), rel(r), cut(c), n_sub(ns), n_threads(nt), stage(st), done(ns) {
+    for (auto& d : done) d.store(0);
+    for (int t = 0; t < n_threads; ++t) threads.emplace_back([this, t] { run(t); });
+  }
+  ~Gatherer() {
+    abort.store(true);
+    for (auto& x : threads) x.join();
+  }
+  void run(int t) {
+    for (int k = 0; k < n_sub; ++k) {
+      for (int spins = 0; released.load(std::memory_order_acquire) <= k; ++spins) {  // buffer k % 3 still holds k - 3
+        if (abort.load()) return;
+        if (spins < 64)
+          std::this_thread::yield();
+        else
+          std::this_thread::sleep_for(std::chrono::microseconds(50));  // do not fight the enqueueing thread for cores
+      }
+      const int f0 = cut[k], f1 = cut[k + 1];
+      const int64_t base = rel[f0], total = rel[f1] - base;
+      float* dst = stage[k % 3];
+      // thread t copies samples [lo, hi) of the sub-batch: whole files where possible, split files otherwise
+      const int64_t lo = base + total * t / n_threads, hi = base + total * (t + 1) / n_threads;
+      if (hi > lo) {
+        int i = (int)(std::upper_bound(rel + f0, rel + f1 + 1, lo) - rel) - 1;
+        for (; i < f1 && rel[i] < hi; ++i) {
+          const int64_t a = std::max(lo, rel[i]), b = std::min(hi, rel[i + 1]);
+          if (b > a) std::memcpy(dst + (a - base), audio[i] + (a - rel[i]), sizeof(float) * (size_t)(b - a));
+        }
+      }
+      done[k].fetch_add(1, std::memory_order_release);
     }
-  };
-  if (n_threads == 1) return work(0);
-  std::vector<std::thread> th;
-  for (int t = 1; t < n_threads; ++t) th.emplace_back(work, t);
-  work(0);
-  for (auto& x : th) x.join();
-}
+  }
+  void release_upto(int k) { released.store(k, std::memory_order_release); }  // sub-batches < k may be gathered
+  void wait(int k) {
+    while (done[k].load(std::memory_order_acquire) < n_threads) std::this_thread::yield();
+  }
+};
 }  // namespace
 
 int bp_transcribe_files_host(bp_model_t* m, const float* const* audio, const int64_t* n_samples, int32_t n_files,
@@ -1342,7 +1375,7 @@ int bp_transcribe_files_host(bp_model_t* m, const float* const* audio, const int
     CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     (m->copy_ev.size() < n_sub ? m->copy_ev : m->conv_ev).push_back(e);
   }
-  int n_threads = (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+  int n_threads = (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency() > 2 ? std::thread::hardware_concurrency() - 1 : 1u));
   if (const char* e = getenv("BP_B200_GATHER_THREADS")) n_threads = std::max(1, std::min(64, atoi(e)));
   const bool timing = getenv("BP_B200_TIMING") != nullptr;  // host-side breakdown of this call on stderr
   auto now = [] { return std::chrono::steady_clock::now(); };
@@ -1352,15 +1385,14 @@ int bp_transcribe_files_host(bp_model_t* m, const float* const* audio, const int
   CK(cudaStreamSynchronize(st));  // st_audio / st_note.. may still be in use by earlier work on the compute stream
   h_frame_off[0] = 0;
   std::vector<int64_t> sub_off;
+  Gatherer gatherer(audio, rel.data(), cut.data(), (int)n_sub, n_threads, m->gather);
+  gatherer.release_upto(std::min<int>(3, (int)n_sub));  // the three buffers are free: the workers start at once
   for (size_t k = 0; k < n_sub; ++k) {
     const int f0 = cut[k], f1 = cut[k + 1];
     const int64_t s0 = rel[f0], s1 = rel[f1];
     float* stage = m->gather[k % 3];
     auto t0 = now();
-    if (k >= 3) CK(cudaEventSynchronize(m->copy_ev[k - 3]));  // the buffer's previous upload has left the host
-    t_wait += ms_since(t0);
-    t0 = now();
-    gather_files(audio, rel.data(), f0, f1, stage, n_threads);
+    gatherer.wait((int)k);  // sub-batch k is in its staging buffer (gathered while earlier sub-batches were enqueued)
     t_gather += ms_since(t0);
     t0 = now();
     if (s1 > s0)
@@ -1371,6 +1403,12 @@ int bp_transcribe_files_host(bp_model_t* m, const float* const* audio, const int
     const int64_t base = h_frame_off[f0];
     rc = run_inference_internal(m, m->st_audio.p, rel.data() + f0, f1 - f0, u, base, sub_off.data(), st);
     if (rc) return rc;
+    if (k >= 1) {  // buffer (k - 1) % 3 = (k + 2) % 3 is free once the upload of sub-batch k - 1 has left the host
+      auto tw = now();
+      CK(cudaEventSynchronize(m->copy_ev[k - 1]));
+      t_wait += ms_since(tw);
+      gatherer.release_upto((int)std::min<size_t>(k + 3, n_sub));
+    }
     for (int i = f0; i < f1; ++i) h_frame_off[i + 1] = base + sub_off[i - f0 + 1];
     // this sub-batch's posteriorgrams: internal -> row-major, then to the host on their own stream while the next
     // sub-batches compute
