@@ -5,12 +5,15 @@ Tolerances (floating point, BASELINE.json north_star): posteriorgram max-abs <= 
 model; the FP32 path is expected (and required here) to stay within 1e-4 of the fp32 oracle.
 Integer work (note decode) must be bit-identical.
 """
+import pathlib
+
 import numpy as np
 import pytest
 
 from tests.golden_util import assert_events_equal, case_expected, case_params, dequant, events_to_arrays
 
 pytestmark = pytest.mark.gpu
+ROOT = pathlib.Path(__file__).resolve().parents[1]
 
 POST_TOL = 1e-4  # vs the fp32 oracle on identical 22 050 Hz input
 GOLD_TOL = 5e-4  # vs the reference's golden file (44.1 kHz source, resampler differs; see tests/golden/README.md)
@@ -607,3 +610,38 @@ def test_predict_and_save_batch_path(model, tmp_path):
         zb = np.load(out_s / f"{p.stem}_basic_pitch.npz", allow_pickle=True)["basic_pitch_model_output"].item()
         for k in ("note", "onset", "contour"):
             np.testing.assert_array_equal(za[k], zb[k])
+
+
+@pytest.mark.gpu
+def test_tensor_map_tma_path_matches_default():
+    """BP_B200_TMAP=1: the conv data tile is fetched by one tensor-map TMA (cp.async.bulk.tensor.4d) instead of 78 1-D bulk
+    copies — an alternative staging of the same bytes, so the posteriorgrams must be bit-identical (run in a subprocess:
+    the switch is read once per process)."""
+    import os
+    import subprocess
+    import sys
+    import textwrap
+
+    code = textwrap.dedent("""
+        import sys, hashlib, numpy as np
+        sys.path.insert(0, %r)
+        from basic_pitch_b200 import ICASSP_2022_MODEL_PATH, synth
+        from basic_pitch_b200.inference import Model
+        m = Model(ICASSP_2022_MODEL_PATH)
+        out = m.run_inference_arrays([synth.tones_clip(25.0, seed=5), synth.tones_clip(3.0, seed=6)])
+        h = hashlib.sha256()
+        for o in out:
+            for k in ("note", "onset", "contour"):
+                h.update(np.ascontiguousarray(o[k]).tobytes())
+        print(h.hexdigest())
+    """) % str(ROOT)
+    digests = []
+    for flag in (None, "1"):
+        env = dict(os.environ)
+        env.pop("BP_B200_TMAP", None)
+        if flag:
+            env["BP_B200_TMAP"] = flag
+        r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        digests.append(r.stdout.strip().splitlines()[-1])
+    assert digests[0] == digests[1] and len(digests[0]) == 64
