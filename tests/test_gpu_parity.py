@@ -506,6 +506,11 @@ def test_transcribe_files_host_equals_packed_entry_point(model):
         np.testing.assert_array_equal(a[4][key], b[4][key])
     np.testing.assert_array_equal(a[5], b[5])
     assert int(a[5][n]) > 50
+    # degenerate batches through the Python mirror
+    outs, res, frames = model.transcribe_arrays([])
+    assert outs == [] and res == [] and frames == []
+    outs, res, frames = model.transcribe_arrays([np.zeros(0, np.float32)])
+    assert frames == [0] and outs[0]["note"].shape == (0, 88) and len(res[0]["start"]) == 0
 
 
 @pytest.mark.gpu
