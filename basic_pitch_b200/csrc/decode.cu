@@ -581,27 +581,21 @@ __global__ void note_finish_kernel(const float* __restrict__ note, const float* 
   const int shift = 25 - g0;
   const int width = hi - lo;           // <= 51
   int* out = bends + bend_off[n];
-  for (int t = t0; t < t1; ++t) {
+  // one frame per lane (a note has 11 .. a few dozen frames): every lane walks its frame's <= 51 bins in ascending order
+  // and keeps the first maximum — np.argmax semantics without any cross-lane reduction
+  for (int t = t0 + lane; t < t1; t += 32) {
     const float* row = contour + (base + t) * kContourBins + lo;
     double bv = -INFINITY;  // np.argmax semantics for any input (callers may pass contours < 0)
-    int bi = 0x7fffffff;
-    for (int j = lane; j < width; j += 32) {
-      double v = __dmul_rn((double)row[j], gauss[g0 + j]);
+    int bi = 0;
+#pragma unroll 4
+    for (int j = 0; j < width; ++j) {
+      const double v = __dmul_rn((double)__ldg(row + j), gauss[g0 + j]);
       if (v > bv) {
         bv = v;
         bi = j;
       }
     }
-#pragma unroll
-    for (int o = 16; o; o >>= 1) {
-      double ov = __shfl_xor_sync(0xffffffffu, bv, o);
-      int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-      if (ov > bv || (ov == bv && oi < bi)) {
-        bv = ov;
-        bi = oi;
-      }
-    }
-    if (lane == 0) out[t - t0] = bi - shift;
+    out[t - t0] = bi - shift;
   }
 }
 
