@@ -873,21 +873,24 @@ __global__ void __launch_bounds__(tc::kThreads, 1) conv_tc_kernel(const __grid_c
 
   if (warp == kProducerWarp) {
     // ------------------------------ producer ------------------------------
-    if (lane == 0) {
-      if constexpr (kFused) {
-        constexpr uint32_t b2_bytes = (uint32_t)B2.n_tiles * 2u * 16u * B2.n2 * 2u;
-        static_assert(b2_bytes <= (uint32_t)SM.b2_bytes, "conv2 weight tiles");
-        mbar_expect_tx(b2_full, b2_bytes);
-        bulk_g2s(s_b2, a.b2, b2_bytes, b2_full);
-      }
-      uint32_t stage = 0, ph_w = 0, ph_d = 0;
-      const size_t plane_elems = (size_t)a.chunks8 * a.rows_total * 8;
-      for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
-        const int mt = it / a.n_split, sp = it % a.n_split;
-        const int g0 = sp * a.n_groups / a.n_split, g1 = (sp + 1) * a.n_groups / a.n_split;
-        mbar_wait_wd(data_empty, ph_d ^ 1, 1);
+    // The whole warp walks the loop with warp-uniform state; the arrive / copy instructions are predicated on the elected
+    // lane.  (With `if (lane == 0)` the compiler put an elect loop and three R2UR around every UBLKCP; the weight ring is
+    // paced by this loop's latency per step — adding a division to it slowed the contour kernel by 70 %.)
+    const uint32_t leader = elect_one() ? 1u : 0u;
+    if constexpr (kFused) {
+      constexpr uint32_t b2_bytes = (uint32_t)B2.n_tiles * 2u * 16u * B2.n2 * 2u;
+      static_assert(b2_bytes <= (uint32_t)SM.b2_bytes, "conv2 weight tiles");
+      bulk_g2s_expect_pred(s_b2, a.b2, b2_bytes, b2_full, leader);
+    }
+    uint32_t stage = 0, ph_w = 0, ph_d = 0;
+    const size_t plane_elems = (size_t)a.chunks8 * a.rows_total * 8;
+    for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+      const int mt = it / a.n_split, sp = it % a.n_split;
+      const int g0 = sp * a.n_groups / a.n_split, g1 = (sp + 1) * a.n_groups / a.n_split;
+      mbar_wait_wd(data_empty, ph_d ^ 1, 1);
+      const size_t row = (size_t)mt * a.ms + a.row0;
+      if (leader) {
         mbar_expect_tx(data_full, 2 * plane_bytes);
-        const size_t row = (size_t)mt * a.ms + a.row0;
         if (a.use_tmap) {  // one tensor-map TMA for the whole (planes x chunks x rows x 8 elements) tile
           tma_load_4d(s_data, &a.data_map, 0, (int)row, 0, 0, data_full);
         } else {
@@ -896,25 +899,26 @@ __global__ void __launch_bounds__(tc::kThreads, 1) conv_tc_kernel(const __grid_c
               bulk_g2s(s_data + p * plane_bytes + c * lbo, a.data + p * plane_elems + ((size_t)c * a.rows_total + row) * 8,
                        lbo, data_full);
         }
-        ph_d ^= 1;
-        const int s0 = c_group_step_off[a.layer][g0], s1 = c_group_step_off[a.layer][g1];
-        for (int s = s0; s < s1; ++s) {
-          mbar_wait_wd(empty_w + stage, ph_w ^ 1, 2);
+      }
+      __syncwarp();
+      ph_d ^= 1;
+      const int s0 = c_group_step_off[a.layer][g0], s1 = c_group_step_off[a.layer][g1];
+      int tile = c_tile_seq[a.layer][s0];
+      for (int s = s0; s < s1; ++s) {
+        const int tile_next = c_tile_seq[a.layer][s + 1];  // (one past the end is inside the array)
+        mbar_wait_wd(empty_w + stage, ph_w ^ 1, 2);
 #ifdef BP_TC_TRACE
-          if (a.dbg_skip_loads) {
-            mbar_arrive(full_w + stage);
-          } else
+        if (a.dbg_skip_loads) {
+          if (leader) mbar_arrive(full_w + stage);
+        } else
 #endif
-          {
-            mbar_expect_tx(full_w + stage, kTileBytes);
-            bulk_g2s(s_w + stage * kTileBytes, a.tiles + (size_t)c_tile_seq[a.layer][s] * (kTileBytes / 2), kTileBytes,
-                     full_w + stage);
-          }
-          if (++stage == kStages) {
-            stage = 0;
-            ph_w ^= 1;
-          }
+          bulk_g2s_expect_pred(s_w + stage * kTileBytes, a.tiles + (size_t)tile * (kTileBytes / 2), kTileBytes, full_w + stage,
+                               leader);
+        if (++stage == kStages) {
+          stage = 0;
+          ph_w ^= 1;
         }
+        tile = tile_next;
       }
     }
   } else if (warp == kMmaWarp0 || warp == kMmaWarp1) {

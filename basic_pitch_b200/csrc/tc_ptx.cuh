@@ -114,6 +114,20 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const void* tmap, in
       "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
+// expect_tx + bulk copy by the elected lane only (PTX predication): with warp-uniform operands the producer loop stays on
+// the uniform datapath (no per-step R2UR / elect loop around UBLKCP)
+__device__ __forceinline__ void bulk_g2s_expect_pred(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar,
+                                                     uint32_t leader) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred q;\n\t"
+      "setp.ne.b32 q, %4, 0;\n\t"
+      "@q mbarrier.arrive.expect_tx.shared::cta.b64 _, [%3], %2;\n\t"
+      "@q cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n\t"
+      "}\n" ::"r"(smem_u32(smem_dst)),
+      "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)), "r"(leader)
+      : "memory");
+}
 // K-major, no-swizzle shared-memory matrix descriptor (SM100 "version 1"):
 //   [0,14) start >> 4, [16,30) leading-dimension byte offset >> 4 (between the two 8-element k-chunks),
 //   [32,46) stride byte offset >> 4 (between 8-row groups), [46,48) = 1, layout type [61,64) = 0.
