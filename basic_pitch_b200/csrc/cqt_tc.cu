@@ -118,7 +118,7 @@ __global__ void __launch_bounds__(cq::kThreads, 1) cqt_tc_kernel(const CqtTcArgs
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) {
-      mbar_init(full + s, kProducers);
+      mbar_init(full + s, kProducers / 32);  // one arrival per producer warp (512 single arrivals per chunk serialise)
       mbar_init(empty + s, 1);
     }
     for (int i = 0; i < 2; ++i) {
@@ -235,7 +235,8 @@ __global__ void __launch_bounds__(cq::kThreads, 1) cqt_tc_kernel(const CqtTcArgs
             *reinterpret_cast<uint4*>(sa + pl * kAPlane + (kc * kMTile + row) * 16) = v;
           }
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-          mbar_arrive(full + stage);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(full + stage);
           if (++stage == kStages) {
             stage = 0;
             ph ^= 1;
@@ -348,7 +349,8 @@ __global__ void __launch_bounds__(cq::kThreads, 1) cqt_tc_kernel(const CqtTcArgs
           *reinterpret_cast<uint4*>(sa + 2 * kAPlane + o16) = *reinterpret_cast<const uint4*>(l);
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the MMA
-        mbar_arrive(full + stage);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(full + stage);
         if (++stage == kStages) {
           stage = 0;
           ph ^= 1;
