@@ -34,6 +34,34 @@ __host__ __device__ constexpr int chain_off(int o) {  // o >= 1
   return off;
 }
 constexpr int kChainStride = (chain_off(8) + octave_len(8) + 3 + 31) & ~31;
+// The same two functions for an octave index only known at run time: a switch over constant-folded values (the loops
+// above cost hundreds of cycles per call when `o` is not a compile-time constant — found in the CQT producers' trace).
+__device__ __forceinline__ int octave_len_rt(int o) {
+  switch (o) {
+    case 0: return octave_len(0);
+    case 1: return octave_len(1);
+    case 2: return octave_len(2);
+    case 3: return octave_len(3);
+    case 4: return octave_len(4);
+    case 5: return octave_len(5);
+    case 6: return octave_len(6);
+    case 7: return octave_len(7);
+    default: return octave_len(8);
+  }
+}
+__device__ __forceinline__ int chain_off_rt(int o) {
+  switch (o) {
+    case 1: return chain_off(1);
+    case 2: return chain_off(2);
+    case 3: return chain_off(3);
+    case 4: return chain_off(4);
+    case 5: return chain_off(5);
+    case 6: return chain_off(6);
+    case 7: return chain_off(7);
+    default: return chain_off(8);
+  }
+}
+
 
 // Where window w's samples come from: sample j = (lo <= j < hi) ? audio[base + j] : 0.
 struct WinDesc {

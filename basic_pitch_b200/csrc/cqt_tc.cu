@@ -24,6 +24,8 @@
 // Shared memory: 2 stages x (48 KB A + 30 KB W); TMEM: 2 accumulators of 128 x 80 (256 columns allocated).
 #include <cuda_bf16.h>
 
+#include <cstdio>
+#include <cstdlib>
 #include <vector>
 
 #include "kernels.cuh"
@@ -100,7 +102,14 @@ struct CqtTcArgs {
   float* logmag;         // [B][172][309]
   unsigned int* minmax;  // [B][2] ordered-uint min / max
   int n_windows, n_mtiles;
+  long long* trace;  // -DBP_TC_TRACE: [item][16] clock64 stamps of CTA 0
 };
+
+#ifdef BP_TC_TRACE
+#define CQ_TRACE(i, ev) do { if (a.trace && blockIdx.x == 0 && (i) < 64 && (threadIdx.x & 31) == 0) a.trace[(i) * 16 + (ev)] = clock64(); } while (0)
+#else
+#define CQ_TRACE(i, ev) do { } while (0)
+#endif
 
 __global__ void __launch_bounds__(cq::kThreads, 1) cqt_tc_kernel(const CqtTcArgs a) {
   using namespace cq;
@@ -156,13 +165,17 @@ __global__ void __launch_bounds__(cq::kThreads, 1) cqt_tc_kernel(const CqtTcArgs
     RowP* rowp = reinterpret_cast<RowP*>(smem + kStages * kStageBytes + 256 + kEpiBytes +
                                          kMTile * kStgPitch * 4) + RW * pw;  // this warp's rows
     uint32_t stage = 0, ph = 0;
+    int icnt = -1;
     for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+      ++icnt;
       const int mt = it / kOctaves, o = it % kOctaves;
       const int hop = 256 >> o;
-      const int len = octave_len(o);
+      if (pw == 0) CQ_TRACE(icnt, 0);  // producer warp 0 starts the item
+      const int len = octave_len_rt(o);
       // The staging area is shared by both paths (rows of a warp / planes of the item's segment): nobody may start
       // writing it for this item while another producer warp still reads it for the previous one.
       asm volatile("bar.sync 1, %0;" ::"n"(kProducers) : "memory");
+      if (pw == 0) CQ_TRACE(icnt, 14);  // all producer warps are done with the previous item
       if (o >= kSegOctave) {
         // ---- octaves with hop <= 32: the 128 rows of the item overlap (by 7/8 .. 255/256 of their 256 taps), so the signal
         // segment they cover is loaded, reflect-padded and split three ways ONCE per item into bf16 planes in shared memory
@@ -190,9 +203,10 @@ __global__ void __launch_bounds__(cq::kThreads, 1) cqt_tc_kernel(const CqtTcArgs
             if (i < 0) i = -i;
             if (i >= len) i = 2 * (len - 1) - i;
             xs[q] = (idx < L0 + L1 && b < a.n_windows && i >= 0 && i < len)
-                        ? __ldg(a.chain + (size_t)b * kChainStride + chain_off(o) + i)
+                        ? __ldg(a.chain + (size_t)b * kChainStride + chain_off_rt(o) + i)
                         : 0.f;
           }
+          if (pw == 0 && xs[0] != 123456.f) CQ_TRACE(icnt, 15);  // first load has arrived
 #pragma unroll
           for (int q = 0; q < NS; ++q) {
             const int idx = ptid + q * kProducers;
@@ -208,8 +222,10 @@ __global__ void __launch_bounds__(cq::kThreads, 1) cqt_tc_kernel(const CqtTcArgs
           }
         }
         asm volatile("bar.sync 1, %0;" ::"n"(kProducers) : "memory");
+        if (pw == 0) CQ_TRACE(icnt, 1);  // segment staged
         for (int c = 0; c < kTaps / kKc; ++c) {
           mbar_wait(empty + stage, ph ^ 1);
+          if (pw == 0) CQ_TRACE(icnt, 2 + c);  // stage acquired for chunk c
           unsigned char* sa = smem + stage * kStageBytes;
           if (ptid == 0) {
             mbar_expect_tx_only(full + stage, 3 * kWPlane);
@@ -263,7 +279,7 @@ __global__ void __launch_bounds__(cq::kThreads, 1) cqt_tc_kernel(const CqtTcArgs
             p.src = a.audio + (long long)b * kWinSamples;
           }
         } else {
-          p.src = a.chain + (size_t)b * kChainStride + chain_off(o);
+          p.src = a.chain + (size_t)b * kChainStride + chain_off_rt(o);
         }
         p.i0 = t * hop - 128;  // signal index of tap 0 of this frame
         rowp[lane] = p;
@@ -324,6 +340,7 @@ __global__ void __launch_bounds__(cq::kThreads, 1) cqt_tc_kernel(const CqtTcArgs
           }
         }
         mbar_wait(empty + stage, ph ^ 1);
+        if (pw == 0) CQ_TRACE(icnt, 2 + c);
         unsigned char* sa = smem + stage * kStageBytes;
         if (ptid == 0) {
           mbar_expect_tx_only(full + stage, 3 * kWPlane);  // the bulk copy of the W slice completes on the same barrier
@@ -369,8 +386,10 @@ __global__ void __launch_bounds__(cq::kThreads, 1) cqt_tc_kernel(const CqtTcArgs
       ph_t[buf] ^= 1;
       tc_fence_after();
       const uint32_t d = tmem_base + buf * 128u;
+      CQ_TRACE(icount, 6);  // accumulator acquired
       for (int c = 0; c < kTaps / kKc; ++c) {
         mbar_wait(full + stage, ph);
+        CQ_TRACE(icount, 7 + c);  // chunk c's operands arrived
         tc_fence_after();
         // descriptors as (low word, shared high word); everything here is warp-uniform, the MMAs themselves are
         // predicated on the elected lane inside the asm block: the loop stays on the uniform datapath (no R2UR per MMA)
@@ -393,6 +412,7 @@ __global__ void __launch_bounds__(cq::kThreads, 1) cqt_tc_kernel(const CqtTcArgs
         }
       }
       umma_commit_pred(tmem_full + buf, leader);
+      CQ_TRACE(icount, 11);  // all MMAs of the item issued
       ++icount;
     }
   } else {
@@ -415,6 +435,7 @@ __global__ void __launch_bounds__(cq::kThreads, 1) cqt_tc_kernel(const CqtTcArgs
       mbar_wait(tmem_full + buf, ph_t[buf]);
       ph_t[buf] ^= 1;
       tc_fence_after();
+      if (warp == 0) CQ_TRACE(icount, 12);  // epilogue saw the accumulator
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * 128u + (uint32_t)(2 * bin0);
       float vmin = INFINITY, vmax = -INFINITY;
       const int g0 = (8 - o) * kBinsPerOctave - 15 + bin0;  // global bin of this warp's first bin (negative for the lowest of o = 8)
@@ -487,6 +508,7 @@ __global__ void __launch_bounds__(cq::kThreads, 1) cqt_tc_kernel(const CqtTcArgs
         atomicMin(a.minmax + 2 * b, float_to_ordered(vmin));
         atomicMax(a.minmax + 2 * b + 1, float_to_ordered(vmax));
       }
+      if (warp == 0) CQ_TRACE(icount, 13);  // epilogue done
       ++icount;
     }
   }
@@ -514,6 +536,16 @@ void launch_cqt_tc(const float* audio, const WinDesc* desc, const float* chain, 
                    float* logmag, unsigned int* minmax, int n_windows, int n_sms, cudaStream_t st) {
   minmax_init_kernel2<<<(n_windows + 255) / 256, 256, 0, st>>>(minmax, n_windows);
   CqtTcArgs a;
+  a.trace = nullptr;
+#ifdef BP_TC_TRACE
+  static long long* d_trace = nullptr;
+  const bool tracing = getenv("BP_TC_TRACE") != nullptr;
+  if (tracing) {
+    if (!d_trace) cudaMalloc(&d_trace, 64 * 16 * sizeof(long long));
+    cudaMemsetAsync(d_trace, 0, 64 * 16 * sizeof(long long), st);
+    a.trace = d_trace;
+  }
+#endif
   a.audio = audio;
   a.desc = desc;
   a.chain = chain;
@@ -526,6 +558,19 @@ void launch_cqt_tc(const float* audio, const WinDesc* desc, const float* chain, 
   const int n_items = a.n_mtiles * kOctaves;
   const int grid = n_items < n_sms ? n_items : n_sms;
   cqt_tc_kernel<<<grid, cq::kThreads, cq::kSmemBytes, st>>>(a);
+#ifdef BP_TC_TRACE
+  if (tracing) {
+    static long long h[64 * 16];
+    cudaMemcpyAsync(h, d_trace, sizeof(h), cudaMemcpyDeviceToHost, st);
+    cudaStreamSynchronize(st);
+    fprintf(stderr, "cqt_trace n_items %d grid %d (columns: item start, segment staged, stage acquired c0..c3, acc acquired, operands arrived c0..c3, MMAs issued, epilogue saw, epilogue done)\n", n_items, grid);
+    for (int i = 0; i < 64 && h[i * 16]; ++i) {
+      fprintf(stderr, "item %2d (octave %d):", i, (i * grid) % 9);
+      for (int e = 0; e < 16; ++e) fprintf(stderr, " %7lld", h[i * 16 + e] ? h[i * 16 + e] - h[0] : -1);
+      fprintf(stderr, "\n");
+    }
+  }
+#endif
 }
 
 }  // namespace bp

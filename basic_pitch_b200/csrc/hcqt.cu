@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(kTailThreads) decimate_tail_kernel(float* __re
   int cur = 0;
 #pragma unroll 1
   for (int stage = kTailFirst; stage < 8; ++stage) {
-    const int len_out = octave_len(stage + 1);
+    const int len_out = octave_len_rt(stage + 1);
     float* nxt = buf[cur ^ 1];
     for (int i = tid; i < 16 * kTailS; i += kTailThreads) nxt[i] = 0.f;
     __syncthreads();  // cur is complete, nxt is zero
@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(kTailThreads) decimate_tail_kernel(float* __re
     if (n < len_out) {
       float o[8];
       fir8<kTailS>(buf[cur], tid, o);
-      float* d = c + chain_off(stage + 1);
+      float* d = c + chain_off_rt(stage + 1);
 #pragma unroll
       for (int i = 0; i < 8; ++i)
         if (n + i < len_out) {
@@ -194,7 +194,7 @@ __global__ void __launch_bounds__(kCqtThreads) cqt_kernel(const float* __restric
   const int b = blockIdx.y;
   const int o = blockIdx.x;  // octave, 0 = top
   const int hop = 256 >> o;
-  const int len = octave_len(o);
+  const int len = octave_len_rt(o);
 
   long long base = 0;
   int lo = 0, hi = len;
@@ -210,7 +210,7 @@ __global__ void __launch_bounds__(kCqtThreads) cqt_kernel(const float* __restric
     }
     src = audio;
   } else {
-    src = chain + (size_t)b * kChainStride + chain_off(o);
+    src = chain + (size_t)b * kChainStride + chain_off_rt(o);
   }
 
   const int tid = threadIdx.x;
