@@ -202,6 +202,36 @@ __device__ __forceinline__ void umma_bf16_x6(uint32_t tmem_d, uint32_t a_h, uint
       "r"(a_h), "r"(a_m), "r"(a_l), "r"(b_h), "r"(b_m), "r"(b_l), "r"(desc_hi32), "r"(idesc), "r"(accumulate), "r"(leader)
       : "memory");
 }
+// Six products of a three-way split with the A operand in tensor memory (TS form): a_* are tensor-memory addresses (K = 16 ->
+// 8 columns each), b_* descriptor low words.  D (+)= Ah*Bh ; += Ah*Bm ; += Am*Bh ; += Ah*Bl ; += Al*Bh ; += Am*Bm.
+__device__ __forceinline__ void umma_ts_bf16_x6(uint32_t tmem_d, uint32_t a_h, uint32_t a_m, uint32_t a_l, uint32_t b_h,
+                                                uint32_t b_m, uint32_t b_l, uint32_t desc_hi32, uint32_t idesc,
+                                                uint32_t accumulate, uint32_t leader) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, q, t;\n\t"
+      ".reg .b64 dbh, dbm, dbl;\n\t"
+      "setp.ne.b32 p, %9, 0;\n\t"
+      "setp.ne.b32 q, %10, 0;\n\t"
+      "setp.eq.b32 t, 0, 0;\n\t"
+      "mov.b64 dbh, {%4, %7};\n\t"
+      "mov.b64 dbm, {%5, %7};\n\t"
+      "mov.b64 dbl, {%6, %7};\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], dbh, %8, p;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], dbm, %8, t;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%2], dbh, %8, t;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], dbl, %8, t;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%3], dbh, %8, t;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%2], dbm, %8, t;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "r"(a_h), "r"(a_m), "r"(a_l), "r"(b_h), "r"(b_m), "r"(b_l), "r"(desc_hi32), "r"(idesc), "r"(accumulate), "r"(leader)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(v[0]),
+               "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
 __device__ __forceinline__ void umma_commit_pred(uint64_t* bar, uint32_t leader) {
   asm volatile(
       "{\n\t"

@@ -650,3 +650,38 @@ def test_tensor_map_tma_path_matches_default():
         assert r.returncode == 0, r.stderr[-2000:]
         digests.append(r.stdout.strip().splitlines()[-1])
     assert digests[0] == digests[1] and len(digests[0]) == 64
+
+
+@pytest.mark.gpu
+def test_cqt_shared_memory_operand_kernel_matches_default():
+    """BP_B200_CQT_SS=1 selects cqt_tc_kernel (A operand staged in shared memory) instead of the default cqt_ts_kernel (A
+    operand written to tensor memory by the producers): same split, same products in the same order -> bit-identical
+    posteriorgrams (subprocesses: the switch is read once per process)."""
+    import os
+    import subprocess
+    import sys
+    import textwrap
+
+    code = textwrap.dedent("""
+        import sys, hashlib, numpy as np
+        sys.path.insert(0, %r)
+        from basic_pitch_b200 import ICASSP_2022_MODEL_PATH, synth
+        from basic_pitch_b200.inference import Model
+        m = Model(ICASSP_2022_MODEL_PATH)
+        out = m.run_inference_arrays([synth.tones_clip(25.0, seed=5), synth.tones_clip(3.0, seed=6), np.zeros(5000, np.float32)])
+        h = hashlib.sha256()
+        for o in out:
+            for k in ("note", "onset", "contour"):
+                h.update(np.ascontiguousarray(o[k]).tobytes())
+        print(h.hexdigest())
+    """) % str(ROOT)
+    digests = []
+    for flag in (None, "1"):
+        env = dict(os.environ)
+        env.pop("BP_B200_CQT_SS", None)
+        if flag:
+            env["BP_B200_CQT_SS"] = flag
+        r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        digests.append(r.stdout.strip().splitlines()[-1])
+    assert digests[0] == digests[1] and len(digests[0]) == 64
