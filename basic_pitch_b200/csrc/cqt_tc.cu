@@ -10,6 +10,9 @@
 // (`get_cqt_complex`, reflect pad + two strided conv1d per octave), :642-661 (concat, sqrt(len) scaling, magnitude) and
 // layers/signal.py:174-176 (power -> 10*log10(. + 1e-10)); the per-window min / max feed lognorm_kernel (hcqt.cu).
 //
+// Two kernels compute it: cqt_ts_kernel (default, further down: A operand written to TENSOR memory by the producers,
+// TS-form MMAs) and cqt_tc_kernel (BP_B200_CQT_SS=1: A operand staged in shared memory, described next).
+//
 // The A operand is an overlapping strided view of the signal (row t starts at sample t*hop), which no UMMA/TMA
 // descriptor can express for hop*4 B < 16 B or non-canonical pitches, so it is staged explicitly ("im2col" into the
 // canonical K-major core-matrix layout) by four producer warps that also do the reflect padding and the hi/lo split.
