@@ -475,23 +475,7 @@ __device__ __forceinline__ void slot_barrier(int slot) {  // the four epilogue w
 // thread.  Sources inside the warp come by shuffle; lanes < a of warps 1..3 take them from the values the previous warp
 // published (lanes 32-a .. 31 -> entries a(a-1)/2 + lane - (32-a)) after the slot barrier (time_edges).  A lane adds
 // a = 0, 1, .., 2H in this order in both places, so the rounding of a frame does not depend on its row in the tile.
-template <int H, int NJ>
-__device__ __forceinline__ void time_tap(float (&S)[NJ], const float (&P)[NJ], int a, int lane, float* pub) {
-  if (a == 0) {
-#pragma unroll
-    for (int j = 0; j < NJ; ++j) S[j] += P[j];
-    return;
-  }
-  const bool ok = lane >= a;
-  const bool publish = lane >= 32 - a;
-  float* e = pub + (a * (a - 1) / 2 + lane - (32 - a)) * NJ;
-#pragma unroll
-  for (int j = 0; j < NJ; ++j) {
-    const float v = __shfl_up_sync(0xffffffffu, P[j], a);
-    if (ok) S[j] += v;
-    if (publish) e[j] = P[j];
-  }
-}
+// (The in-warp part is written out in pitch_tile_taps / contour_tile, the cross-warp part is time_edges.)
 template <int H, int NJ>
 __device__ __forceinline__ void time_edges(float (&S)[NJ], int quad, int lane, const float* xb /* [3][XF] */, int XF) {
   if (quad == 0) return;
@@ -557,7 +541,7 @@ __device__ __forceinline__ void convert_tile(uint32_t taddr, bool live, int n_va
 // Onset / note layers after the conv2 MMAs: the conv2 accumulator holds, for the thread's frame, P[j][dt] (column
 // j * JS + dt) = sum over channels and frequency taps for output offset j = 0 .. 5 (bins 4 ft - 1 + j) and time tap dt.
 // Reads them, zeroes the accumulator and hands it back, then sums the time taps: S[j] = sum_dt P[j][dt][frame + dt - H],
-// sources inside the warp by shuffle, the top lanes published for the next warp (see time_tap).
+// sources inside the warp by shuffle, the top lanes published for the next warp (see time_edges).
 template <int KH2>
 __device__ __forceinline__ void pitch_tile_taps(uint32_t d2, int lane, int quad, float* pub, uint64_t* d2_empty, float (&S)[6]) {
   const int pub_from = quad < 3 ? 32 : 64;  // the last warp of a slot publishes nothing
@@ -669,7 +653,7 @@ __device__ __forceinline__ void store_contour_chunk(const TcArgs& a, const RowOu
 
 // Contour layer after the conv2 MMAs (8 -> 1 channels, 5 x 5 taps, models.py:252-259): the conv2 accumulator holds
 //   P[j][dt] (column j * 5 + dt) = sum_{c, df} relu(conv1)[c][t][16 ft + j + df - 4] * w2[c][dt][df]     j = 0 .. 19
-// for output bins 16 ft - 2 + j of the thread's frame.  Time taps by shuffles (time_tap), frequency halo by register
+// for output bins 16 ft - 2 + j of the thread's frame.  Time taps by shuffles (see time_edges), frequency halo by register
 // carry, then sigmoid and the stores.
 __device__ __forceinline__ void contour_tile(const TcArgs& a, const RowOut& ro, uint32_t d2, uint64_t* d2_empty, int ft,
                                              bool first, bool last, int quad, int lane, int slot, float* xb,

@@ -1,5 +1,6 @@
 """CPU: the index arithmetic of the fused second convolutions in the epilogues of the tensor-core kernels
-(csrc/tc_conv.cu: contour_tile, pitch_tile_sums, time_tap / time_taps_col / time_edges, finish_pitch_tile, edge_fix_kernel),
+(csrc/tc_conv.cu: convert_tile + the TS-form conv2 MMAs, contour_tile, pitch_tile_taps, time_edges, finish_pitch_tile,
+edge_fix_kernel),
 restated in NumPy with the SAME structure and compared with the direct convolution of the oracle:
 
   * per frequency tile of FLT bins the thread of a frame reduces relu(conv1) over channels and frequency taps into
