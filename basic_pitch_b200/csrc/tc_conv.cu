@@ -10,7 +10,8 @@
 // One kernel template, three specs (TcConvSpec).  The epilogue (EPI 1 / 2 / 3 = onset / note / contour) also computes
 // the FOLLOWING single-output convolution (onset conv2 models.py:305-313, note conv2 :282-290, contour conv2 :254-262)
 // completely, so neither the 8- / 32-channel activations nor any partial sums of them reach HBM:
-//   * channels and frequency taps are reduced inside the thread that owns the frame (packed FP32 FMAs),
+//   * channels and frequency taps are reduced by a SECOND tensor-core contraction whose A operand is bias + ReLU of the
+//     accumulator, split to bf16 hi/lo and written back into the same tensor-memory columns (TS-form MMAs, see TcB2),
 //   * the time taps are summed across the lanes of the warp (the 32 lanes hold 32 consecutive frames: shuffles) and
 //     across the four epilogue warps of an accumulator slot through a small shared-memory exchange; M-tiles overlap
 //     by KH2 - 1 rows, so every frame is complete in exactly one tile.  The thread of tile row r finishes the output
@@ -42,17 +43,18 @@
 // (SURVEY.md Appendix C.4); a single bf16 product would miss the 1e-3 bar.
 //
 // Work decomposition: item = (M-tile of 128 rows, split s of S over the frequency groups); group g = the two
-// frequency tiles {g, g + G0} (they share weight tiles; 2 x 128 TMEM columns; the 512 columns hold two groups, so the
-// epilogue of one group overlaps the MMAs of the next).  A CTA (1 per SM, persistent) walks items
+// frequency tiles {g, g + G0} (two accumulator slots; shared weight tiles where their content is equal).  Tensor memory:
+// three 128-column conv1 accumulator regions used as a ring + the conv2 accumulators.  A CTA (1 per SM, persistent) walks items
 // i = blockIdx.x, +gridDim.x, ...:
 //   warp 8      producer: bulk-copies the (128+KH-1) x 320 bf16 hi/lo data tile (k-chunk-major) once per item and
-//               streams the weight tiles of each group's program (8 KB each) through a 6-stage ring
+//               streams the weight tiles of each group's program (8 KB each) through a 7- / 9-stage ring
 //   warps 9, 10 MMA issuers, one per accumulator slot of the group (instruction issue, not the tensor pipe, limits
 //               a single issuing warp at this MMA size): program words from constant memory, descriptors are
 //               base + precomputed offset, 3 x tcgen05.mma per step by one elected lane, tcgen05.commit frees the
 //               weight stage / publishes the accumulators
+//   warp 11     conv2 MMA issuer (A operand in tensor memory)
 //   warps 0-3, 4-7  epilogue, one warpgroup-like set of 4 warps (= the 4 TMEM lane quadrants) per accumulator slot:
-//               tcgen05.ld the accumulator columns, + bias, ReLU, then the whole next conv as described above
+//               tcgen05.ld the accumulator columns, + bias, ReLU, split, tcgen05.st; then the conv2 sums as described above
 #include <cuda.h>  // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint)
 #include <cuda_bf16.h>
 
