@@ -393,3 +393,16 @@ def test_streaming_windowing_equals_whole_file_windowing():
                 got = np.concatenate([q[k] for q in parts]) if parts else np.zeros((0, width), np.float32)
                 want = ref[k] if ref is not None else np.zeros((0, width), np.float32)
                 assert got.shape == want.shape and np.array_equal(got, want), (n, block, k)
+
+
+def test_batched_writer_reports_unwritable_paths(tmp_path):
+    """bp_write_note_files: a path that cannot be opened is an error (BpError), files before it are still written."""
+    from basic_pitch_b200 import _lib
+    from basic_pitch_b200 import note_creation as nc
+
+    ev = [[(0.1, 0.5, 60, np.float32(0.5), [0, 1])], [(0.2, 0.9, 62, np.float32(0.7), None)]]
+    good, bad = tmp_path / "a.mid", tmp_path / "no_such_dir" / "b.mid"
+    with pytest.raises(_lib.BpError):
+        nc.write_note_files(ev, [good, bad], None, n_threads=1)
+    assert good.exists() and not bad.exists()
+    nc.write_note_files([], [], [])  # an empty batch is fine
