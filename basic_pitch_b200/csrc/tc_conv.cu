@@ -403,14 +403,19 @@ __device__ __forceinline__ void store_split8(const float (&v)[8], __nv_bfloat16*
 __global__ void lognorm_split_kernel(const float* __restrict__ y, const unsigned int* __restrict__ minmax,
                                      const float* __restrict__ bn, __nv_bfloat16* __restrict__ dst, int n_windows,
                                      int rows_used, int rows_total /* stride */, int chunks8, int rows_per_window, int lead) {
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // one (row, q8) per thread
-  const long long total = (long long)rows_used * chunks8;
+  // one (row, pair of chunks q8, q8 + chunks8 / 2) per thread: the two 32-byte loads are independent (the kernel is bound by
+  // load latency, not bandwidth); rows fastest, so the 16-byte stores of a warp are contiguous
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int half = chunks8 / 2;  // chunks8 is even
+  const long long total = (long long)rows_used * half;
   if (idx >= total) return;
-  const int d = (int)(idx % rows_used);  // rows fastest: 16-byte stores of a warp are contiguous
-  const int q8 = (int)(idx / rows_used);
-  float v[8];
+  const int d = (int)(idx % rows_used);
+  const int qa = (int)(idx / rows_used);
+  float v[2][8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) v[j] = 0.f;
+  for (int h = 0; h < 2; ++h)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[h][j] = 0.f;
   const int m = d - lead;
   if (m >= 0) {
     const int b = m / rows_per_window, t = m - b * rows_per_window;
@@ -418,16 +423,28 @@ __global__ void lognorm_split_kernel(const float* __restrict__ y, const unsigned
       const float bn_scale = __ldg(bn), bn_bias = __ldg(bn + 1);
       const float mn = ordered_to_float(minmax[2 * b]);
       const float mx = __fsub_rn(ordered_to_float(minmax[2 * b + 1]), mn);
-      const float* p = y + ((size_t)b * kFrames + t) * kCqtBins + q8 * 8;
+      const float* p = y + ((size_t)b * kFrames + t) * kCqtBins;
+      float raw[2][8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
-        if (q8 * 8 + j < kCqtBins) {
-          const float q = (mx == 0.f) ? 0.f : __fdiv_rn(__fsub_rn(__ldg(p + j), mn), mx);
-          v[j] = __fadd_rn(__fmul_rn(q, bn_scale), bn_bias);
+      for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int bin = (qa + h * half) * 8 + j;
+          raw[h][j] = bin < kCqtBins ? __ldg(p + bin) : 0.f;
         }
+#pragma unroll
+      for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if ((qa + h * half) * 8 + j < kCqtBins) {
+            const float q = (mx == 0.f) ? 0.f : __fdiv_rn(__fsub_rn(raw[h][j], mn), mx);
+            v[h][j] = __fadd_rn(__fmul_rn(q, bn_scale), bn_bias);
+          }
     }
   }
-  store_split8(v, dst, ((size_t)q8 * rows_total + d) * 8, (size_t)chunks8 * rows_total * 8);
+  const size_t plane = (size_t)chunks8 * rows_total * 8;
+  store_split8(v[0], dst, ((size_t)qa * rows_total + d) * 8, plane);
+  store_split8(v[1], dst, ((size_t)(qa + half) * rows_total + d) * 8, plane);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1232,7 +1249,7 @@ int tc_setup() {
 void launch_lognorm_split(const float* y, const unsigned int* minmax, const float* bn, __nv_bfloat16* dst,
                           const TcConvSpec& sp, int n_windows, int rows_stride, cudaStream_t st) {
   const int rows_used = tc_rows_total(n_windows, sp.rows_per_window);  // <= rows_stride
-  const long long cells = (long long)rows_used * sp.chunks8;
+  const long long cells = (long long)rows_used * (sp.chunks8 / 2);  // a thread converts two chunks of a row
   lognorm_split_kernel<<<(unsigned)((cells + 255) / 256), 256, 0, st>>>(y, minmax, bn, dst, n_windows, rows_used, rows_stride,
                                                                        sp.chunks8, sp.rows_per_window, sp.lead_rows);
 }
