@@ -158,3 +158,38 @@ def test_dense_same_time_candidates_chain():
     pk = decode_ref.strict_time_peaks(onsets.astype(np.float64))
     got = parallel_decode(frames, pk & (onsets >= 0.5), 0.3, 11)
     assert got == [(a, b, p - 21) for a, b, p, _amp in exp]
+
+
+def test_block_maxima_track_the_column_argmax():
+    """decode_seq_kernel keeps, per pitch column, the maxima of 256-frame blocks (value + lowest frame) so that a melodia
+    iteration rescans only the blocks it changed and reduces T / 256 entries (csrc/decode.cu: refresh_column).  NumPy model of
+    that bookkeeping: after arbitrary range zeroings the reduced (max, first index) equals np.max / np.argmax of the
+    column, ties included (the reference takes the FIRST maximum, note_creation.py:449-452)."""
+    rng = np.random.default_rng(3)
+    BLK = 256
+    for T in (1, 255, 256, 257, 865, 4000):
+        col = np.round(rng.random(T) * 8) / 8  # coarse values: many exact ties
+        nblk = (T + BLK - 1) // BLK
+        bmax = np.full(nblk, -np.inf)
+        barg = np.zeros(nblk, np.int64)
+
+        def refresh(b_lo, b_hi):
+            for b in range(b_lo, b_hi + 1):
+                seg = col[b * BLK : min(T, (b + 1) * BLK)]
+                bmax[b] = seg.max()
+                barg[b] = b * BLK + int(np.argmax(seg))  # first maximum inside the block
+            best_v, best_t = -np.inf, 2**31 - 1
+            for b in range(nblk):  # ascending blocks, strict '>' keeps the lower block on ties
+                if bmax[b] > best_v:
+                    best_v, best_t = bmax[b], barg[b]
+            return best_v, best_t
+
+        v, t = refresh(0, nblk - 1)
+        assert v == col.max() and t == int(np.argmax(col))
+        for _ in range(60):
+            tm = int(rng.integers(0, T))
+            lo = max(0, tm - int(rng.integers(0, 40)))
+            hi = min(T - 1, tm + int(rng.integers(0, 40)))
+            col[lo : hi + 1] = 0.0
+            v, t = refresh(lo // BLK, hi // BLK)
+            assert v == col.max() and t == int(np.argmax(col)), (T, lo, hi)
